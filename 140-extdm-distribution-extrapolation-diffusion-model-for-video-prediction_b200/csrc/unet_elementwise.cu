@@ -1,0 +1,767 @@
+// Bandwidth-bound UNet kernels: normalisations, layout shuffles, the time-embedding MLP and the output heads.
+// Channels-last bf16 activations, fp32 arithmetic, 16-byte vector accesses, warp-shuffle reductions.
+#include "common.cuh"
+#include "../../include/extdm_b200.h"
+
+namespace extdm {
+
+constexpr int kGnChunks = EXTDM_GN_CHUNKS;
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+  uint4 t = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16(t.x), b = unpack_bf16(t.y), c = unpack_bf16(t.z), d = unpack_bf16(t.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 t;
+  t.x = pack_bf16(v[0], v[1]); t.y = pack_bf16(v[2], v[3]); t.z = pack_bf16(v[4], v[5]); t.w = pack_bf16(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = t;
+}
+
+// ------------------------------------------------------------------------------------------------ GroupNorm
+// Partial sums per (sample, chunk, group): deterministic (no atomics); the apply kernel folds the chunks.
+__global__ void __launch_bounds__(256) groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ x,
+                                                              float* __restrict__ part, long long P, int C, int G) {
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int vecs = C / 8;                  // vectors per pixel
+  const int cg8 = (C / G) / 8;             // vectors per group
+  const long long total = P * vecs;
+  const long long per = (total + gridDim.x - 1) / gridDim.x;
+  const long long begin = chunk * per;
+  const long long end = min(begin + per, total);
+  const __nv_bfloat16* xb = x + static_cast<long long>(b) * P * C;
+  __shared__ float s_sum[256], s_sq[256];
+  float sum = 0.f, sq = 0.f;
+  for (long long i = begin + threadIdx.x; i < end; i += blockDim.x) {
+    float v[8];
+    load8(xb + i * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sum += v[j]; sq += v[j] * v[j]; }
+  }
+  s_sum[threadIdx.x] = sum;
+  s_sq[threadIdx.x] = sq;
+  __syncthreads();
+  // blockDim (256) is a multiple of vecs, so thread t always touched vector slot (begin + t) % vecs -> one group.
+  // Fixed-order fold => bitwise reproducible statistics.
+  if (threadIdx.x < G) {
+    float a = 0.f, q = 0.f;
+    for (int t = 0; t < 256; ++t) {
+      const int slot = static_cast<int>((begin + t) % vecs);
+      if (slot / cg8 == static_cast<int>(threadIdx.x)) { a += s_sum[t]; q += s_sq[t]; }
+    }
+    float* o = part + ((static_cast<long long>(b) * kGnChunks + chunk) * G + threadIdx.x) * 2;
+    o[0] = a;
+    o[1] = q;
+  }
+}
+
+__global__ void __launch_bounds__(256) groupnorm_apply_kernel(
+    const __nv_bfloat16* __restrict__ x, const float* __restrict__ part, const float* __restrict__ gamma,
+    const float* __restrict__ beta, const float* __restrict__ ss, long long ss_stride, int ss_off,
+    const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ y, long long P, int C, int G, float eps) {
+  extern __shared__ float s_aff[];         // a[C], d[C]
+  float* s_a = s_aff;
+  float* s_d = s_aff + C;
+  __shared__ float s_mean[64], s_rstd[64];
+  const int b = blockIdx.y;
+  if (threadIdx.x < G) {
+    float sum = 0.f, sq = 0.f;
+    for (int c = 0; c < kGnChunks; ++c) {
+      const float* o = part + ((static_cast<long long>(b) * kGnChunks + c) * G + threadIdx.x) * 2;
+      sum += o[0];
+      sq += o[1];
+    }
+    const float cnt = static_cast<float>(P) * (C / G);
+    const float mean = sum / cnt;
+    const float var = fmaxf(sq / cnt - mean * mean, 0.f);
+    s_mean[threadIdx.x] = mean;
+    s_rstd[threadIdx.x] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / (C / G);
+    float a = s_rstd[g] * gamma[c];
+    float d = beta[c] - s_mean[g] * a;
+    if (ss) {
+      const float sc = ss[b * ss_stride + ss_off + c] + 1.0f;
+      const float sh = ss[b * ss_stride + ss_off + C + c];
+      a *= sc;
+      d = d * sc + sh;
+    }
+    s_a[c] = a;
+    s_d[c] = d;
+  }
+  __syncthreads();
+  const int vecs = C / 8;
+  const long long total = P * vecs;
+  const long long base = static_cast<long long>(b) * P * C;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c0 = static_cast<int>(i % vecs) * 8;
+    float v[8];
+    load8(x + base + i * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = silu(v[j] * s_a[c0 + j] + s_d[c0 + j]);
+    if (res) {
+      float r[8];
+      load8(res + base + i * 8, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += r[j];
+    }
+    store8(y + base + i * 8, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ channel LayerNorm
+// One warp per row; lane owns V consecutive channels of each source.
+template <int V>
+__device__ __forceinline__ void load_vec(const __nv_bfloat16* p, float (&v)[V]) {
+  if constexpr (V == 2) {
+    float2 a = unpack_bf16(*reinterpret_cast<const uint32_t*>(p));
+    v[0] = a.x; v[1] = a.y;
+  } else if constexpr (V == 4) {
+    uint2 t = *reinterpret_cast<const uint2*>(p);
+    float2 a = unpack_bf16(t.x), b = unpack_bf16(t.y);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  } else {
+#pragma unroll
+    for (int k = 0; k < V; k += 8) {
+      float t[8];
+      load8(p + k, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[k + j] = t[j];
+    }
+  }
+}
+template <int V>
+__device__ __forceinline__ void store_vec(__nv_bfloat16* p, const float (&v)[V]) {
+  if constexpr (V == 2) {
+    *reinterpret_cast<uint32_t*>(p) = pack_bf16(v[0], v[1]);
+  } else if constexpr (V == 4) {
+    uint2 t;
+    t.x = pack_bf16(v[0], v[1]); t.y = pack_bf16(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = t;
+  } else {
+#pragma unroll
+    for (int k = 0; k < V; k += 8) {
+      float t[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t[j] = v[k + j];
+      store8(p + k, t);
+    }
+  }
+}
+
+template <int V, bool DUAL>
+__global__ void __launch_bounds__(256) chan_layernorm_kernel(const __nv_bfloat16* __restrict__ x0, long long s0,
+                                                             const __nv_bfloat16* __restrict__ x1, long long s1,
+                                                             const float* __restrict__ gamma,
+                                                             __nv_bfloat16* __restrict__ y, long long n_outer,
+                                                             long long n_inner, float eps) {
+  constexpr int C0 = 32 * V;
+  constexpr int CT = DUAL ? 2 * C0 : C0;
+  const int lane = threadIdx.x & 31;
+  const long long rows = n_outer * n_inner;
+  for (long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; row < rows;
+       row += (static_cast<long long>(gridDim.x) * blockDim.x) >> 5) {
+    const long long outer = row / n_inner, inner = row % n_inner;
+    float a[V], b[V];
+    load_vec<V>(x0 + outer * s0 + inner * C0 + lane * V, a);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) sum += a[j];
+    if constexpr (DUAL) {
+      load_vec<V>(x1 + outer * s1 + inner * C0 + lane * V, b);
+#pragma unroll
+      for (int j = 0; j < V; ++j) sum += b[j];
+    }
+    const float mean = warp_sum(sum) * (1.0f / CT);
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) { const float d = a[j] - mean; sq += d * d; }
+    if constexpr (DUAL) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) { const float d = b[j] - mean; sq += d * d; }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) * (1.0f / CT) + eps);
+#pragma unroll
+    for (int j = 0; j < V; ++j) a[j] = (a[j] - mean) * rstd * __ldg(gamma + lane * V + j);
+    store_vec<V>(y + row * CT + lane * V, a);
+    if constexpr (DUAL) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) b[j] = (b[j] - mean) * rstd * __ldg(gamma + C0 + lane * V + j);
+      store_vec<V>(y + row * CT + C0 + lane * V, b);
+    }
+  }
+}
+
+// z = chanLN(x)*gamma ; u = LayerNorm(z)*w + b ; xz = x + z
+template <int V>
+__global__ void __launch_bounds__(256) temporal_prenorm_kernel(const __nv_bfloat16* __restrict__ x,
+                                                               const float* __restrict__ gamma,
+                                                               const float* __restrict__ lw,
+                                                               const float* __restrict__ lb,
+                                                               __nv_bfloat16* __restrict__ u,
+                                                               __nv_bfloat16* __restrict__ xz, long long rows,
+                                                               float eps) {
+  constexpr int C = 32 * V;
+  const int lane = threadIdx.x & 31;
+  for (long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; row < rows;
+       row += (static_cast<long long>(gridDim.x) * blockDim.x) >> 5) {
+    float a[V], z[V];
+    load_vec<V>(x + row * C + lane * V, a);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) sum += a[j];
+    float mean = warp_sum(sum) * (1.0f / C);
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) { const float d = a[j] - mean; sq += d * d; }
+    float rstd = rsqrtf(warp_sum(sq) * (1.0f / C) + eps);
+    sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      z[j] = (a[j] - mean) * rstd * __ldg(gamma + lane * V + j);
+      sum += z[j];
+      a[j] += z[j];
+    }
+    store_vec<V>(xz + row * C + lane * V, a);
+    mean = warp_sum(sum) * (1.0f / C);
+    sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) { const float d = z[j] - mean; sq += d * d; }
+    rstd = rsqrtf(warp_sum(sq) * (1.0f / C) + eps);
+#pragma unroll
+    for (int j = 0; j < V; ++j)
+      z[j] = (z[j] - mean) * rstd * __ldg(lw + lane * V + j) + __ldg(lb + lane * V + j);
+    store_vec<V>(u + row * C + lane * V, z);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ adaptor stats
+// partial (B, chunks, C, 2) of pivot-shifted sums; pivot = x[b, 0, 0, c].
+constexpr int kAdChunks = 32;
+__global__ void __launch_bounds__(256) adaptor_stats_kernel(const __nv_bfloat16* __restrict__ x, long long sstride,
+                                                            float* __restrict__ part, long long rows, int C) {
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int vecs = C / 8;
+  const int rows_per_pass = blockDim.x / vecs;
+  const int myvec = threadIdx.x % vecs, myrow = threadIdx.x / vecs;
+  const __nv_bfloat16* xb = x + b * sstride;
+  const long long per = (rows + gridDim.x - 1) / gridDim.x;
+  const long long begin = chunk * per, end = min(begin + per, rows);
+  float piv[8], sum[8], sq[8];
+  load8(xb + myvec * 8, piv);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sum[j] = 0.f; sq[j] = 0.f; }
+  for (long long r = begin + myrow; r < end; r += rows_per_pass) {
+    float v[8];
+    load8(xb + r * C + myvec * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float d = v[j] - piv[j]; sum[j] += d; sq[j] += d * d; }
+  }
+  extern __shared__ float s_red[];        // [rows_per_pass][C][2]
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s_red[(myrow * C + myvec * 8 + j) * 2] = sum[j];
+    s_red[(myrow * C + myvec * 8 + j) * 2 + 1] = sq[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, q = 0.f;
+    for (int r = 0; r < rows_per_pass; ++r) { a += s_red[(r * C + c) * 2]; q += s_red[(r * C + c) * 2 + 1]; }
+    float* o = part + ((static_cast<long long>(b) * kAdChunks + chunk) * C + c) * 2;
+    o[0] = a;
+    o[1] = q;
+  }
+}
+
+__global__ void __launch_bounds__(256) adaptor_normalize_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                long long sstride, const float* __restrict__ part,
+                                                                __nv_bfloat16* __restrict__ y,
+                                                                float* __restrict__ mean_std, int B, long long rows,
+                                                                int C, float eps) {
+  extern __shared__ float s_ms[];          // mean[C], inv_std[C]
+  const int b = blockIdx.y;
+  const __nv_bfloat16* xb = x + b * sstride;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, q = 0.f;
+    for (int k = 0; k < kAdChunks; ++k) {
+      const float* o = part + ((static_cast<long long>(b) * kAdChunks + k) * C + c) * 2;
+      a += o[0];
+      q += o[1];
+    }
+    const float n = static_cast<float>(rows);
+    const float piv = __bfloat162float(xb[c]);
+    const float dm = a / n;
+    const float var = fmaxf((q - n * dm * dm) / (n - 1.0f), 0.f);     // unbiased
+    const float sd = sqrtf(var + eps);
+    const float mean = piv + dm;
+    s_ms[c] = mean;
+    s_ms[C + c] = 1.0f / sd;
+    if (blockIdx.x == 0) {
+      mean_std[static_cast<long long>(b) * C + c] = mean;                              // plane 0: mean (B, C)
+      mean_std[static_cast<long long>(B) * C + static_cast<long long>(b) * C + c] = sd; // plane 1: std  (B, C)
+    }
+  }
+  __syncthreads();
+  const int vecs = C / 8;
+  const long long total = rows * vecs;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c0 = static_cast<int>(i % vecs) * 8;
+    float v[8];
+    load8(xb + i * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (v[j] - s_ms[c0 + j]) * s_ms[C + c0 + j];
+    store8(y + static_cast<long long>(b) * rows * C + i * 8, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ layout kernels
+__global__ void __launch_bounds__(256) space_to_depth_kernel(const __nv_bfloat16* __restrict__ x,
+                                                             __nv_bfloat16* __restrict__ z, long long F, int H, int W,
+                                                             int C) {
+  const int Ho = H / 2 + 1, Wo = W / 2 + 1, vecs = C / 8;
+  const long long total = F * Ho * Wo * 4 * vecs;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long r = i;
+    const int v = r % vecs; r /= vecs;
+    const int ph = r % 4; r /= 4;
+    const int xo = r % Wo; r /= Wo;
+    const int yo = r % Ho; r /= Ho;
+    const long long f = r;
+    const int yi = 2 * yo - 1 + (ph >> 1), xi = 2 * xo - 1 + (ph & 1);
+    uint4 t = make_uint4(0, 0, 0, 0);
+    if (yi >= 0 && yi < H && xi >= 0 && xi < W)
+      t = *reinterpret_cast<const uint4*>(x + ((f * H + yi) * W + xi) * C + v * 8);
+    *reinterpret_cast<uint4*>(z + i * 8) = t;
+  }
+}
+
+// one thread per (row, tap-pair): rows of 192 bf16 = 24 uint4; we build them 8 elements at a time
+__global__ void __launch_bounds__(256) im2col7_flow_kernel(const float* __restrict__ cond,
+                                                           const float* __restrict__ xin,
+                                                           __nv_bfloat16* __restrict__ a, int B, int tc, int tp,
+                                                           int t0, int nt, int H, int W) {
+  const long long rows = static_cast<long long>(B) * nt * H * W;
+  const long long total = rows * 24;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = i % 24;
+    long long r = i / 24;
+    const int xx = r % W; r /= W;
+    const int yy = r % H; r /= H;
+    const int t = t0 + static_cast<int>(r % nt);
+    const int b = static_cast<int>(r / nt);
+    const float* src;
+    long long cstride;
+    if (t < tc) {
+      src = cond + ((static_cast<long long>(b) * 3 * tc + t) * H) * W;
+      cstride = static_cast<long long>(tc) * H * W;
+    } else {
+      src = xin + ((static_cast<long long>(b) * 3 * tp + (t - tc)) * H) * W;
+      cstride = static_cast<long long>(tp) * H * W;
+    }
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = v * 8 + j;
+      float val = 0.f;
+      if (k < 147) {
+        const int tap = k / 3, c = k % 3;
+        const int y2 = yy + tap / 7 - 3, x2 = xx + tap % 7 - 3;
+        if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) val = __ldg(src + c * cstride + y2 * W + x2);
+      }
+      o[j] = val;
+    }
+    store8(a + i * 8, o);
+  }
+}
+
+__global__ void __launch_bounds__(256) im2col7_image_kernel(const float* __restrict__ img,
+                                                            __nv_bfloat16* __restrict__ a, long long F, int H, int W) {
+  const long long total = F * H * W * 24;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = i % 24;
+    long long r = i / 24;
+    const int xx = r % W; r /= W;
+    const int yy = r % H; r /= H;
+    const float* src = img + r * 3 * H * W;
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = v * 8 + j;
+      float val = 0.f;
+      if (k < 147) {
+        const int tap = k / 3, c = k % 3;
+        const int y2 = yy + tap / 7 - 3, x2 = xx + tap % 7 - 3;
+        if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) val = __ldg(src + (static_cast<long long>(c) * H + y2) * W + x2);
+      }
+      o[j] = val;
+    }
+    store8(a + i * 8, o);
+  }
+}
+
+// F.interpolate(mode='bilinear', align_corners=False) index math (ATen area_pixel_compute_source_index)
+__device__ __forceinline__ void bilinear_src(int dst, float scale, int in, int& i0, int& i1, float& l1) {
+  float s = scale * (dst + 0.5f) - 0.5f;
+  if (s < 0.f) s = 0.f;
+  i0 = static_cast<int>(s);
+  i1 = i0 + (i0 < in - 1 ? 1 : 0);
+  l1 = s - i0;
+}
+
+__global__ void __launch_bounds__(256) bilinear_resize_cl_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                 __nv_bfloat16* __restrict__ y, long long F, int h,
+                                                                 int w, int H, int W, int C) {
+  const int vecs = C / 8;
+  const float sy = static_cast<float>(h) / H, sx = static_cast<float>(w) / W;
+  const long long total = F * H * W * vecs;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long r = i;
+    const int v = r % vecs; r /= vecs;
+    const int X = r % W; r /= W;
+    const int Y = r % H; r /= H;
+    int y0, y1, x0, x1;
+    float ly, lx;
+    bilinear_src(Y, sy, h, y0, y1, ly);
+    bilinear_src(X, sx, w, x0, x1, lx);
+    const __nv_bfloat16* xf = x + r * h * w * C + v * 8;
+    float a[8], b[8], c[8], d[8], o[8];
+    load8(xf + (static_cast<long long>(y0) * w + x0) * C, a);
+    load8(xf + (static_cast<long long>(y0) * w + x1) * C, b);
+    load8(xf + (static_cast<long long>(y1) * w + x0) * C, c);
+    load8(xf + (static_cast<long long>(y1) * w + x1) * C, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      o[j] = (1.f - ly) * ((1.f - lx) * a[j] + lx * b[j]) + ly * ((1.f - lx) * c[j] + lx * d[j]);
+    store8(y + i * 8, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ time MLP
+__global__ void __launch_bounds__(256) time_mlp_kernel(const long long* __restrict__ time,
+                                                       const float* __restrict__ w1, const float* __restrict__ b1,
+                                                       const float* __restrict__ w2, const float* __restrict__ b2,
+                                                       const float* __restrict__ wss, const float* __restrict__ bss,
+                                                       float* __restrict__ out, int dim, int n_ss) {
+  extern __shared__ float s_t[];           // e[dim], h[4dim], st[4dim]
+  float* s_e = s_t;
+  float* s_h = s_t + dim;
+  float* s_s = s_h + 4 * dim;
+  const int b = blockIdx.x, td = 4 * dim, half = dim / 2;
+  const float t = static_cast<float>(time[b]);
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    const float f = expf(static_cast<float>(i) * -(logf(10000.0f) / (half - 1)));
+    s_e[i] = sinf(t * f);
+    s_e[half + i] = cosf(t * f);
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < td; r += blockDim.x) {
+    float acc = b1[r];
+    for (int k = 0; k < dim; ++k) acc += w1[r * dim + k] * s_e[k];
+    s_h[r] = 0.5f * acc * (1.0f + erff(acc * 0.70710678118654752440f));   // exact GELU
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < td; r += blockDim.x) {
+    float acc = b2[r];
+    for (int k = 0; k < td; ++k) acc += w2[r * td + k] * s_h[k];
+    s_s[r] = acc / (1.0f + expf(-acc));                                   // SiLU feeding every block's Linear
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int r = blockIdx.y * nw + warp; r < n_ss; r += gridDim.y * nw) {
+    float acc = 0.f;
+    for (int k = lane; k < td; k += 32) acc += wss[static_cast<long long>(r) * td + k] * s_s[k];
+    acc = warp_sum(acc);
+    if (lane == 0) out[static_cast<long long>(b) * n_ss + r] = acc + bss[r];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ output heads
+__global__ void __launch_bounds__(128) head_project_kernel(const __nv_bfloat16* __restrict__ hf,
+                                                           const __nv_bfloat16* __restrict__ ho,
+                                                           const float* __restrict__ wf, const float* __restrict__ bf,
+                                                           const float* __restrict__ wo, const float* __restrict__ bo,
+                                                           float* __restrict__ out, int B, int T, int t0, int HW,
+                                                           int C) {
+  extern __shared__ float s_w[];            // wf[2][C], wo[C]
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) s_w[i] = i < 2 * C ? wf[i] : wo[i - 2 * C];
+  __syncthreads();
+  const int nt = T - t0;
+  const long long total = static_cast<long long>(B) * nt * HW;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int p = i % HW;
+    const int t = (i / HW) % nt;
+    const int b = i / (static_cast<long long>(HW) * nt);
+    const long long row = (static_cast<long long>(b) * T + t0 + t) * HW + p;
+    float a0 = bf[0], a1 = bf[1], a2 = bo[0];
+    for (int c = 0; c < C; c += 8) {
+      float f[8], o[8];
+      load8(hf + row * C + c, f);
+      load8(ho + row * C + c, o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a0 += f[j] * s_w[c + j];
+        a1 += f[j] * s_w[C + c + j];
+        a2 += o[j] * s_w[2 * C + c + j];
+      }
+    }
+    const long long ob = ((static_cast<long long>(b) * 3) * nt + t) * HW + p;
+    out[ob] = a0;
+    out[ob + static_cast<long long>(nt) * HW] = a1;
+    out[ob + 2ll * nt * HW] = a2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LFAE helpers
+__global__ void __launch_bounds__(256) bn_relu_cl_kernel(const __nv_bfloat16* __restrict__ x,
+                                                         const float* __restrict__ scale,
+                                                         const float* __restrict__ shift,
+                                                         __nv_bfloat16* __restrict__ y, long long rows, int C) {
+  const int vecs = C / 8;
+  const long long total = rows * vecs;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c0 = static_cast<int>(i % vecs) * 8;
+    float v[8];
+    load8(x + i * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j] * __ldg(scale + c0 + j) + __ldg(shift + c0 + j), 0.f);
+    store8(y + i * 8, v);
+  }
+}
+
+__global__ void __launch_bounds__(256) avgpool2_cl_kernel(const __nv_bfloat16* __restrict__ x,
+                                                          __nv_bfloat16* __restrict__ y, long long F, int H, int W,
+                                                          int C) {
+  const int vecs = C / 8, Ho = H / 2, Wo = W / 2;
+  const long long total = F * Ho * Wo * vecs;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long r = i;
+    const int v = r % vecs; r /= vecs;
+    const int xo = r % Wo; r /= Wo;
+    const int yo = r % Ho; r /= Ho;
+    const __nv_bfloat16* p = x + ((r * H + 2 * yo) * W + 2 * xo) * C + v * 8;
+    float a[8], b[8], c[8], d[8], o[8];
+    load8(p, a);
+    load8(p + C, b);
+    load8(p + static_cast<long long>(W) * C, c);
+    load8(p + static_cast<long long>(W) * C + C, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (a[j] + b[j] + c[j] + d[j]) * 0.25f;
+    store8(y + i * 8, o);
+  }
+}
+
+__global__ void __launch_bounds__(256) ncthw_to_cl_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                          int B, int C, long long THW) {
+  const long long total = static_cast<long long>(B) * THW * C;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = i % C;
+    const long long p = (i / C) % THW;
+    const long long b = i / (static_cast<long long>(C) * THW);
+    y[i] = __float2bfloat16(x[(b * C + c) * THW + p]);
+  }
+}
+__global__ void __launch_bounds__(256) cl_to_ncthw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y,
+                                                          int B, int C, long long THW) {
+  const long long total = static_cast<long long>(B) * THW * C;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = i % THW;
+    const int c = (i / THW) % C;
+    const long long b = i / (static_cast<long long>(C) * THW);
+    y[i] = __bfloat162float(x[(b * THW + p) * C + c]);
+  }
+}
+
+static inline int grid_for(long long total, int threads, int cap = 148 * 16) {
+  long long g = (total + threads - 1) / threads;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return static_cast<int>(g);
+}
+
+}  // namespace extdm
+
+using namespace extdm;
+#define STREAM static_cast<cudaStream_t>(stream)
+#define BF(p) reinterpret_cast<const __nv_bfloat16*>(p)
+#define BFW(p) reinterpret_cast<__nv_bfloat16*>(p)
+
+static int bad_arg(const char* msg) {
+  extdm_set_error(msg, __FILE__, __LINE__);
+  return EXTDM_ERR_ARG;
+}
+
+extern "C" int extdm_groupnorm_stats(const void* x, float* part, int B, long long P, int C, int G, void* stream) {
+  if (C % (8 * G) || G > 64 || 256 % (C / 8)) return bad_arg("groupnorm_stats: need C % (8G) == 0, C/8 | 256");
+  dim3 grid(kGnChunks, B);
+  groupnorm_stats_kernel<<<grid, 256, 0, STREAM>>>(BF(x), part, P, C, G);
+  EXTDM_CHECK_LAUNCH();
+  return EXTDM_OK;
+}
+
+extern "C" int extdm_groupnorm_apply(const void* x, const float* part, const float* gamma, const float* beta,
+                                     const float* ss, long long ss_stride, int ss_off, const void* res, void* y,
+                                     int B, long long P, int C, int G, float eps, void* stream) {
+  if (C % (8 * G) || G > 64) return bad_arg("groupnorm_apply: need C % (8G) == 0");
+  long long per_sample = P * (C / 8);
+  int gx = grid_for(per_sample, 256, (148 * 8 + B - 1) / B);
+  dim3 grid(gx, B);
+  groupnorm_apply_kernel<<<grid, 256, 2 * C * sizeof(float), STREAM>>>(BF(x), part, gamma, beta, ss, ss_stride, ss_off,
+                                                                     BF(res), BFW(y), P, C, G, eps);
+  EXTDM_CHECK_LAUNCH();
+  return EXTDM_OK;
+}
+
+template <bool DUAL>
+static int launch_cln(int V, const void* x0, long long s0, const void* x1, long long s1, const float* gamma, void* y,
+                      long long n_outer, long long n_inner, float eps, cudaStream_t st) {
+  const long long rows = n_outer * n_inner;
+  const int grid = grid_for(rows * 32, 256);
+#define CLN(VV)                                                                                                    \
+  chan_layernorm_kernel<VV, DUAL><<<grid, 256, 0, st>>>(BF(x0), s0, BF(x1), s1, gamma, BFW(y), n_outer, n_inner, eps)
+  switch (V) {
+    case 2: CLN(2); break;
+    case 4: CLN(4); break;
+    case 8: CLN(8); break;
+    case 16: CLN(16); break;
+    case 32: CLN(32); break;
+    default: return bad_arg("chan_layernorm: C must be 64, 128, 256, 512 or 1024 per source");
+  }
+#undef CLN
+  EXTDM_CHECK_LAUNCH();
+  return EXTDM_OK;
+}
+
+extern "C" int extdm_chan_layernorm(const void* x0, long long x0_outer_stride, int C0, const void* x1,
+                                    long long x1_outer_stride, int C1, const float* gamma, void* y, long long n_outer,
+                                    long long n_inner, float eps, void* stream) {
+  if (C0 % 32) return bad_arg("chan_layernorm: C0 % 32");
+  if (x1) {
+    if (C1 != C0) return bad_arg("chan_layernorm: dual sources must have equal channel counts");
+    return launch_cln<true>(C0 / 32, x0, x0_outer_stride, x1, x1_outer_stride, gamma, y, n_outer, n_inner, eps, STREAM);
+  }
+  return launch_cln<false>(C0 / 32, x0, x0_outer_stride, nullptr, 0, gamma, y, n_outer, n_inner, eps, STREAM);
+}
+
+extern "C" int extdm_temporal_prenorm(const void* x, const float* gamma, const float* ln_w, const float* ln_b, void* u,
+                                      void* xz, long long rows, int C, float eps, void* stream) {
+  const int grid = grid_for(rows * 32, 256);
+#define TPN(VV) \
+  temporal_prenorm_kernel<VV><<<grid, 256, 0, STREAM>>>(BF(x), gamma, ln_w, ln_b, BFW(u), BFW(xz), rows, eps)
+  switch (C) {
+    case 64: TPN(2); break;
+    case 128: TPN(4); break;
+    case 256: TPN(8); break;
+    case 512: TPN(16); break;
+    default: return bad_arg("temporal_prenorm: C must be 64, 128, 256 or 512");
+  }
+#undef TPN
+  EXTDM_CHECK_LAUNCH();
+  return EXTDM_OK;
+}
+
+extern "C" long long extdm_adaptor_workspace_floats(int B, int C) {
+  return static_cast<long long>(B) * kAdChunks * C * 2;
+}
+
+extern "C" int extdm_adaptor_normalize(const void* x, long long x_sample_stride, void* y, float* mean_std,
+                                       float* workspace, int B, int n_frames, int HW, int C, float eps, void* stream) {
+  if (C % 8 || 256 % (C / 8) || C > 1024) return bad_arg("adaptor_normalize: C/8 must divide 256");
+  const long long rows = static_cast<long long>(n_frames) * HW;
+  const int rpp = 256 / (C / 8);
+  dim3 g1(kAdChunks, B);
+  adaptor_stats_kernel<<<g1, 256, rpp * C * 2 * sizeof(float), STREAM>>>(BF(x), x_sample_stride, workspace, rows, C);
+  EXTDM_CHECK_LAUNCH();
+  dim3 g2(grid_for(rows * (C / 8), 256, (148 * 8 + B - 1) / B), B);
+  adaptor_normalize_kernel<<<g2, 256, 2 * C * sizeof(float), STREAM>>>(BF(x), x_sample_stride, workspace, BFW(y),
+                                                                     mean_std, B, rows, C, eps);
+  EXTDM_CHECK_LAUNCH();
+  return EXTDM_OK;
+}
+
+extern "C" int extdm_space_to_depth(const void* x, void* z, long long F, int H, int W, int C, void* stream) {
+  if (C % 8 || H % 2 || W % 2) return bad_arg("space_to_depth: C % 8, even H and W");
+  const long long total = F * (H / 2 + 1) * (W / 2 + 1) * 4 * (C / 8);
+  space_to_depth_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(BF(x), BFW(z), F, H, W, C);
+  EXTDM_CHECK_LAUNCH();
+  return EXTDM_OK;
+}
+
+extern "C" int extdm_im2col7_flow(const float* cond, const float* x, void* a, int B, int tc, int tp, int t0, int nt,
+                                  int H, int W, void* stream) {
+  const long long total = static_cast<long long>(B) * nt * H * W * 24;
+  im2col7_flow_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(cond, x, BFW(a), B, tc, tp, t0, nt, H, W);
+  EXTDM_CHECK_LAUNCH();
+  return EXTDM_OK;
+}
+
+extern "C" int extdm_im2col7_image(const float* img, void* a, long long F, int H, int W, void* stream) {
+  im2col7_image_kernel<<<grid_for(F * H * W * 24, 256), 256, 0, STREAM>>>(img, BFW(a), F, H, W);
+  EXTDM_CHECK_LAUNCH();
+  return EXTDM_OK;
+}
+
+extern "C" int extdm_bilinear_resize_cl(const void* x, void* y, long long F, int h, int w, int H, int W, int C,
+                                        void* stream) {
+  if (C % 8) return bad_arg("bilinear_resize_cl: C % 8");
+  bilinear_resize_cl_kernel<<<grid_for(F * H * W * (C / 8), 256), 256, 0, STREAM>>>(BF(x), BFW(y), F, h, w, H, W, C);
+  EXTDM_CHECK_LAUNCH();
+  return EXTDM_OK;
+}
+
+extern "C" int extdm_time_mlp(const long long* time, const float* w1, const float* b1, const float* w2,
+                              const float* b2, const float* wss, const float* bss, float* out, int B, int dim,
+                              int n_ss, void* stream) {
+  dim3 grid(B, 8);
+  time_mlp_kernel<<<grid, 256, 9 * dim * sizeof(float), STREAM>>>(time, w1, b1, w2, b2, wss, bss, out, dim, n_ss);
+  EXTDM_CHECK_LAUNCH();
+  return EXTDM_OK;
+}
+
+extern "C" int extdm_head_project(const void* hf, const void* ho, const float* wf, const float* bf, const float* wo,
+                                  const float* bo, float* out, int B, int T, int t0, int HW, int C, void* stream) {
+  if (C % 8) return bad_arg("head_project: C % 8");
+  const long long total = static_cast<long long>(B) * (T - t0) * HW;
+  head_project_kernel<<<grid_for(total, 128), 128, 3 * C * sizeof(float), STREAM>>>(BF(hf), BF(ho), wf, bf, wo, bo, out,
+                                                                                  B, T, t0, HW, C);
+  EXTDM_CHECK_LAUNCH();
+  return EXTDM_OK;
+}
+
+extern "C" int extdm_bn_relu_cl(const void* x, const float* scale, const float* shift, void* y, long long rows, int C,
+                                void* stream) {
+  if (C % 8) return bad_arg("bn_relu_cl: C % 8");
+  bn_relu_cl_kernel<<<grid_for(rows * (C / 8), 256), 256, 0, STREAM>>>(BF(x), scale, shift, BFW(y), rows, C);
+  EXTDM_CHECK_LAUNCH();
+  return EXTDM_OK;
+}
+
+extern "C" int extdm_avgpool2_cl(const void* x, void* y, long long F, int H, int W, int C, void* stream) {
+  if (C % 8 || H % 2 || W % 2) return bad_arg("avgpool2_cl: C % 8, even H and W");
+  avgpool2_cl_kernel<<<grid_for(F * (H / 2) * (W / 2) * (C / 8), 256), 256, 0, STREAM>>>(BF(x), BFW(y), F, H, W, C);
+  EXTDM_CHECK_LAUNCH();
+  return EXTDM_OK;
+}
+
+extern "C" int extdm_ncthw_to_cl(const float* x, void* y, int B, int C, long long T, long long HW, void* stream) {
+  ncthw_to_cl_kernel<<<grid_for(static_cast<long long>(B) * C * T * HW, 256), 256, 0, STREAM>>>(x, BFW(y), B, C, T * HW);
+  EXTDM_CHECK_LAUNCH();
+  return EXTDM_OK;
+}
+extern "C" int extdm_cl_to_ncthw(const void* x, float* y, int B, int C, long long T, long long HW, void* stream) {
+  cl_to_ncthw_kernel<<<grid_for(static_cast<long long>(B) * C * T * HW, 256), 256, 0, STREAM>>>(BF(x), y, B, C, T * HW);
+  EXTDM_CHECK_LAUNCH();
+  return EXTDM_OK;
+}

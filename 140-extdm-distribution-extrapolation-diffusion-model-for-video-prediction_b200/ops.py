@@ -1,0 +1,337 @@
+"""Host-side launch helpers: torch tensors in, C-ABI calls out (include/extdm_b200.h).
+
+Every helper goes through a `Recorder`: in immediate mode the call is issued on the current CUDA
+stream; in record mode it is appended to a launch list that a model runner replays (and captures into a
+CUDA graph).  Nothing here computes with torch ops on the hot path -- torch only provides device memory.
+"""
+import ctypes as C
+
+import torch
+
+from . import lib as _lib
+
+BF16 = torch.bfloat16
+
+
+# ----------------------------------------------------------------------------- recorder
+class Recorder:
+    """Immediate or deferred issue of C-ABI launches (stream appended as the last argument)."""
+
+    def __init__(self, record=False):
+        self.record = record
+        self.steps = []          # (cfunc, args, name)
+        self.keep = []           # tensors / ctypes objects that must outlive the launch list
+
+    def emit(self, name, args, keep=()):
+        if self.record:
+            self.keep.extend(keep)
+            self.steps.append((getattr(_lib.load(), name), args, name))
+        else:
+            _lib.call(name, *args, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+
+    def run(self):
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        lib = _lib.load()
+        for fn, args, name in self.steps:
+            rc = fn(*args, stream)
+            if rc != 0:
+                raise _lib.ExtdmError(f"{name} failed ({rc}): {lib.extdm_last_error().decode()}")
+        _lib._launches += len(self.steps)
+
+    def __len__(self):
+        return len(self.steps)
+
+
+IMMEDIATE = Recorder(record=False)
+
+
+def _p(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _chk(t, dtype, name):
+    if t is None:
+        return
+    if not t.is_cuda or t.dtype != dtype or not t.is_contiguous():
+        raise ValueError(f"{name}: expected contiguous CUDA {dtype}, got {t.dtype} cuda={t.is_cuda} "
+                         f"contig={t.is_contiguous()}")
+
+
+# ----------------------------------------------------------------------------- weight packing (load time)
+def pack_conv_weight(w):
+    """(Cout, Cin, [1,] kh, kw) fp32 -> (Cout, kh*kw*Cin) bf16, K index = (ky*kw + kx)*Cin + ci."""
+    if w.dim() == 5:
+        w = w[:, :, 0]
+    co, ci, kh, kw = w.shape
+    return w.permute(0, 2, 3, 1).reshape(co, kh * kw * ci).to(BF16).contiguous()
+
+
+def pack_linear_weight(w):
+    return w.reshape(w.shape[0], -1).to(BF16).contiguous()
+
+
+def pack_downsample_weight(w):
+    """Conv3d (1,4,4)/s2/p1 weight (Cout, Cin, 1, 4, 4) -> 2x2 taps over the space-to-depth tensor:
+    K index = (a*2+b)*4Cin + (py*2+px)*Cin + ci with ky = 2a+py, kx = 2b+px."""
+    co, ci = w.shape[:2]
+    w = w[:, :, 0].reshape(co, ci, 2, 2, 2, 2)             # co ci a py b px
+    return w.permute(0, 2, 4, 3, 5, 1).reshape(co, 16 * ci).to(BF16).contiguous()
+
+
+# output phase py -> [(input offset dy, kernel index ky)] for ConvTranspose (k=4, s=2, p=1): o = 2i - 1 + k
+_UP_TAPS = {0: [(0, 1), (-1, 3)], 1: [(1, 0), (0, 2)]}
+
+
+def pack_upsample_weight(w):
+    """ConvTranspose3d weight (Cin, Cout, 1, 4, 4) -> 4 phase matrices (Cout, 4*Cin) bf16 + tap offsets."""
+    ci, co = w.shape[:2]
+    w = w[:, :, 0]
+    out = {}
+    for py in (0, 1):
+        for px in (0, 1):
+            mats, taps = [], []
+            for dy, ky in _UP_TAPS[py]:
+                for dx, kx in _UP_TAPS[px]:
+                    mats.append(w[:, :, ky, kx].t())       # (co, ci)
+                    taps.append((dx, dy, 0))
+            out[(py, px)] = (torch.cat(mats, dim=1).to(BF16).contiguous(), taps)
+    return out
+
+
+def conv_taps(k):
+    return [(kx - k // 2, ky - k // 2, 0) for ky in range(k) for kx in range(k)]
+
+
+def std_box(H, W):
+    """128-row tile as (bw, bh, bt) pixels."""
+    bw = min(W, 128)
+    bh = min(H, 128 // bw)
+    bt = 128 // (bw * bh)
+    return bw, bh, bt
+
+
+# ----------------------------------------------------------------------------- GEMM
+def gemm(rec, *, a0, c0, dims, strides0, box, start, count, taps, w, n, out, out_stride, out_base=0,
+         a1=None, c1=0, strides1=None, out_fp32=False, col_group=None, col_group_stride=0, bias=None,
+         res=None, res_fp32=False, res_base=0, res_stride=None, col_scale=None, col_shift=None, act=0,
+         block_n=0):
+    """Generic launch of extdm_conv_gemm.  dims/strides: extents and element strides of D1..D4 of the A
+    tensor(s); box/start/count: tile geometry; taps: list of (o1,o2,o3)."""
+    g = _lib.ExtdmGemm()
+    g.a0 = a0.data_ptr()
+    g.a1 = 0 if a1 is None else a1.data_ptr()
+    g.a0_channels, g.a1_channels = c0, (c1 if a1 is not None else 0)
+    for i in range(4):
+        g.a0_dim[i], g.a0_stride[i] = dims[i], strides0[i]
+        g.a1_dim[i] = dims[i]
+        g.a1_stride[i] = (strides1 or strides0)[i]
+        g.box[i], g.start[i], g.count[i] = box[i], start[i], count[i]
+        g.out_stride[i] = out_stride[i]
+        g.res_stride[i] = (res_stride or out_stride)[i]
+    g.ntaps = len(taps)
+    for i, t in enumerate(taps):
+        g.tap[i][0], g.tap[i][1], g.tap[i][2], g.tap[i][3] = t[0], t[1], t[2], 0
+    _chk(w, BF16, "gemm weight")
+    if w.shape[1] != len(taps) * (c0 + (c1 if a1 is not None else 0)):
+        raise ValueError(f"gemm: weight K {w.shape[1]} != taps*channels {len(taps)}*{c0}+{c1}")
+    g.w, g.n, g.w_rows = w.data_ptr(), n, w.shape[0]
+    g.out, g.out_fp32, g.out_base = out.data_ptr(), int(out_fp32), out_base
+    g.col_group = col_group if col_group else max(n, 1)
+    g.col_group_stride = col_group_stride
+    g.bias = 0 if bias is None else bias.data_ptr()
+    g.res = 0 if res is None else res.data_ptr()
+    g.res_fp32, g.res_base = int(res_fp32), res_base
+    g.col_scale = 0 if col_scale is None else col_scale.data_ptr()
+    g.col_shift = 0 if col_shift is None else col_shift.data_ptr()
+    g.act, g.block_n = act, block_n
+    rec.emit("extdm_conv_gemm", (C.byref(g),), keep=(g, a0, a1, w, out, bias, res, col_scale, col_shift))
+
+
+def linear_rows(rec, x, w, n, out, *, bias=None, res=None, res_fp32=False, act=0, out_fp32=False, x2=None,
+                block_n=0):
+    """out[r, :n] = x[r, :] @ w.T (+bias, +res, act) for dense row-major x (rows, C) [+ x2 (rows, C2)]."""
+    rows, c0 = x.numel() // x.shape[-1], x.shape[-1]
+    c1 = 0 if x2 is None else x2.shape[-1]
+    ld_out = out.shape[-1]
+    gemm(rec, a0=x, c0=c0, a1=x2, c1=c1, dims=(rows, 1, 1, 1), strides0=(c0, rows * c0, rows * c0, rows * c0),
+         strides1=None if x2 is None else (c1, rows * c1, rows * c1, rows * c1),
+         box=(128, 1, 1, 1), start=(0, 0, 0, 0), count=(rows, 1, 1, 1), taps=[(0, 0, 0)], w=w, n=n, out=out,
+         out_stride=(ld_out, 0, 0, 0), out_fp32=out_fp32, bias=bias, res=res, res_fp32=res_fp32,
+         res_stride=None if res is None else (res.shape[-1], 0, 0, 0), act=act, block_n=block_n)
+
+
+def conv_cl(rec, x, w, n, k, out, *, x2=None, bias=None, res=None, res_fp32=False, act=0, out_fp32=False,
+            t_range=None, col_scale=None, col_shift=None, out_t_offset=0, res_t_offset=0, taps=None,
+            out_scale=1, out_phase=(0, 0), block_n=0):
+    """k x k 'same' convolution over channels-last x (B, T, H, W, C) [channel-concatenated with x2].
+    out: (B, To, Ho, Wo, n') with n' >= n.  t_range=(t0, t1) restricts the frames computed; the output
+    frame index is t + out_t_offset.  out_scale/out_phase write a strided output (ConvTranspose phases)."""
+    B, T, H, W, c0 = x.shape
+    c1 = 0 if x2 is None else x2.shape[-1]
+    bw, bh, bt = std_box(H, W)
+    t0, t1 = t_range if t_range else (0, T)
+    oB, oT, oH, oW, oC = out.shape
+    s = out_scale
+    ostr = (s * oC, s * oW * oC, oH * oW * oC, oT * oH * oW * oC)
+    obase = out_t_offset * oH * oW * oC + (out_phase[0] * oW + out_phase[1]) * oC
+    rstr, rbase = None, 0
+    if res is not None:
+        rB, rT, rH, rW, rC = res.shape
+        rstr = (rC, rW * rC, rH * rW * rC, rT * rH * rW * rC)
+        rbase = res_t_offset * rH * rW * rC
+    gemm(rec, a0=x, c0=c0, a1=x2, c1=c1, dims=(W, H, T, B),
+         strides0=(c0, W * c0, H * W * c0, T * H * W * c0),
+         strides1=None if x2 is None else (c1, W * c1, H * W * c1, x2.shape[1] * H * W * c1),
+         box=(bw, bh, bt, 1), start=(0, 0, t0, 0), count=(W, H, t1 - t0, B),
+         taps=taps if taps is not None else conv_taps(k), w=w, n=n, out=out, out_stride=ostr, out_base=obase,
+         out_fp32=out_fp32, bias=bias, res=res, res_fp32=res_fp32, res_base=rbase, res_stride=rstr,
+         col_scale=col_scale, col_shift=col_shift, act=act, block_n=block_n)
+
+
+# ----------------------------------------------------------------------------- normalisation etc.
+def groupnorm_silu(rec, x, stats_ws, gamma, beta, y, *, groups=8, scale_shift=None, ss_off=0, res=None, eps=1e-5):
+    """x, y, res: (B, P..., C) bf16 channels-last.  stats_ws: float32 workspace >= B*32*groups*2."""
+    B, Cc = x.shape[0], x.shape[-1]
+    P = x.numel() // (B * Cc)
+    rec.emit("extdm_groupnorm_stats", (_p(x), _p(stats_ws), B, P, Cc, groups), keep=(x, stats_ws))
+    ss_stride = 0 if scale_shift is None else scale_shift.shape[1]
+    rec.emit("extdm_groupnorm_apply", (_p(x), _p(stats_ws), _p(gamma), _p(beta), _p(scale_shift), ss_stride, ss_off,
+                                       _p(res), _p(y), B, P, Cc, groups, C.c_float(eps)),
+             keep=(x, gamma, beta, scale_shift, res, y))
+
+
+def chan_layernorm(rec, x, gamma, y, *, x2=None, t_range=None, eps=1e-5):
+    """Channel LayerNorm of x (B, T, H, W, C) [cat x2 on channels] over frames t_range -> dense y."""
+    B, T, H, W, Cc = x.shape
+    t0, t1 = t_range if t_range else (0, T)
+    hw = H * W
+    n_inner = (t1 - t0) * hw
+    x0p = C.c_void_p(x.data_ptr() + t0 * hw * Cc * 2)
+    if x2 is not None:
+        T2, C2 = x2.shape[1], x2.shape[-1]
+        x1p = C.c_void_p(x2.data_ptr())
+        s1 = T2 * hw * C2
+    else:
+        x1p, s1, C2 = C.c_void_p(0), 0, 0
+    rec.emit("extdm_chan_layernorm", (x0p, T * hw * Cc, Cc, x1p, s1, C2, _p(gamma), _p(y), B, n_inner,
+                                      C.c_float(eps)), keep=(x, x2, gamma, y))
+
+
+def temporal_prenorm(rec, x, gamma, ln_w, ln_b, u, xz, eps=1e-5):
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    rec.emit("extdm_temporal_prenorm", (_p(x), _p(gamma), _p(ln_w), _p(ln_b), _p(u), _p(xz), rows, Cc,
+                                        C.c_float(eps)), keep=(x, gamma, ln_w, ln_b, u, xz))
+
+
+def adaptor_workspace(B, Cc, device):
+    n = _lib.load().extdm_adaptor_workspace_floats(B, Cc)
+    return torch.empty(n, dtype=torch.float32, device=device)
+
+
+def adaptor_normalize(rec, x, n_frames, y, mean_std, ws, eps=1e-5):
+    """x: (B, Ttot, H, W, C); stats over frames [0, n_frames); y: (B, n_frames, H, W, C); mean_std (2, B, C)."""
+    B, Tt, H, W, Cc = x.shape
+    rec.emit("extdm_adaptor_normalize", (_p(x), Tt * H * W * Cc, _p(y), _p(mean_std), _p(ws), B, n_frames, H * W, Cc,
+                                         C.c_float(eps)), keep=(x, y, mean_std, ws))
+
+
+def space_to_depth(rec, x, z):
+    B, T, H, W, Cc = x.shape
+    rec.emit("extdm_space_to_depth", (_p(x), _p(z), B * T, H, W, Cc), keep=(x, z))
+
+
+def im2col7_flow(rec, cond, x, a, t0, nt):
+    B, _, tc, H, W = cond.shape
+    tp = x.shape[2]
+    rec.emit("extdm_im2col7_flow", (_p(cond), _p(x), _p(a), B, tc, tp, t0, nt, H, W), keep=(cond, x, a))
+
+
+def bilinear_resize_cl(rec, x, y):
+    h, w, Cc = x.shape[-3:]
+    H, W = y.shape[-3:-1]
+    F = x.numel() // (h * w * Cc)
+    rec.emit("extdm_bilinear_resize_cl", (_p(x), _p(y), F, h, w, H, W, Cc), keep=(x, y))
+
+
+def time_mlp(rec, time, w1, b1, w2, b2, wss, bss, out, dim):
+    rec.emit("extdm_time_mlp", (_p(time), _p(w1), _p(b1), _p(w2), _p(b2), _p(wss), _p(bss), _p(out), time.shape[0],
+                                dim, wss.shape[0]), keep=(time, w1, b1, w2, b2, wss, bss, out))
+
+
+def head_project(rec, hf, ho, wf, bf, wo, bo, out, t0):
+    B, T, H, W, Cc = hf.shape
+    rec.emit("extdm_head_project", (_p(hf), _p(ho), _p(wf), _p(bf), _p(wo), _p(bo), _p(out), B, T, t0, H * W, Cc),
+             keep=(hf, ho, wf, bf, wo, bo, out))
+
+
+def window_attention(rec, qkv, out, bias_table, rcos, rsin, heads, dh, window, shift):
+    B, T, H, W, _ = qkv.shape
+    rec.emit("extdm_window_attention", (_p(qkv), _p(out), _p(bias_table), _p(rcos), _p(rsin), B, T, H, W, heads, dh,
+                                        window[0], window[1], window[2], shift[0], shift[1], shift[2]),
+             keep=(qkv, out, bias_table, rcos, rsin))
+
+
+def temporal_attention(rec, qkv, out, rel_bias, rcos, rsin, heads, dh):
+    B, T, H, W, _ = qkv.shape
+    rec.emit("extdm_temporal_attention", (_p(qkv), _p(out), _p(rel_bias), _p(rcos), _p(rsin), B, T, H * W, heads, dh),
+             keep=(qkv, out, rel_bias, rcos, rsin))
+
+
+# ----------------------------------------------------------------------------- sampler
+def ddim_threshold(rec, img, pred, c_recip, c_recipm1, q, s):
+    B = img.shape[0]
+    rec.emit("extdm_ddim_threshold", (_p(img), _p(pred), C.c_float(c_recip), C.c_float(c_recipm1), C.c_float(q),
+                                      _p(s), B, img.numel() // B), keep=(img, pred, s))
+
+
+def ddim_update(rec, img, pred, noise, s, c_recip, c_recipm1, sqrt_alpha_next, c, sigma, img_out, x_start_out=None):
+    B = img.shape[0]
+    rec.emit("extdm_ddim_update", (_p(img), _p(pred), _p(noise), _p(s), C.c_float(c_recip), C.c_float(c_recipm1),
+                                   C.c_float(sqrt_alpha_next), C.c_float(c), C.c_float(sigma), _p(img_out),
+                                   _p(x_start_out), B, img.numel() // B),
+             keep=(img, pred, noise, s, img_out, x_start_out))
+
+
+# ----------------------------------------------------------------------------- LFAE decode
+def warp_blend_cl(rec, skip, prev, flow, occ, out, up2=False):
+    """skip (Fs,H,W,C) bf16, prev (F,H,W,C) or None, flow (F,h,w,2) fp32, occ (F,1,h,w) fp32 or None."""
+    Fs, H, W, Cc = skip.shape
+    F, h, w = flow.shape[:3]
+    rec.emit("extdm_warp_blend_cl", (_p(skip), _p(prev), _p(flow), _p(occ), _p(out), F, Fs, H, W, Cc, h, w, int(up2)),
+             keep=(skip, prev, flow, occ, out))
+
+
+def warp_image(rec, src, dec, flow, occ, prediction, deformed):
+    Fs, _, H, W = src.shape
+    F, h, w = flow.shape[:3]
+    dstride = 0 if dec is None else dec.shape[-1]
+    rec.emit("extdm_warp_image", (_p(src), _p(dec), dstride, _p(flow), _p(occ), _p(prediction), _p(deformed), F, Fs,
+                                  H, W, h, w), keep=(src, dec, flow, occ, prediction, deformed))
+
+
+def bn_relu_cl(rec, x, scale, shift, y):
+    Cc = x.shape[-1]
+    rec.emit("extdm_bn_relu_cl", (_p(x), _p(scale), _p(shift), _p(y), x.numel() // Cc, Cc), keep=(x, scale, shift, y))
+
+
+def avgpool2_cl(rec, x, y):
+    F, H, W, Cc = x.shape
+    rec.emit("extdm_avgpool2_cl", (_p(x), _p(y), F, H, W, Cc), keep=(x, y))
+
+
+def im2col7_image(rec, img, a):
+    F, _, H, W = img.shape
+    rec.emit("extdm_im2col7_image", (_p(img), _p(a), F, H, W), keep=(img, a))
+
+
+def ncthw_to_cl(rec, x, y):
+    B, Cc = x.shape[:2]
+    rest = x.numel() // (B * Cc)
+    rec.emit("extdm_ncthw_to_cl", (_p(x), _p(y), B, Cc, rest, 1), keep=(x, y))
+
+
+def cl_to_ncthw(rec, x, y):
+    B, Cc = y.shape[:2]
+    rest = y.numel() // (B * Cc)
+    rec.emit("extdm_cl_to_ncthw", (_p(x), _p(y), B, Cc, rest, 1), keep=(x, y))

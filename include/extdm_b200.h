@@ -1,0 +1,207 @@
+/* extdm_b200.h -- C ABI of the B200-native ExtDM sampling hot path.
+ *
+ * The reference (/root/reference) is pure Python/PyTorch: it has no FFI, plugin or operator boundary
+ * (SURVEY.md section 8b).  Each entry point below therefore names the reference *call site* whose library
+ * kernels it replaces (file:line, relative to the reference root).  All pointers are device pointers
+ * unless stated otherwise, all sizes are element counts, `stream` is a cudaStream_t passed as void*.
+ * Every function returns 0 on success; on failure extdm_last_error() holds a message.
+ * No function allocates device memory: the host (Python/torch) owns every buffer.
+ *
+ * Activation layout used by every UNet kernel: channels-last bf16, (B, T, H, W, C).
+ * Sampler / warp kernels keep the reference's fp32 NCTHW / NCHW tensors.
+ */
+#ifndef EXTDM_B200_H
+#define EXTDM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* extdm_last_error(void);
+int extdm_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution / linear layer on tcgen05 tensor cores (bf16 x bf16 -> fp32 in TMEM).
+ * Replaces nn.Conv3d (1,k,k) / nn.Conv2d / nn.Linear / ConvTranspose3d / Conv2d-on-(T C) call sites:
+ *   model/BaseDM_adaptor/DenoiseNet_STWAtt_w_wo_ref_adaptor_cross_multi.py:166 (Block.proj), :192 (res_conv),
+ *   :125-136 (Up/Downsample), :267-268 (to_qkv/to_out), :454-456 (qkv/proj), :662-666,704-705 (adaptor),
+ *   :803 (init_conv); ..._traj_ada.py:916 (init_noise_conv); model/LFAE/util.py:76-79,102,121,141 (LFAE convs).
+ *
+ * The A operand is a 5-D channels-last tensor (C, D1, D2, D3, D4), optionally the channel-concatenation
+ * of two tensors (skip connections are never materialised).  One CTA computes a 128-row tile
+ * box[0]*box[1]*box[2]*box[3] == 128 positions of (D1..D4) x BLOCK_N output columns; for every tap the
+ * tile is fetched by TMA at (coord + tap offset), out-of-range positions read as zero (= zero padding).
+ * W is [w_rows][ntaps * (a0_channels + a1_channels)] bf16, K-major, K index = tap*(C0+C1) + c.
+ * Epilogue: v = acc + bias[n]; v += res; v = v*col_scale[d4][n] + col_shift[d4][n]; act; store.
+ * Output element address: out_base + sum_k coord_k*out_stride[k] + (n / col_group)*col_group_stride
+ * + n % col_group   (same for `res` with res_base / res_stride).
+ */
+typedef struct ExtdmGemm {
+  const void* a0;
+  const void* a1;
+  int a0_channels;
+  int a1_channels;
+  long long a0_dim[4];
+  long long a0_stride[4]; /* elements */
+  long long a1_dim[4];
+  long long a1_stride[4];
+  int box[4];
+  int start[4];
+  int count[4];
+  int ntaps;
+  signed char tap[64][4];
+  const void* w;
+  int n;
+  int w_rows;
+  void* out;
+  int out_fp32;
+  long long out_base;
+  long long out_stride[4];
+  int col_group;
+  long long col_group_stride;
+  const float* bias;
+  const void* res;
+  int res_fp32;
+  long long res_base;
+  long long res_stride[4];
+  const float* col_scale;
+  const float* col_shift;
+  int act; /* 0 none, 1 relu, 2 silu, 3 sigmoid */
+  int block_n; /* 0 = choose automatically (16/64/128/256) */
+} ExtdmGemm;
+
+int extdm_conv_gemm(const ExtdmGemm* g, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Bandwidth-bound UNet kernels (channels-last bf16 activations, fp32 statistics).
+ */
+
+/* GroupNorm statistics: per (sample, group) sum and sum of squares over (T,H,W,C/G), as EXTDM_GN_CHUNKS
+ * deterministic partial sums.  x: (B, P, C) bf16 with P = T*H*W.  stats: (B, EXTDM_GN_CHUNKS, G, 2) fp32.
+ * Reference: nn.GroupNorm in Block.forward, ...cross_multi.py:166-171. */
+#define EXTDM_GN_CHUNKS 32
+int extdm_groupnorm_stats(const void* x, float* stats, int B, long long P, int C, int G, void* stream);
+
+/* GroupNorm apply + optional (scale+1, shift) + SiLU (+ residual).  ...cross_multi.py:170-178, :203.
+ * y = silu(gn(x)*gamma+beta [* (scale[b,c]+1) + shift[b,c]]) [+ res].  scale_shift: (B, ss_stride) fp32 rows,
+ * scale at [ss_off + c], shift at [ss_off + C + c]; may be NULL.  x, res, y: (B, P, C) bf16; in-place allowed. */
+int extdm_groupnorm_apply(const void* x, const float* stats, const float* gamma, const float* beta,
+                          const float* scale_shift, long long ss_stride, int ss_off, const void* res, void* y,
+                          int B, long long P, int C, int G, float eps, void* stream);
+
+/* Channel LayerNorm (gamma only, biased variance, eps) over the last dim of up to two concatenated
+ * sources: y[row, :C0+C1] = LN(cat(x0[row], x1[row])) * gamma.  ...cross_multi.py:139-148.
+ * Rows are (outer, inner) pairs: source row address = outer*x_outer_stride + inner*C (elements), which
+ * lets a caller normalise only frames [t0,t1) of each sample.  y is dense (rows, C0+C1) bf16. */
+int extdm_chan_layernorm(const void* x0, long long x0_outer_stride, int C0, const void* x1,
+                         long long x1_outer_stride, int C1, const float* gamma, void* y, long long n_outer,
+                         long long n_inner, float eps, void* stream);
+
+/* Temporal-attention prologue (...cross_multi.py:307-328 with PreNorm :151-159): z = chanLN(x)*gamma;
+ * u = LayerNorm(z)*w + b; xz = x + z.   x, u, xz: (rows, C) bf16. */
+int extdm_temporal_prenorm(const void* x, const float* gamma, const float* ln_w, const float* ln_b, void* u,
+                           void* xz, long long rows, int C, float eps, void* stream);
+
+/* Per-(sample, channel) mean and unbiased std over frames [0, n_frames) x (H*W): adaptor.calc_mean_std,
+ * ..._traj_ada.py:671-679, then normalise: y = (x - mean)/std (bf16).  x: (B, frames_total, HW, C) with sample
+ * stride x_sample_stride.  mean_std: (2, B, C) fp32 = plane 0 mean, plane 1 std (the planes feed the GEMM
+ * epilogue's col_shift / col_scale).  y: dense (B, n_frames, HW, C).
+ * workspace: extdm_adaptor_workspace_floats(B, C) floats. */
+long long extdm_adaptor_workspace_floats(int B, int C);
+int extdm_adaptor_normalize(const void* x, long long x_sample_stride, void* y, float* mean_std, float* workspace,
+                            int B, int n_frames, int HW, int C, float eps, void* stream);
+
+/* Space-to-depth for the (1,4,4)/stride-2/pad-1 Downsample conv (...cross_multi.py:134-136):
+ * z[f, y', x', (py*2+px)*C + c] = x[f, 2y'-1+py, 2x'-1+px, c] (zero outside), y' in [0,H/2], x' in [0,W/2]. */
+int extdm_space_to_depth(const void* x, void* z, long long F, int H, int W, int C, void* stream);
+
+/* im2col for the two 3-channel 7x7 convolutions whose input is the fp32 flow/occlusion volume
+ * (init_noise_conv ..._traj_ada.py:916,1032 and the flow half of the base init_conv ...cross_multi.py:803):
+ * a[(b*nt + t)*H*W + p, (ky*7+kx)*3 + c] = src(b, c, t0 + t, y+ky-3, x+kx-3), K padded to 192 with zeros.
+ * Frames t < tc come from cond (B,3,tc,H,W), the rest from x (B,3,tp,H,W); both fp32 NCTHW. */
+int extdm_im2col7_flow(const float* cond, const float* x, void* a, int B, int tc, int tp, int t0, int nt, int H,
+                       int W, void* stream);
+
+/* Bilinear resize (align_corners=False) of channels-last frames: F.interpolate in ..._traj_ada.py:1039-1041. */
+int extdm_bilinear_resize_cl(const void* x, void* y, long long F, int h, int w, int H, int W, int C, void* stream);
+
+/* Sinusoidal embedding + time_mlp + every ResnetBlock's SiLU->Linear in one launch
+ * (...cross_multi.py:110-122, 812-817, 184-199).  time: (B,) int64.  w1 (4d, d), w2 (4d, 4d) fp32;
+ * wss: (n_ss, 4d) fp32 = all blocks' mlp.1.weight stacked, bss (n_ss).  out: (B, n_ss) fp32. */
+int extdm_time_mlp(const long long* time, const float* w1, const float* b1, const float* w2, const float* b2,
+                   const float* wss, const float* bss, float* out, int B, int dim, int n_ss, void* stream);
+
+/* Final 1x1 projections of the two heads (final_conv[1], occlusion_map[1]; ...cross_multi.py:875-892) on
+ * frames [t0, T): out (B, 3, T-t0, H, W) fp32 NCTHW; hf / ho: (B, T, HW, C) bf16 head features. */
+int extdm_head_project(const void* hf, const void* ho, const float* wf, const float* bf, const float* wo,
+                       const float* bo, float* out, int B, int T, int t0, int HW, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Attention.  qkv: channels-last bf16 with channel = which*heads*dh + head*dh + d (which in q,k,v).
+ */
+
+/* 3-D shifted-window attention core (WindowAttention3D + window_partition/roll/mask/reverse,
+ * ...cross_multi.py:345-390, 462-497, 522-560).  qkv: (B, T, H, W, 3*heads*dh); out: (B, T, H, W, heads*dh).
+ * Window (wd, wh, ww) tokens = 32 or 64; T is zero-padded to a multiple of wd; shift (sd, sh, sw).
+ * bias_table: ((2wd-1)(2wh-1)(2ww-1), heads) fp32; rope_cos/sin: (tokens, dh/2) fp32. */
+int extdm_window_attention(const void* qkv, void* out, const float* bias_table, const float* rope_cos,
+                           const float* rope_sin, int B, int T, int H, int W, int heads, int dh, int wd, int wh,
+                           int ww, int sd, int sh, int sw, void* stream);
+
+/* Temporal attention core (Attention.forward ...cross_multi.py:269-302): sequence = T frames of one pixel.
+ * qkv: (B, T, HW, 3*heads*dh); out: (B, T, HW, heads*dh); rel_bias: (heads, 2T-1) fp32 indexed by (j-i+T-1). */
+int extdm_temporal_attention(const void* qkv, void* out, const float* rel_bias, const float* rope_cos,
+                             const float* rope_sin, int B, int T, int HW, int heads, int dh, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * DDIM sampler (GaussianDiffusion.ddim_sample, model/BaseDM_adaptor/Diffusion.py:231-255), fp32.
+ */
+
+/* x_start = c_recip*img - c_recipm1*pred; s[b] = max(1, quantile_0.9(|x_start[b]|)) with torch.quantile's
+ * fp32 linear interpolation (exact order statistics by radix select).  n = elements per sample. */
+int extdm_ddim_threshold(const float* img, const float* pred, float c_recip, float c_recipm1, float q, float* s,
+                         int B, int n, void* stream);
+/* img_out = clamp(x_start, -s, s)/s * sqrt_alpha_next + c*pred + sigma*noise (noise may be NULL). */
+int extdm_ddim_update(const float* img, const float* pred, const float* noise, const float* s, float c_recip,
+                      float c_recipm1, float sqrt_alpha_next, float c, float sigma, float* img_out,
+                      float* x_start_out, int B, int n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LFAE decode (Generator.forward_with_flow / deform_input / apply_optical, model/LFAE/generator.py:63-93,
+ * 152-206).  flow: (F, h, w, 2) fp32 normalised (x, y); occ: (F, 1, h, w) fp32 or NULL.
+ */
+
+/* out[f, y, x, c] = warp(skip)[..] * occ + prev * (1 - occ) on channels-last bf16 features.
+ * skip: (Fs, H, W, C) with Fs == F or F % Fs == 0 (skip of frame f is skip[f / (F/Fs)]: the encoder runs once
+ * per video); prev: (F, H, W, C) or NULL; flow/occ are bilinearly resized (align_corners=False) from (h, w)
+ * to (H, W) on the fly; grid_sample is bilinear / zeros / align_corners=True.  If up2 != 0 the result is
+ * written nearest-upsampled x2: out is (F, 2H, 2W, C) (F.interpolate(scale_factor=2) of UpBlock2d, util.py:107). */
+int extdm_warp_blend_cl(const void* skip, const void* prev, const float* flow, const float* occ, void* out,
+                        long long F, long long Fs, int H, int W, int C, int h, int w, int up2, void* stream);
+
+/* Image-space warp + final blend, fp32 NCHW (generator.py:163 and :201-204):
+ * deformed = grid_sample(src, resize(flow));  prediction = deformed*occ + dec*(1-occ)  (or = deformed when
+ * occ == NULL, generator.py:81-90).  src: (Fs, 3, H, W); dec: (F, H, W, dec_stride) fp32 channels-last
+ * decoder output (sigmoid already applied), first 3 channels used; prediction / deformed: (F, 3, H, W);
+ * either output pointer may be NULL. */
+int extdm_warp_image(const float* src, const float* dec, int dec_stride, const float* flow, const float* occ,
+                     float* prediction, float* deformed, long long F, long long Fs, int H, int W, int h, int w,
+                     void* stream);
+
+/* Eval-mode BatchNorm + ReLU on channels-last bf16 (ResBlock2d pre-activation, util.py:83-89):
+ * y = relu(x*scale[c] + shift[c]). */
+int extdm_bn_relu_cl(const void* x, const float* scale, const float* shift, void* y, long long rows, int C,
+                     void* stream);
+/* 2x2 average pool, channels-last bf16 (DownBlock2d, util.py:124,130). */
+int extdm_avgpool2_cl(const void* x, void* y, long long F, int H, int W, int C, void* stream);
+/* fp32 NCHW image -> channels-last bf16 im2col rows for the 7x7 `first` conv (K = 147 padded to 192). */
+int extdm_im2col7_image(const float* img, void* a, long long F, int H, int W, void* stream);
+
+/* Generic layout helpers. */
+int extdm_ncthw_to_cl(const float* x, void* y, int B, int C, long long T, long long HW, void* stream);
+int extdm_cl_to_ncthw(const void* x, float* y, int B, int C, long long T, long long HW, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

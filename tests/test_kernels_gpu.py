@@ -1,0 +1,411 @@
+"""Kernel-level parity (-m gpu): every C-ABI kernel against a plain fp32 torch statement of the same op.
+
+Tolerances: bf16 kernels (GEMM/conv/norm/attention outputs are stored in bf16) -- max abs error
+<= 2e-2 * max|ref| (+ small atol); fp32 kernels (DDIM update, quantile, warp) -- exact or 1e-6.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+import extdm_b200  # noqa: E402
+from extdm_b200 import ops  # noqa: E402
+
+DEV = "cuda"
+BF = torch.bfloat16
+R = ops.IMMEDIATE
+
+
+def rnd(*shape, seed=0, scale=1.0, dtype=torch.float32):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV).to(dtype)
+
+
+def close(out, ref, rel=2e-2, atol=2e-3, what=""):
+    out, ref = out.float(), ref.float()
+    err = (out - ref).abs().max().item()
+    lim = rel * ref.abs().max().item() + atol
+    assert err <= lim, f"{what}: max err {err:.4g} > {lim:.4g} (ref max {ref.abs().max().item():.4g})"
+
+
+def to_cl(x):      # (B,C,T,H,W) fp32 -> (B,T,H,W,C) bf16
+    return x.permute(0, 2, 3, 4, 1).contiguous().to(BF)
+
+
+def from_cl(x):
+    return x.float().permute(0, 4, 1, 2, 3)
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("rows,K,N,bn", [(1000, 128, 64, 0), (256, 64, 96, 0), (4096, 256, 384, 0),
+                                         (300, 512, 256, 0), (130, 64, 5, 0), (513, 192, 256, 128),
+                                         (2048, 1024, 512, 256)])
+def test_linear(rows, K, N, bn):
+    x = rnd(rows, K, seed=1).to(BF)
+    w = rnd(N, K, seed=2, scale=K ** -0.5).to(BF)
+    b = rnd(N, seed=3)
+    res = rnd(rows, N, seed=4).to(BF)
+    out = torch.zeros(rows, N, device=DEV, dtype=BF)
+    ops.linear_rows(R, x, w, N, out, bias=b, res=res, act=2, block_n=bn)
+    ref = F.silu(x.float() @ w.float().t() + b + res.float())
+    close(out, ref, what="linear")
+    out32 = torch.zeros(rows, N, device=DEV)
+    ops.linear_rows(R, x, w, N, out32, out_fp32=True, block_n=bn)
+    close(out32, x.float() @ w.float().t(), rel=2e-3, atol=1e-4, what="linear fp32")
+
+
+@pytest.mark.parametrize("H,C0,C1,N,k,T,B", [(32, 64, 0, 64, 3, 3, 2), (16, 128, 0, 128, 3, 5, 1),
+                                             (8, 256, 0, 256, 3, 7, 2), (4, 256, 0, 256, 3, 7, 2),
+                                             (32, 64, 64, 64, 3, 2, 1), (32, 256, 0, 64, 7, 2, 1),
+                                             (16, 128, 128, 128, 1, 3, 1), (64, 64, 0, 16, 7, 1, 2)])
+def test_conv(H, C0, C1, N, k, T, B):
+    x = rnd(B, C0, T, H, H, seed=1)
+    x2 = rnd(B, C1, T, H, H, seed=2) if C1 else None
+    w = rnd(N, C0 + C1, 1, k, k, seed=3, scale=((C0 + C1) * k * k) ** -0.5)
+    b = rnd(N, seed=4)
+    xc, x2c = to_cl(x), (to_cl(x2) if C1 else None)
+    out = torch.zeros(B, T, H, H, N, device=DEV, dtype=BF)
+    ops.conv_cl(R, xc, ops.pack_conv_weight(w), N, k, out, x2=x2c, bias=b)
+    xin = xc.float().permute(0, 4, 1, 2, 3)
+    if C1:
+        xin = torch.cat([xin, x2c.float().permute(0, 4, 1, 2, 3)], dim=1)
+    ref = F.conv3d(xin, w.to(BF).float(), b, padding=(0, k // 2, k // 2))
+    close(from_cl(out), ref, what="conv")
+
+
+def test_conv_frame_range_and_affine():
+    B, T, H, C = 2, 6, 16, 64
+    x = rnd(B, C, T, H, H, seed=1)
+    w = rnd(C, C, 1, 3, 3, seed=2, scale=(9 * C) ** -0.5)
+    res = rnd(B, C, 4, H, H, seed=3)
+    cs, cb = rnd(B, C, seed=4).abs() + 0.5, rnd(B, C, seed=5)
+    out = torch.zeros(B, 8, H, H, C, device=DEV, dtype=BF)
+    # frames [1,5) of x -> frames [3,7) of out, residual frames [0,4) of res
+    ops.conv_cl(R, to_cl(x), ops.pack_conv_weight(w), C, 3, out, t_range=(1, 5), out_t_offset=2, res=to_cl(res),
+                res_t_offset=-1, col_scale=cs, col_shift=cb)
+    ref = F.conv3d(to_cl(x).float().permute(0, 4, 1, 2, 3)[:, :, 1:5], w.to(BF).float(), None, padding=(0, 1, 1))
+    ref = (ref + to_cl(res).float().permute(0, 4, 1, 2, 3)) * cs[:, :, None, None, None] + cb[:, :, None, None, None]
+    got = from_cl(out)
+    close(got[:, :, 3:7], ref, what="conv range")
+    assert got[:, :, :3].abs().max() == 0 and got[:, :, 7:].abs().max() == 0
+
+
+def test_downsample_upsample():
+    B, T, H, C = 2, 3, 16, 64
+    x = rnd(B, C, T, H, H, seed=1)
+    xc = to_cl(x)
+    wd, bd = rnd(C, C, 1, 4, 4, seed=2, scale=(16 * C) ** -0.5), rnd(C, seed=3)
+    z = torch.zeros(B, T, H // 2 + 1, H // 2 + 1, 4 * C, device=DEV, dtype=BF)
+    ops.space_to_depth(R, xc, z)
+    out = torch.zeros(B, T, H // 2, H // 2, C, device=DEV, dtype=BF)
+    # 2x2 taps over z; count restricted to the H/2 x W/2 output positions
+    Ho = H // 2
+    bw, bh, bt = ops.std_box(Ho, Ho)
+    ops.gemm(R, a0=z, c0=4 * C, dims=(Ho + 1, Ho + 1, T, B),
+             strides0=(4 * C, (Ho + 1) * 4 * C, (Ho + 1) ** 2 * 4 * C, T * (Ho + 1) ** 2 * 4 * C),
+             box=(bw, bh, bt, 1), start=(0, 0, 0, 0), count=(Ho, Ho, T, B),
+             taps=[(0, 0, 0), (1, 0, 0), (0, 1, 0), (1, 1, 0)], w=ops.pack_downsample_weight(wd), n=C, out=out,
+             out_stride=(C, Ho * C, Ho * Ho * C, T * Ho * Ho * C), bias=bd)
+    xin = xc.float().permute(0, 4, 1, 2, 3)
+    ref = F.conv3d(xin, wd.to(BF).float(), bd, stride=(1, 2, 2), padding=(0, 1, 1))
+    close(from_cl(out), ref, what="downsample")
+
+    wu, bu = rnd(C, C, 1, 4, 4, seed=4, scale=(4 * C) ** -0.5), rnd(C, seed=5)
+    up = torch.zeros(B, T, 2 * H, 2 * H, C, device=DEV, dtype=BF)
+    for (py, px), (wm, taps) in ops.pack_upsample_weight(wu).items():
+        ops.conv_cl(R, xc, wm, C, 0, up, bias=bu, taps=taps, out_scale=2, out_phase=(py, px))
+    ref = F.conv_transpose3d(xin, wu.to(BF).float(), bu, stride=(1, 2, 2), padding=(0, 1, 1))
+    close(from_cl(up), ref, what="upsample")
+
+
+def test_tmodulator_layout():
+    """Conv2d 1x1 over '(T C)' channels read straight from the (B,T,H,W,C) layout (frames = taps)."""
+    B, Te, tm, tp, H, C = 2, 6, 2, 3, 8, 64
+    x = rnd(B, C, Te, H, H, seed=1)
+    w = rnd(tp * C, (Te - tm) * C, seed=2, scale=((Te - tm) * C) ** -0.5)
+    b = rnd(tp * C, seed=3)
+    xc = to_cl(x)
+    out = torch.zeros(B, tp, H, H, C, device=DEV, dtype=BF)
+    hw = H * H
+    ops.gemm(R, a0=xc, c0=C, dims=(hw, 1, Te, B), strides0=(C, hw * C, hw * C, Te * hw * C),
+             box=(64, 1, 1, 2), start=(0, 0, 0, 0), count=(hw, 1, 1, B),
+             taps=[(0, 0, tm + t) for t in range(Te - tm)], w=w.to(BF).contiguous(), n=tp * C, out=out,
+             out_stride=(C, 0, 0, tp * hw * C), col_group=C, col_group_stride=hw * C, bias=b)
+    flat = xc.float().permute(0, 4, 1, 2, 3)[:, :, tm:].permute(0, 2, 1, 3, 4).reshape(B, (Te - tm) * C, H, H)
+    ref = F.conv2d(flat, w.to(BF).float()[:, :, None, None], b).reshape(B, tp, C, H, H).permute(0, 2, 1, 3, 4)
+    close(from_cl(out), ref, what="tmodulator")
+
+
+# ------------------------------------------------------------------------------------------------ norms
+@pytest.mark.parametrize("C,T,H", [(64, 5, 32), (128, 3, 16), (256, 7, 8), (512, 7, 4)])
+def test_groupnorm_silu(C, T, H):
+    B = 2
+    x = rnd(B, C, T, H, H, seed=1, scale=2.0) + 0.5
+    g, b = rnd(C, seed=2) * 0.1 + 1, rnd(C, seed=3) * 0.1
+    ss = rnd(B, 2 * C + 10, seed=4) * 0.3
+    res = rnd(B, C, T, H, H, seed=5)
+    xc = to_cl(x)
+    ws = torch.zeros(B * 32 * 8 * 2, device=DEV)
+    y = torch.zeros_like(xc)
+    ops.groupnorm_silu(R, xc, ws, g, b, y, scale_shift=ss, ss_off=10, res=to_cl(res))
+    xf = xc.float().permute(0, 4, 1, 2, 3)
+    ref = F.group_norm(xf, 8, g, b, eps=1e-5)
+    ref = ref * (ss[:, 10:10 + C, None, None, None] + 1) + ss[:, 10 + C:10 + 2 * C, None, None, None]
+    ref = F.silu(ref) + to_cl(res).float().permute(0, 4, 1, 2, 3)
+    close(from_cl(y), ref, rel=1e-2, what="groupnorm")
+    y2 = torch.zeros_like(xc)
+    ops.groupnorm_silu(R, xc, ws, g, b, y2)
+    close(from_cl(y2), F.silu(F.group_norm(xf, 8, g, b, eps=1e-5)), rel=1e-2, what="groupnorm plain")
+
+
+@pytest.mark.parametrize("C", [64, 128, 256, 512])
+def test_chan_layernorm(C):
+    B, T, H = 2, 5, 8
+    x, x2 = rnd(B, C, T, H, H, seed=1) + 0.3, rnd(B, C, 3, H, H, seed=2)
+    g1, g2 = rnd(C, seed=3) * 0.1 + 1, rnd(2 * C, seed=4) * 0.1 + 1
+    xc, x2c = to_cl(x), to_cl(x2)
+
+    def ln(v, g):
+        var = v.var(dim=1, unbiased=False, keepdim=True)
+        return (v - v.mean(dim=1, keepdim=True)) / (var + 1e-5).sqrt() * g[None, :, None, None, None]
+
+    y = torch.zeros(B, T, H, H, C, device=DEV, dtype=BF)
+    ops.chan_layernorm(R, xc, g1, y)
+    close(from_cl(y), ln(xc.float().permute(0, 4, 1, 2, 3), g1), rel=1e-2, what="chanLN")
+    y = torch.zeros(B, 3, H, H, 2 * C, device=DEV, dtype=BF)
+    ops.chan_layernorm(R, xc, g2, y, x2=x2c, t_range=(2, 5))
+    cat = torch.cat([xc.float().permute(0, 4, 1, 2, 3)[:, :, 2:5], x2c.float().permute(0, 4, 1, 2, 3)], dim=1)
+    close(from_cl(y), ln(cat, g2), rel=1e-2, what="chanLN dual")
+
+
+@pytest.mark.parametrize("C", [64, 256])
+def test_temporal_prenorm(C):
+    rows = 1000
+    x = rnd(rows, C, seed=1).to(BF)
+    g, w, b = rnd(C, seed=2) * 0.1 + 1, rnd(C, seed=3) * 0.1 + 1, rnd(C, seed=4) * 0.1
+    u, xz = torch.zeros_like(x), torch.zeros_like(x)
+    ops.temporal_prenorm(R, x, g, w, b, u, xz)
+    xf = x.float()
+    z = (xf - xf.mean(-1, keepdim=True)) / (xf.var(-1, unbiased=False, keepdim=True) + 1e-5).sqrt() * g
+    close(xz, xf + z, rel=1e-2, what="xz")
+    close(u, F.layer_norm(z, (C,), w, b), rel=1e-2, what="u")
+
+
+@pytest.mark.parametrize("C,H", [(64, 32), (256, 8), (128, 16)])
+def test_adaptor_normalize(C, H):
+    B, Tt, n = 2, 6, 4
+    x = rnd(B, C, Tt, H, H, seed=1, scale=1.5) + 0.7
+    xc = to_cl(x)
+    y = torch.zeros(B, n, H, H, C, device=DEV, dtype=BF)
+    ms = torch.zeros(2, B, C, device=DEV)
+    ops.adaptor_normalize(R, xc, n, y, ms, ops.adaptor_workspace(B, C, DEV))
+    xf = xc.float().permute(0, 4, 1, 2, 3)[:, :, :n]
+    flat = xf.reshape(B, C, -1)
+    mean, std = flat.mean(2), (flat.var(2) + 1e-5).sqrt()
+    close(ms[0], mean, rel=1e-4, atol=1e-4, what="mean")
+    close(ms[1], std, rel=1e-4, atol=1e-4, what="std")
+    close(from_cl(y), (xf - mean[:, :, None, None, None]) / std[:, :, None, None, None], rel=1e-2, what="norm")
+
+
+def test_resize_im2col_time_head():
+    B, C = 2, 64
+    x = rnd(B * 3, 16, 16, C, seed=1).to(BF)
+    y = torch.zeros(B * 3, 32, 32, C, device=DEV, dtype=BF)
+    ops.bilinear_resize_cl(R, x, y)
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), size=(32, 32), mode="bilinear").permute(0, 2, 3, 1)
+    close(y, ref, rel=1e-2, what="resize")
+
+    tc, tp, H = 2, 3, 32
+    cond, xt = rnd(B, 3, tc, H, H, seed=2), rnd(B, 3, tp, H, H, seed=3)
+    w, b = rnd(256, 3, 1, 7, 7, seed=4, scale=147 ** -0.5), rnd(256, seed=5)
+    a = torch.zeros(B * (tc + tp) * H * H, 192, device=DEV, dtype=BF)
+    ops.im2col7_flow(R, cond, xt, a, 0, tc + tp)
+    wp = torch.zeros(256, 192, device=DEV, dtype=BF)
+    wp[:, :147] = w[:, :, 0].permute(0, 2, 3, 1).reshape(256, 147).to(BF)
+    out = torch.zeros(B, tc + tp, H, H, 256, device=DEV, dtype=BF)
+    ops.linear_rows(R, a, wp, 256, out, bias=b)
+    ref = F.conv3d(torch.cat([cond, xt], 2).to(BF).float(), w.to(BF).float(), b, padding=(0, 3, 3))
+    close(from_cl(out), ref, what="im2col conv")
+
+    dim, nss = 64, 1000
+    time = torch.tensor([545, 90], device=DEV, dtype=torch.long)
+    w1, b1 = rnd(256, 64, seed=6, scale=0.125), rnd(256, seed=7) * 0.1
+    w2, b2 = rnd(256, 256, seed=8, scale=1 / 16), rnd(256, seed=9) * 0.1
+    wss, bss = rnd(nss, 256, seed=10, scale=1 / 16), rnd(nss, seed=11) * 0.1
+    o = torch.zeros(B, nss, device=DEV)
+    ops.time_mlp(R, time, w1, b1, w2, b2, wss, bss, o, dim)
+    half = dim // 2
+    f = torch.exp(torch.arange(half, device=DEV, dtype=torch.float32) * -(math.log(10000) / (half - 1)))
+    e = time[:, None].float() * f[None]
+    e = torch.cat((e.sin(), e.cos()), -1)
+    t = F.linear(F.gelu(F.linear(e, w1, b1)), w2, b2)
+    close(o, F.linear(F.silu(t), wss, bss), rel=1e-4, atol=1e-4, what="time mlp")
+
+    T, t0, H = 5, 2, 8
+    hf, ho = rnd(B, T, H, H, C, seed=12).to(BF), rnd(B, T, H, H, C, seed=13).to(BF)
+    wf, bf_, wo, bo = rnd(2, C, seed=14) * 0.1, rnd(2, seed=15), rnd(1, C, seed=16) * 0.1, rnd(1, seed=17)
+    out = torch.zeros(B, 3, T - t0, H, H, device=DEV)
+    ops.head_project(R, hf, ho, wf, bf_, wo, bo, out, t0)
+    rf = torch.einsum("bthwc,oc->bothw", hf.float(), wf) + bf_[None, :, None, None, None]
+    ro = torch.einsum("bthwc,oc->bothw", ho.float(), wo) + bo[None, :, None, None, None]
+    close(out, torch.cat([rf, ro], 1)[:, :, t0:], rel=1e-4, atol=1e-4, what="head")
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def _rope_tables(n, dh):
+    freqs = 1.0 / (10000.0 ** (torch.arange(0, dh, 2, dtype=torch.float32)[: dh // 2] / dh))
+    ang = torch.arange(n, dtype=torch.float32)[:, None] * freqs[None]
+    return ang.cos().contiguous().to(DEV), ang.sin().contiguous().to(DEV)
+
+
+@pytest.mark.parametrize("window,dh,T,H,shift", [((4, 4, 4), 16, 7, 8, (2, 2, 2)), ((4, 4, 4), 16, 7, 8, (0, 0, 0)),
+                                                 ((2, 4, 4), 32, 5, 8, (1, 2, 2)), ((4, 4, 4), 16, 6, 4, (2, 0, 0)),
+                                                 ((2, 4, 4), 32, 4, 16, (0, 0, 0))])
+def test_window_attention(window, dh, T, H, shift):
+    from oracle import extdm_oracle as O
+    B, heads = 2, 8
+    hid = heads * dh
+    N = window[0] * window[1] * window[2]
+    qkv = rnd(B, T, H, H, 3 * hid, seed=1).to(BF)
+    tbl = rnd((2 * window[0] - 1) * (2 * window[1] - 1) * (2 * window[2] - 1), heads, seed=2) * 0.5
+    rc, rs = _rope_tables(N, dh)
+    out = torch.zeros(B, T, H, H, hid, device=DEV, dtype=BF)
+    ops.window_attention(R, qkv, out, tbl, rc, rs, heads, dh, window, shift)
+    # reference (CPU, fp32) with the oracle's partition / mask helpers
+    z = qkv.float().cpu()
+    ws, ss = window, shift
+    Dp = -(-T // ws[0]) * ws[0]
+    z = F.pad(z, (0, 0, 0, 0, 0, 0, 0, Dp - T))
+    shifted = any(s > 0 for s in ss)
+    if shifted:
+        z = torch.roll(z, shifts=(-ss[0], -ss[1], -ss[2]), dims=(1, 2, 3))
+    win = z.reshape(B, Dp // ws[0], ws[0], H // ws[1], ws[1], H // ws[2], ws[2], 3 * hid)
+    win = win.permute(0, 1, 3, 5, 2, 4, 6, 7).reshape(-1, N, 3, heads, dh).permute(2, 0, 3, 1, 4)
+    q, k, v = win[0] * dh ** -0.5, win[1], win[2]
+    q, k = O.rotary(q), O.rotary(k)
+    att = q @ k.transpose(-1, -2)
+    idx = O._rel_pos_index(window)[:N, :N].reshape(-1)
+    att = att + tbl.cpu()[idx].reshape(N, N, heads).permute(2, 0, 1)[None]
+    if shifted:
+        mask = O._shift_mask(Dp, H, H, ws, ss)
+        att = (att.reshape(B, mask.shape[0], heads, N, N) + mask[None, :, None]).reshape(-1, heads, N, N)
+    o = (att.softmax(-1) @ v).transpose(1, 2).reshape(-1, N, hid)
+    o = o.reshape(B, Dp // ws[0], H // ws[1], H // ws[2], ws[0], ws[1], ws[2], hid)
+    o = o.permute(0, 1, 4, 2, 5, 3, 6, 7).reshape(B, Dp, H, H, hid)
+    if shifted:
+        o = torch.roll(o, shifts=ss, dims=(1, 2, 3))
+    close(out.cpu(), o[:, :T], rel=2e-2, atol=5e-3, what="window attention")
+
+
+@pytest.mark.parametrize("T,dh", [(30, 16), (12, 32), (14, 32), (7, 16)])
+def test_temporal_attention(T, dh):
+    from oracle import extdm_oracle as O
+    B, H, heads = 2, 4, 8
+    hid = heads * dh
+    qkv = rnd(B, T, H, H, 3 * hid, seed=1).to(BF)
+    rel = rnd(heads, 2 * T - 1, seed=2) * 0.5
+    rc, rs = _rope_tables(32, dh)
+    out = torch.zeros(B, T, H, H, hid, device=DEV, dtype=BF)
+    ops.temporal_attention(R, qkv, out, rel, rc, rs, heads, dh)
+    z = qkv.float().cpu().permute(0, 2, 3, 1, 4).reshape(B * H * H, T, 3, heads, dh).permute(2, 0, 3, 1, 4)
+    q, k, v = O.rotary(z[0] * dh ** -0.5), O.rotary(z[1]), z[2]
+    i = torch.arange(T)
+    bias = rel.cpu()[:, (i[None, :] - i[:, None]) + T - 1]
+    o = ((q @ k.transpose(-1, -2) + bias[None]).softmax(-1) @ v).permute(0, 2, 1, 3).reshape(B, H, H, T, hid)
+    close(out.cpu(), o.permute(0, 3, 1, 2, 4), rel=2e-2, atol=5e-3, what="temporal attention")
+
+
+# ------------------------------------------------------------------------------------------------ sampler
+@pytest.mark.parametrize("n", [15360, 61440, 3072])
+def test_ddim_step_bit_exact(n):
+    B = 3
+    img, pred, noise = rnd(B, n, seed=1), rnd(B, n, seed=2), rnd(B, n, seed=3)
+    img[1] *= 0.2          # one sample whose quantile is < 1 (clamped to 1)
+    a, b2 = torch.tensor(1.7, device=DEV), torch.tensor(1.3, device=DEV)
+    san, c, sig = torch.tensor(0.83, device=DEV), torch.tensor(0.41, device=DEV), torch.tensor(0.27, device=DEV)
+    xs = a * img - b2 * pred
+    s_ref = torch.quantile(xs.abs(), 0.9, dim=-1).clamp_(min=1.0)
+    s = torch.zeros(B, device=DEV)
+    ops.ddim_threshold(R, img, pred, a.item(), b2.item(), 0.9, s)
+    assert torch.equal(s, s_ref), (s, s_ref)
+    xs_c = xs.clamp(-s_ref[:, None], s_ref[:, None]) / s_ref[:, None]
+    ref = xs_c * san + c * pred + sig * noise
+    out, xso = torch.zeros_like(img), torch.zeros_like(img)
+    ops.ddim_update(R, img, pred, noise, s, a.item(), b2.item(), san.item(), c.item(), sig.item(), out, xso)
+    assert torch.equal(xso, xs_c)
+    assert torch.equal(out, ref)
+    ops.ddim_update(R, img, pred, None, s, a.item(), b2.item(), 1.0, 0.0, 0.0, out)
+    assert torch.equal(out, xs_c * 1.0 + 0.0 * pred)
+
+
+# ------------------------------------------------------------------------------------------------ warp
+def _flow(Fn, h, seed):
+    ident = torch.stack(torch.meshgrid(torch.linspace(-1, 1, h), torch.linspace(-1, 1, h), indexing="xy"), -1)
+    return (ident[None].to(DEV) + rnd(Fn, h, h, 2, seed=seed) * 0.2).contiguous()
+
+
+@pytest.mark.parametrize("H,C,up2,with_prev", [(16, 256, 1, True), (32, 128, 1, True), (64, 64, 0, True),
+                                               (16, 256, 0, False)])
+def test_warp_blend(H, C, up2, with_prev):
+    Fs, rep, h = 2, 3, 32
+    Fn = Fs * rep
+    skip = rnd(Fs, H, H, C, seed=1).to(BF)
+    prev = rnd(Fn, H, H, C, seed=2).to(BF) if with_prev else None
+    flow, occ = _flow(Fn, h, 3), torch.rand(Fn, 1, h, h, device=DEV)
+    out = torch.zeros(Fn, H * (2 if up2 else 1), H * (2 if up2 else 1), C, device=DEV, dtype=BF)
+    ops.warp_blend_cl(R, skip, prev, flow, occ, out, up2=bool(up2))
+    sk = skip.float().permute(0, 3, 1, 2).repeat_interleave(rep, dim=0)
+    fl = flow if h == H else F.interpolate(flow.permute(0, 3, 1, 2), size=(H, H), mode="bilinear").permute(0, 2, 3, 1)
+    oc = occ if h == H else F.interpolate(occ, size=(H, H), mode="bilinear")
+    ref = F.grid_sample(sk, fl, align_corners=True) * oc
+    if with_prev:
+        ref = ref + prev.float().permute(0, 3, 1, 2) * (1 - oc)
+    if up2:
+        ref = F.interpolate(ref, scale_factor=2)
+    close(out.float().permute(0, 3, 1, 2), ref, rel=1e-2, atol=1e-2, what="warp blend")
+    outn = torch.zeros_like(out)
+    ops.warp_blend_cl(R, skip, None, flow, None, outn, up2=bool(up2))
+    refn = F.grid_sample(sk, fl, align_corners=True)
+    if up2:
+        refn = F.interpolate(refn, scale_factor=2)
+    close(outn.float().permute(0, 3, 1, 2), refn, rel=1e-2, atol=1e-2, what="warp no occ")
+
+
+def test_warp_image_fp32():
+    Fs, rep, H, h = 2, 2, 64, 32
+    Fn = Fs * rep
+    src = torch.rand(Fs, 3, H, H, device=DEV)
+    dec = torch.rand(Fn, H, H, 4, device=DEV)
+    flow, occ = _flow(Fn, h, 5), torch.rand(Fn, 1, h, h, device=DEV)
+    pred, deformed = torch.zeros(Fn, 3, H, H, device=DEV), torch.zeros(Fn, 3, H, H, device=DEV)
+    ops.warp_image(R, src, dec, flow, occ, pred, deformed)
+    # CPU ATen is the oracle for the fp32 index math
+    srcr = src.cpu().repeat_interleave(rep, dim=0)
+    fl = F.interpolate(flow.cpu().permute(0, 3, 1, 2), size=(H, H), mode="bilinear").permute(0, 2, 3, 1)
+    oc = F.interpolate(occ.cpu(), size=(H, H), mode="bilinear")
+    d_ref = F.grid_sample(srcr, fl, align_corners=True)
+    p_ref = d_ref * oc + dec.cpu()[..., :3].permute(0, 3, 1, 2) * (1 - oc)
+    assert (deformed.cpu() - d_ref).abs().max().item() <= 2e-6
+    assert (pred.cpu() - p_ref).abs().max().item() <= 2e-6
+    ops.warp_image(R, src, None, flow, None, pred, None)
+    assert (pred.cpu() - d_ref).abs().max().item() <= 2e-6
+
+
+def test_lfae_helpers():
+    x = rnd(3, 16, 16, 64, seed=1).to(BF)
+    sc, sh = rnd(64, seed=2) * 0.2 + 1, rnd(64, seed=3) * 0.2
+    y = torch.zeros_like(x)
+    ops.bn_relu_cl(R, x, sc, sh, y)
+    close(y, F.relu(x.float() * sc + sh), rel=1e-2, what="bn relu")
+    p = torch.zeros(3, 8, 8, 64, device=DEV, dtype=BF)
+    ops.avgpool2_cl(R, x, p)
+    close(p, F.avg_pool2d(x.float().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1), rel=1e-2, what="avgpool")
+    img = torch.rand(2, 3, 64, 64, device=DEV)
+    a = torch.zeros(2 * 64 * 64, 192, device=DEV, dtype=BF)
+    ops.im2col7_image(R, img, a)
+    cols = F.unfold(img, 7, padding=3).reshape(2, 3, 49, 64 * 64).permute(0, 3, 2, 1).reshape(2 * 4096, 147)
+    close(a[:, :147], cols, rel=1e-2, what="im2col image")
+    assert a[:, 147:].abs().max() == 0
