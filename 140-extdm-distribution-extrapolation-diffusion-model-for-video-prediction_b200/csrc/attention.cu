@@ -286,8 +286,12 @@ extern "C" int extdm_window_attention(const void* qkv, void* out, const float* b
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define LAUNCH_WIN(N, D)                                                                                            \
   do {                                                                                                              \
-    int rc = set_smem(window_attention_kernel<N, D>, smem);                                                         \
-    if (rc) return rc;                                                                                              \
+    static size_t configured = 0;                                                                                   \
+    if (smem > configured) {                                                                                        \
+      int rc = set_smem(window_attention_kernel<N, D>, smem);                                                       \
+      if (rc) return rc;                                                                                            \
+      configured = smem;                                                                                            \
+    }                                                                                                               \
     window_attention_kernel<N, D><<<grid, 256, smem, st>>>(                                                         \
         reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), bias_table, rope_cos,   \
         rope_sin, T, H, W, heads, wd, wh, ww, sd, sh, sw, Dp);                                                      \
@@ -315,8 +319,12 @@ extern "C" int extdm_temporal_attention(const void* qkv, void* out, const float*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define LAUNCH_TMP(N, D)                                                                                            \
   do {                                                                                                              \
-    int rc = set_smem(temporal_attention_kernel<N, D>, smem);                                                       \
-    if (rc) return rc;                                                                                              \
+    static size_t configured = 0;                                                                                   \
+    if (smem > configured) {                                                                                        \
+      int rc = set_smem(temporal_attention_kernel<N, D>, smem);                                                     \
+      if (rc) return rc;                                                                                            \
+      configured = smem;                                                                                            \
+    }                                                                                                               \
     temporal_attention_kernel<N, D><<<grid, 256, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),           \
                                                              reinterpret_cast<__nv_bfloat16*>(out), rel_bias,       \
                                                              rope_cos, rope_sin, T, HW, heads);                     \

@@ -21,11 +21,13 @@ class Recorder:
         self.record = record
         self.steps = []          # (cfunc, args, name)
         self.keep = []           # tensors / ctypes objects that must outlive the launch list
+        self.meta = []           # per-launch algorithmic work (flops / bytes) for bench.py's roofline
 
-    def emit(self, name, args, keep=()):
+    def emit(self, name, args, keep=(), meta=None):
         if self.record:
             self.keep.extend(keep)
             self.steps.append((getattr(_lib.load(), name), args, name))
+            self.meta.append(meta or {})
         else:
             _lib.call(name, *args, C.c_void_p(torch.cuda.current_stream().cuda_stream))
 
@@ -40,6 +42,22 @@ class Recorder:
 
     def __len__(self):
         return len(self.steps)
+
+    def run_timed(self):
+        """Eager replay with one CUDA-event pair per launch -> list of (name, meta, milliseconds)."""
+        stream = torch.cuda.current_stream()
+        sp = C.c_void_p(stream.cuda_stream)
+        evs = []
+        for fn, args, name in self.steps:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            rc = fn(*args, sp)
+            b.record(stream)
+            if rc != 0:
+                raise _lib.ExtdmError(f"{name} failed ({rc})")
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        return [(name, m, a.elapsed_time(b)) for (_, _, name), m, (a, b) in zip(self.steps, self.meta, evs)]
 
 
 IMMEDIATE = Recorder(record=False)
@@ -144,7 +162,12 @@ def gemm(rec, *, a0, c0, dims, strides0, box, start, count, taps, w, n, out, out
     g.col_scale = 0 if col_scale is None else col_scale.data_ptr()
     g.col_shift = 0 if col_shift is None else col_shift.data_ptr()
     g.act, g.block_n = act, block_n
-    rec.emit("extdm_conv_gemm", (C.byref(g),), keep=(g, a0, a1, w, out, bias, res, col_scale, col_shift))
+    rows = count[0] * count[1] * count[2] * count[3]
+    ktot = len(taps) * (c0 + (c1 if a1 is not None else 0))
+    meta = dict(flops=2.0 * rows * n * ktot, rows=rows, n=n, k=ktot, taps=len(taps),
+                bytes=2.0 * rows * (c0 + (c1 if a1 is not None else 0)) + 2.0 * n * ktot
+                + rows * n * (4.0 if out_fp32 else 2.0))
+    rec.emit("extdm_conv_gemm", (C.byref(g),), keep=(g, a0, a1, w, out, bias, res, col_scale, col_shift), meta=meta)
 
 
 def linear_rows(rec, x, w, n, out, *, bias=None, res=None, res_fp32=False, act=0, out_fp32=False, x2=None,
@@ -200,8 +223,9 @@ def groupnorm_silu(rec, x, stats_ws, gamma, beta, y, *, groups=8, scale_shift=No
              keep=(x, gamma, beta, scale_shift, res, y))
 
 
-def chan_layernorm(rec, x, gamma, y, *, x2=None, t_range=None, eps=1e-5):
-    """Channel LayerNorm of x (B, T, H, W, C) [cat x2 on channels] over frames t_range -> dense y."""
+def chan_layernorm(rec, x, gamma, y, *, x2=None, t_range=None, t2_range=None, eps=1e-5):
+    """Channel LayerNorm of frames t_range of x (B, T, H, W, C) [channel-concatenated with frames t2_range
+    of x2 (B, T2, H, W, C)] -> dense y (B, nt, H, W, C[+C])."""
     B, T, H, W, Cc = x.shape
     t0, t1 = t_range if t_range else (0, T)
     hw = H * W
@@ -209,7 +233,10 @@ def chan_layernorm(rec, x, gamma, y, *, x2=None, t_range=None, eps=1e-5):
     x0p = C.c_void_p(x.data_ptr() + t0 * hw * Cc * 2)
     if x2 is not None:
         T2, C2 = x2.shape[1], x2.shape[-1]
-        x1p = C.c_void_p(x2.data_ptr())
+        u0, u1 = t2_range if t2_range else (0, T2)
+        if u1 - u0 != t1 - t0:
+            raise ValueError("chan_layernorm: frame ranges of the two sources differ")
+        x1p = C.c_void_p(x2.data_ptr() + u0 * hw * C2 * 2)
         s1 = T2 * hw * C2
     else:
         x1p, s1, C2 = C.c_void_p(0), 0, 0
