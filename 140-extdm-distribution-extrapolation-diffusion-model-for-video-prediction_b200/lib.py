@@ -35,6 +35,7 @@ _I, _L, _F, _P = C.c_int, C.c_longlong, C.c_float, C.c_void_p
 PROTOTYPES = {
     "extdm_abi_version": [],
     "extdm_last_error": [],
+    "extdm_sizeof_gemm": [],
     "extdm_conv_gemm": [C.POINTER(ExtdmGemm), _P],
     "extdm_groupnorm_stats": [_P, _P, _I, _L, _I, _I, _P],
     "extdm_groupnorm_apply": [_P, _P, _P, _P, _P, _L, _I, _P, _P, _I, _L, _I, _I, _F, _P],
@@ -80,6 +81,8 @@ def load():
             fn = getattr(lib, name)
             fn.argtypes = args
             fn.restype = _RET.get(name, C.c_int)
+        if lib.extdm_sizeof_gemm() != C.sizeof(ExtdmGemm):
+            raise ExtdmError("struct ExtdmGemm: ctypes mirror and compiled library disagree on the layout")
         _lib = lib
     return _lib
 

@@ -71,6 +71,8 @@ typedef struct ExtdmGemm {
 } ExtdmGemm;
 
 int extdm_conv_gemm(const ExtdmGemm* g, void* stream);
+/* sizeof(ExtdmGemm) as the library was compiled: lets a foreign-language binding verify its struct mirror. */
+int extdm_sizeof_gemm(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Bandwidth-bound UNet kernels (channels-last bf16 activations, fp32 statistics).

@@ -1,0 +1,132 @@
+"""CPU: host logic of the product -- state_dict manifests, schedules, the C ABI surface, sharding."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+import extdm_b200  # noqa: F401
+from extdm_b200 import lib
+from extdm_b200.manifest import UnetConfig, adaptor_layers, unet_manifest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.mark.parametrize("name,variant,tc,tp,dm", [("unet_ada_c2p5", "ada", 2, 5, (1, 2, 4, 4)),
+                                                   ("unet_u12_c2p3", "u12", 2, 3, (1, 2, 4, 4)),
+                                                   ("unet_base_c3p2", "base", 3, 2, (1, 2, 4, 8))])
+def test_unet_manifest_matches_reference(name, variant, tc, tp, dm):
+    fx = torch.load(os.path.join(GOLD, name + ".pt"))
+    ref = {k: tuple(v) for k, v in fx["manifest"].items()}
+    assert unet_manifest(UnetConfig(variant, tc, tp, dim_mults=dm)) == ref
+
+
+def test_adaptor_layers():
+    # KTH L=2/30 frames, BAIR L=3/14, SMMNIST L=1/9, UCF L=2/12, City L=2/6
+    assert adaptor_layers(10, 20) == (2, 30)
+    assert adaptor_layers(2, 10) == (3, 14)
+    assert adaptor_layers(9, 5) == (1, 9)
+    assert adaptor_layers(4, 8) == (2, 12)
+    assert adaptor_layers(2, 5) == (2, 6)
+
+
+def test_wrapper_state_dicts_match_reference():
+    from extdm_b200.flow_diffusion import FlowDiffusion
+    fx = torch.load(os.path.join(GOLD, "pipeline_kth_c2p5.pt"))
+    fd = FlowDiffusion(config=fx["cfg"], pretrained_pth="", is_train=False,
+                       Unet3D_architecture="DenoiseNet_STWAtt_w_w_ref_adaptor_cross_multi_traj_ada")
+    for part in ("generator", "region_predictor", "bg_predictor", "diffusion"):
+        mine = {k: tuple(v.shape) for k, v in getattr(fd, part).state_dict().items()}
+        assert mine == {k: tuple(v) for k, v in fx["manifests"][part].items()}, part
+    assert fd.cond_frame_num == 2 and fd.pred_frame_num == 5
+
+
+def test_conditioning_stage_matches_reference_on_cpu():
+    from extdm_b200.flow_diffusion import FlowDiffusion
+    from extdm_b200.weights import synth_state_dict
+    fx = torch.load(os.path.join(GOLD, "pipeline_kth_c2p5.pt"))
+    fd = FlowDiffusion(config=fx["cfg"], pretrained_pth="", is_train=False,
+                       Unet3D_architecture="DenoiseNet_STWAtt_w_w_ref_adaptor_cross_multi_traj_ada").eval()
+    for part, seed in fx["weight_seeds"].items():
+        m = getattr(fd, part)
+        m.load_state_dict(synth_state_dict(fx["manifests"][part], seed, base=m.state_dict()), strict=True)
+    real_vid = torch.rand((1, 1, 2, 64, 64), generator=torch.Generator().manual_seed(500)).expand(1, 3, 2, 64, 64)
+    ret, x_cond, fea, _ = fd.condition(real_vid.contiguous())
+    for k in ("real_vid_grid", "real_vid_conf", "real_out_vid", "real_warped_vid"):
+        assert (ret[k] - fx["out"][k]).abs().max().item() < 2e-4, k
+    assert x_cond.shape == (1, 3, 2, 32, 32) and fea.shape == (1, 256, 7, 16, 16)
+
+
+def test_hot_path_refuses_cpu():
+    """No CPU / PyTorch fallback: the UNet and the decoder raise when they are not on a CUDA device."""
+    from extdm_b200.unet import Unet3D
+    u = Unet3D(dim=64, channels=512, dim_mults=(1, 2, 4, 4), cond_num=2, pred_num=5)
+    with pytest.raises(RuntimeError):
+        u(torch.zeros(1, 3, 5, 32, 32), torch.zeros(1, dtype=torch.long), cond_frames=torch.zeros(1, 3, 2, 32, 32),
+          cond_fea=torch.zeros(1, 256, 7, 16, 16))
+
+
+def test_ddim_schedule_matches_oracle():
+    from oracle import extdm_oracle as O
+    from extdm_b200.diffusion import GaussianDiffusion
+    d = GaussianDiffusion(torch.nn.Identity(), image_size=32, num_frames=30, sampling_timesteps=10, timesteps=1000)
+    sched = d.ddim_schedule()
+    assert [s[0] for s in sched] == [909, 818, 727, 636, 545, 454, 363, 272, 181, 90]
+    assert [(a, b) for a, b, *_ in sched] == O.ddim_time_pairs()
+    tab = O.cosine_schedule_tables()
+    for k in ("alphas_cumprod_prev", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod"):
+        assert torch.equal(getattr(d, k), tab[k])
+    assert sched[-1][5] == 0.0 and sched[-1][6] == 0.0 and sched[-1][4] == 1.0      # last step: img = x_start
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The shared library loads without a GPU and exports every function include/extdm_b200.h declares."""
+    hdr = open(os.path.join(ROOT, "include", "extdm_b200.h")).read()
+    declared = set(re.findall(r"\b(extdm_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    cdll = ctypes.CDLL(lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(cdll, name), f"{name} declared in the header but not exported"
+    assert declared == set(lib.PROTOTYPES), declared ^ set(lib.PROTOTYPES)
+    assert lib.load().extdm_abi_version() == 1
+    assert ctypes.sizeof(lib.ExtdmGemm) == lib.load().extdm_sizeof_gemm()
+
+
+def test_pack_weights_layouts():
+    from extdm_b200 import ops
+    w = torch.arange(2 * 3 * 9, dtype=torch.float32).reshape(2, 3, 1, 3, 3)
+    p = ops.pack_conv_weight(w).float()
+    assert p.shape == (2, 27) and p[1, (1 * 3 + 2) * 3 + 1] == w[1, 1, 0, 1, 2]
+    wd = torch.randn(4, 2, 1, 4, 4)
+    pd = ops.pack_downsample_weight(wd).float()
+    a, b, py, px, ci = 1, 0, 1, 1, 1
+    assert torch.allclose(pd[3, (a * 2 + b) * 8 + (py * 2 + px) * 2 + ci], wd[3, ci, 0, 2 * a + py, 2 * b + px].bfloat16().float())
+    assert ops.std_box(32, 32) == (32, 4, 1) and ops.std_box(4, 4) == (4, 4, 8) and ops.std_box(64, 64) == (64, 2, 1)
+
+
+def test_two_rank_sharding_gloo(tmp_path):
+    """world_size-2 gloo run of the host-side sharding logic: each rank takes its slice of the videos and the
+    predicted frames are all-gathered in rank order (bench.py's N>1 path, without a GPU)."""
+    script = tmp_path / "shard.py"
+    script.write_text(
+        "import os, sys, torch, torch.distributed as dist\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import extdm_b200\n"
+        "from extdm_b200.sharding import shard_range, gather_predictions\n"
+        "dist.init_process_group('gloo')\n"
+        "r, w = dist.get_rank(), dist.get_world_size()\n"
+        "lo, hi = shard_range(10, r, w)\n"
+        "vids = torch.arange(10.).view(10, 1, 1, 1, 1).expand(10, 3, 4, 2, 2)\n"
+        "out = gather_predictions(vids[lo:hi].contiguous() * 2, 10)\n"
+        "assert torch.equal(out, vids * 2), out.flatten()[:12]\n"
+        "assert shard_range(10, 0, 4) == (0, 3) and shard_range(10, 3, 4) == (8, 10)\n"
+        "dist.destroy_process_group()\n")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29581")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29581", str(script)],
+                       capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
