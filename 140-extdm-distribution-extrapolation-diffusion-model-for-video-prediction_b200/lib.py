@@ -49,6 +49,8 @@ PROTOTYPES = {
     "extdm_time_mlp": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "extdm_head_project": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "extdm_window_attention": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "extdm_stw_fused_supported": [_I, _I, _I, _I, _I, _I],
+    "extdm_stw_fused": [_P, _P, _P, _P, _P, _P, _P, _P, _P] + [_I] * 14 + [_F, _P],
     "extdm_temporal_attention": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "extdm_ddim_threshold": [_P, _P, _F, _F, _F, _P, _I, _I, _P],
     "extdm_ddim_update": [_P, _P, _P, _P, _F, _F, _F, _F, _F, _P, _P, _I, _I, _P],

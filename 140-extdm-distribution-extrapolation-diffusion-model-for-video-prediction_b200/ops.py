@@ -299,6 +299,19 @@ def window_attention(rec, qkv, out, bias_table, rcos, rsin, heads, dh, window, s
              keep=(qkv, out, bias_table, rcos, rsin))
 
 
+def stw_fused_supported(C_, heads, dh, window):
+    return bool(_lib.load().extdm_stw_fused_supported(C_, heads, dh, window[0], window[1], window[2]))
+
+
+def stw_fused(rec, x, y, gamma, wqkv, wproj, proj_bias, bias_table, rcos, rsin, heads, dh, window, shift, eps=1e-5):
+    B, T, H, W, Cc = x.shape
+    rec.emit("extdm_stw_fused", (_p(x), _p(y), _p(gamma), _p(wqkv), _p(wproj), _p(proj_bias), _p(bias_table),
+                                 _p(rcos), _p(rsin), B, T, H, W, Cc, heads, dh, window[0], window[1], window[2],
+                                 shift[0], shift[1], shift[2], C.c_float(eps)),
+             keep=(x, y, gamma, wqkv, wproj, proj_bias, bias_table, rcos, rsin),
+             meta=dict(bytes=4.0 * x.numel()))
+
+
 def temporal_attention(rec, qkv, out, rel_bias, rcos, rsin, heads, dh):
     B, T, H, W, _ = qkv.shape
     rec.emit("extdm_temporal_attention", (_p(qkv), _p(out), _p(rel_bias), _p(rcos), _p(rsin), B, T, H * W, heads, dh),

@@ -106,6 +106,8 @@ class PackedUnet:
 class UnetRunner:
     """Launch lists + static buffers for one (config, batch, resolution)."""
 
+    fuse_stw = True          # class-level switch (tests compare the fused and the un-fused STW paths)
+
     def __init__(self, packed, B, H=32, W=32, fea_hw=16):
         cfg = packed.cfg
         if cfg.variant == "u12":
@@ -155,6 +157,13 @@ class UnetRunner:
                 if size != window[i]:
                     raise NotImplementedError(f"window {cfg.window} larger than the volume {(T, H, W)}")
                 shift[i] = 0
+        if self.fuse_stw and ops.stw_fused_supported(C, cfg.heads, cfg.dim_head, window):
+            y = self.buf(B, T, H, W, C)
+            ops.stw_fused(rec, x, y, pk.f32[p + ".fn.norm.gamma"], pk.w[p + ".fn.fn.attn.qkv.weight"],
+                          pk.w[p + ".fn.fn.attn.proj.weight"], pk.f32[p + ".fn.fn.attn.proj.bias"],
+                          pk.f32[p + ".fn.fn.attn.relative_position_bias_table"], pk.rope_w[0], pk.rope_w[1],
+                          cfg.heads, cfg.dim_head, window, shift)
+            return y
         z = self.buf(B, T, H, W, C)
         ops.chan_layernorm(rec, x, pk.f32[p + ".fn.norm.gamma"], z)
         qkv = self.buf(B, T, H, W, 3 * cfg.hidden)

@@ -150,6 +150,16 @@ int extdm_window_attention(const void* qkv, void* out, const float* bias_table, 
                            const float* rope_sin, int B, int T, int H, int W, int heads, int dh, int wd, int wh,
                            int ww, int sd, int sh, int sw, void* stream);
 
+/* Whole Residual(PreNorm(STWAttentionLayer)) in one kernel for the high-resolution levels:
+ * y = x + proj(window_attention(chanLN(x) @ Wqkv^T)) (...cross_multi.py:139-159, 409-560).  x, y: (B,T,H,W,C) bf16
+ * (y must not alias x); wqkv: (3*heads*dh, C) bf16; wproj: (C, heads*dh) bf16.  Supported: heads 8 and
+ * (64 tokens, dh 16, C 64|128) or (32 tokens, dh 32, C 64) -- extdm_stw_fused_supported() returns 1. */
+int extdm_stw_fused_supported(int C, int heads, int dh, int wd, int wh, int ww);
+int extdm_stw_fused(const void* x, void* y, const float* gamma, const void* wqkv, const void* wproj,
+                    const float* proj_bias, const float* bias_table, const float* rope_cos, const float* rope_sin,
+                    int B, int T, int H, int W, int C, int heads, int dh, int wd, int wh, int ww, int sd, int sh,
+                    int sw, float eps, void* stream);
+
 /* Temporal attention core (Attention.forward ...cross_multi.py:269-302): sequence = T frames of one pixel.
  * qkv: (B, T, HW, 3*heads*dh); out: (B, T, HW, heads*dh); rel_bias: (heads, 2T-1) fp32 indexed by (j-i+T-1). */
 int extdm_temporal_attention(const void* qkv, void* out, const float* rel_bias, const float* rope_cos,

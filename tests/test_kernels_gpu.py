@@ -409,3 +409,32 @@ def test_lfae_helpers():
     cols = F.unfold(img, 7, padding=3).reshape(2, 3, 49, 64 * 64).permute(0, 3, 2, 1).reshape(2 * 4096, 147)
     close(a[:, :147], cols, rel=1e-2, what="im2col image")
     assert a[:, 147:].abs().max() == 0
+
+
+@pytest.mark.parametrize("window,dh,C,T,H,shifted", [((4, 4, 4), 16, 64, 7, 16, True), ((4, 4, 4), 16, 64, 7, 16, False),
+                                                     ((4, 4, 4), 16, 128, 6, 8, True), ((2, 4, 4), 32, 64, 5, 8, True),
+                                                     ((4, 4, 4), 16, 64, 30, 32, True)])
+def test_stw_fused_layer(window, dh, C, T, H, shifted):
+    """Whole Residual(PreNorm(STWAttentionLayer)) in one kernel vs the oracle's stw_attention (CPU fp32)."""
+    from oracle import extdm_oracle as O
+    B, heads = 2, 8
+    hid = heads * dh
+    N = window[0] * window[1] * window[2]
+    x = rnd(B, C, T, H, H, seed=1)
+    sd = {"fn.norm.gamma": (rnd(1, C, 1, 1, 1, seed=2) * 0.1 + 1).cpu(),
+          "fn.fn.attn.qkv.weight": rnd(3 * hid, C, seed=3, scale=C ** -0.5).to(BF).float().cpu(),
+          "fn.fn.attn.proj.weight": rnd(C, hid, seed=4, scale=hid ** -0.5).to(BF).float().cpu(),
+          "fn.fn.attn.proj.bias": (rnd(C, seed=5) * 0.1).cpu(),
+          "fn.fn.attn.relative_position_bias_table":
+              (rnd((2 * window[0] - 1) * (2 * window[1] - 1) * (2 * window[2] - 1), heads, seed=6) * 0.5).cpu()}
+    xc = to_cl(x)
+    y = torch.zeros_like(xc)
+    shift = tuple(w // 2 for w in window) if shifted else (0, 0, 0)
+    rc, rs = _rope_tables(N, dh)
+    assert ops.stw_fused_supported(C, heads, dh, window)
+    ops.stw_fused(R, xc, y, sd["fn.norm.gamma"].reshape(-1).to(DEV), sd["fn.fn.attn.qkv.weight"].to(DEV).to(BF),
+                  sd["fn.fn.attn.proj.weight"].to(DEV).to(BF), sd["fn.fn.attn.proj.bias"].to(DEV),
+                  sd["fn.fn.attn.relative_position_bias_table"].to(DEV), rc, rs, heads, dh, window, shift)
+    with torch.no_grad():
+        ref = O.stw_attention(xc.float().permute(0, 4, 1, 2, 3).cpu(), O.SD(sd), window, shift, heads, dh)
+    close(from_cl(y).cpu(), ref, rel=2e-2, atol=5e-3, what="stw fused")
