@@ -23,6 +23,7 @@ struct GemmDev {
   int box[4], start[4], count[4], ntile[4];
   signed char tap[64][4];
   int n;
+  int n_tiles_n, total_tiles;
   void* out;
   int out_fp32;
   long long out_base, out_stride[4];
@@ -35,6 +36,7 @@ struct GemmDev {
   const float* col_scale;
   const float* col_shift;
   int act;
+  float* gn_part;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -44,35 +46,50 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
-template <int BN, int STAGES>
+struct TileCoord {
+  int c1, c2, c3, c4, n0, m_tile;
+};
+__device__ __forceinline__ TileCoord decode_tile(const GemmDev& p, int tile, int BN) {
+  TileCoord t;
+  const int nt = tile % p.n_tiles_n;
+  int tidx = tile / p.n_tiles_n;
+  t.m_tile = tidx;
+  const int t0 = tidx % p.ntile[0]; tidx /= p.ntile[0];
+  const int t1 = tidx % p.ntile[1]; tidx /= p.ntile[1];
+  const int t2 = tidx % p.ntile[2]; tidx /= p.ntile[2];
+  t.c1 = p.start[0] + t0 * p.box[0];
+  t.c2 = p.start[1] + t1 * p.box[1];
+  t.c3 = p.start[2] + t2 * p.box[2];
+  t.c4 = p.start[3] + tidx * p.box[3];
+  t.n0 = nt * BN;
+  return t;
+}
+
+// Persistent CTAs: each loops over output tiles (tile = blockIdx.x + i*gridDim.x, n-tile fastest).  The TMA
+// producer runs ahead through the smem ring across tile boundaries; the MMA issuer alternates between two TMEM
+// accumulators so the epilogue of tile i overlaps the main loop of tile i+1.
+// GN: the epilogue also emits per-tile GroupNorm partial sums (8 groups over the BN == n columns) of the
+// bf16-rounded output -- the statistics pass of Block.forward's GroupNorm costs no extra read of the tensor.
+template <int BN, int STAGES, bool GN>
 __global__ void __launch_bounds__(kGemmThreads, BN == 256 ? 1 : 2)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                  const __grid_constant__ CUtensorMap map_b, const __grid_constant__ GemmDev p) {
   constexpr int kBTileBytes = BN * kBlockK * 2;
   constexpr int kStageBytes = kATileBytes + kBTileBytes;
-  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  constexpr uint32_t kAccCols = BN < 32 ? 32 : BN;
+  constexpr uint32_t kTmemCols = 2 * kAccCols;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* acc_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+  uint64_t* acc_full = empty_bar + STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* s_gn = reinterpret_cast<float*>(tmem_slot + 4);          // [2][4][16]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  // ---- tile coordinates
-  int tidx = blockIdx.x;
-  int t0 = tidx % p.ntile[0]; tidx /= p.ntile[0];
-  int t1 = tidx % p.ntile[1]; tidx /= p.ntile[1];
-  int t2 = tidx % p.ntile[2]; tidx /= p.ntile[2];
-  int t3 = tidx;
-  const int c1 = p.start[0] + t0 * p.box[0];
-  const int c2 = p.start[1] + t1 * p.box[1];
-  const int c3 = p.start[2] + t2 * p.box[2];
-  const int c4 = p.start[3] + t3 * p.box[3];
-  const int n0 = blockIdx.y * BN;
   const int nk = p.nk0 + p.nk1;
   const int total_k = p.ntaps * nk;
 
@@ -84,7 +101,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(acc_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -101,44 +121,58 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tap = 0; tap < p.ntaps; ++tap) {
-        const int o1 = p.tap[tap][0], o2 = p.tap[tap][1], o3 = p.tap[tap][2];
-        for (int kc = 0; kc < nk; ++kc) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * kStageBytes;
-          uint8_t* sb = sa + kATileBytes;
-          mbar_expect_tx(&full_bar[stage], kStageBytes);
-          if (kc < p.nk0)
-            tma_load_5d(&map_a0, sa, &full_bar[stage], kc * kBlockK, c1 + o1, c2 + o2, c3 + o3, c4);
-          else
-            tma_load_5d(&map_a1, sa, &full_bar[stage], (kc - p.nk0) * kBlockK, c1 + o1, c2 + o2, c3 + o3, c4);
-          tma_load_2d(&map_b, sb, &full_bar[stage], (tap * nk + kc) * kBlockK, n0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile, BN);
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          const int o1 = p.tap[tap][0], o2 = p.tap[tap][1], o3 = p.tap[tap][2];
+          for (int kc = 0; kc < nk; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * kStageBytes;
+            uint8_t* sb = sa + kATileBytes;
+            mbar_expect_tx(&full_bar[stage], kStageBytes);
+            if (kc < p.nk0)
+              tma_load_5d(&map_a0, sa, &full_bar[stage], kc * kBlockK, tc.c1 + o1, tc.c2 + o2, tc.c3 + o3, tc.c4);
+            else
+              tma_load_5d(&map_a1, sa, &full_bar[stage], (kc - p.nk0) * kBlockK, tc.c1 + o1, tc.c2 + o2, tc.c3 + o3,
+                          tc.c4);
+            tma_load_2d(&map_b, sb, &full_bar[stage], (tap * nk + kc) * kBlockK, tc.n0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     // =========================== MMA issuer (single thread)
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN < 16 ? 16 : BN);
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < total_k; ++it) {
-        mbar_wait(&full_bar[stage], phase);
+      int local = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+        const int as = local & 1;
+        const uint32_t aphase = (local >> 1) & 1;
+        mbar_wait(&acc_empty[as], aphase ^ 1);            // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-        const uint64_t da = umma_desc_sw128(sa);
-        const uint64_t db = umma_desc_sw128(sa + kATileBytes);
+        const uint32_t tmem_d = tmem_base + as * kAccCols;
+        for (int it = 0; it < total_k; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint64_t da = umma_desc_sw128(sa);
+          const uint64_t db = umma_desc_sw128(sa + kATileBytes);
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-          // advance 16 bf16 = 32 B along K inside the 128B swizzle row: +2 in (addr >> 4) units
-          umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128B swizzle row: +2 in (addr >> 4) units
+            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&empty_bar[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        umma_commit(&acc_full[as]);
       }
-      umma_commit(acc_bar);
     }
+    __syncwarp();
   } else {
     // =========================== epilogue warps
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
@@ -148,96 +182,189 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     const int i2 = r % p.box[1]; r /= p.box[1];
     const int i3 = r % p.box[2]; r /= p.box[2];
     const int i4 = r;
-    const int g1 = c1 + i1, g2 = c2 + i2, g3 = c3 + i3, g4 = c4 + i4;
-    const bool row_ok = g1 < p.start[0] + p.count[0] && g2 < p.start[1] + p.count[1] &&
-                        g3 < p.start[2] + p.count[2] && g4 < p.start[3] + p.count[3];
-    const long long orow = p.out_base + g1 * p.out_stride[0] + g2 * p.out_stride[1] + g3 * p.out_stride[2] +
-                           g4 * p.out_stride[3];
-    const long long rrow = p.res_base + g1 * p.res_stride[0] + g2 * p.res_stride[1] + g3 * p.res_stride[2] +
-                           g4 * p.res_stride[3];
-    mbar_wait(acc_bar, 0);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     constexpr int kChunks = (BN + 15) / 16;
-#pragma unroll 1
-    for (int ch = 0; ch < kChunks; ++ch) {
-      uint32_t raw[16];
-      tmem_ld16(taddr + ch * 16, raw);
-      tmem_ld_wait();
-      const int nb = n0 + ch * 16;
-      if (!row_ok || nb >= p.n) continue;
-      float v[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
-      const long long coff = static_cast<long long>(nb / p.col_group) * p.col_group_stride + (nb % p.col_group);
-      const bool full = (nb + 16 <= p.n);
-      if (p.bias) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (full || nb + j < p.n) v[j] += __ldg(p.bias + nb + j);
-      }
-      if (p.res) {
+    int local = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+      const int as = local & 1;
+      const uint32_t aphase = (local >> 1) & 1;
+      const TileCoord tc = decode_tile(p, tile, BN);
+      const int n0 = tc.n0;
+      const int g1 = tc.c1 + i1, g2 = tc.c2 + i2, g3 = tc.c3 + i3, g4 = tc.c4 + i4;
+      const bool row_ok = g1 < p.start[0] + p.count[0] && g2 < p.start[1] + p.count[1] &&
+                          g3 < p.start[2] + p.count[2] && g4 < p.start[3] + p.count[3];
+      const long long orow = p.out_base + g1 * p.out_stride[0] + g2 * p.out_stride[1] + g3 * p.out_stride[2] +
+                             g4 * p.out_stride[3];
+      const long long rrow = p.res_base + g1 * p.res_stride[0] + g2 * p.res_stride[1] + g3 * p.res_stride[2] +
+                             g4 * p.res_stride[3];
+      // residual prefetch: bf16 residuals 64 columns (8 x 16 B) at a time, fp32 residuals 32 columns
+      uint4 rpre[8];
+      const bool res_vec = p.res != nullptr && row_ok && p.col_group >= p.n && (n0 + BN <= p.n);
+      auto prefetch_res = [&](int ch) {
+        if (!res_vec) return;
         if (p.res_fp32) {
-          const float* rp = reinterpret_cast<const float*>(p.res) + rrow + coff;
-          if (full) {
+          const float* rp = reinterpret_cast<const float*>(p.res) + rrow + n0 + ch * 16;
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              float4 t = *reinterpret_cast<const float4*>(rp + j);
-              v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+          for (int j = 0; j < 8; ++j)
+            if (ch * 16 + j * 4 < BN) rpre[j] = *reinterpret_cast<const uint4*>(rp + j * 4);
+        } else {
+          const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + rrow + n0 + ch * 16;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (ch * 16 + j * 8 < BN) rpre[j] = *reinterpret_cast<const uint4*>(rp + j * 8);
+        }
+      };
+      prefetch_res(0);
+      float gsum[8], gsq[8];
+      if (GN) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { gsum[j] = 0.f; gsq[j] = 0.f; }
+      }
+
+      mbar_wait(&acc_full[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + as * kAccCols + (static_cast<uint32_t>(q * 32) << 16);
+      uint32_t raw[2][16];
+      tmem_ld16(taddr, raw[0]);
+#pragma unroll
+      for (int ch = 0; ch < kChunks; ++ch) {
+        tmem_ld_wait();
+        if (ch + 1 < kChunks) tmem_ld16(taddr + (ch + 1) * 16, raw[(ch + 1) & 1]);
+        const int nb = n0 + ch * 16;
+        if (row_ok && nb < p.n) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[ch & 1][j]);
+          const long long coff = static_cast<long long>(nb / p.col_group) * p.col_group_stride + (nb % p.col_group);
+          const bool full = (nb + 16 <= p.n);
+          if (p.bias) {
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              }
+            } else {
+              _Pragma("unroll")
+              for (int j = 0; j < 16; ++j)
+                if (nb + j < p.n) v[j] += __ldg(p.bias + nb + j);
+            }
+          }
+          if (p.res) {
+            if (res_vec) {
+              if (p.res_fp32) {
+                const int j0 = (ch & 1) * 4;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint4 t = rpre[j0 + j];
+                  v[j * 4] += __uint_as_float(t.x); v[j * 4 + 1] += __uint_as_float(t.y);
+                  v[j * 4 + 2] += __uint_as_float(t.z); v[j * 4 + 3] += __uint_as_float(t.w);
+                }
+              } else {
+                const int j0 = (ch & 3) * 2;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                  const uint4 t = rpre[j0 + j];
+                  const float2 a = unpack_bf16(t.x), b = unpack_bf16(t.y), c = unpack_bf16(t.z), d = unpack_bf16(t.w);
+                  v[j * 8] += a.x; v[j * 8 + 1] += a.y; v[j * 8 + 2] += b.x; v[j * 8 + 3] += b.y;
+                  v[j * 8 + 4] += c.x; v[j * 8 + 5] += c.y; v[j * 8 + 6] += d.x; v[j * 8 + 7] += d.y;
+                }
+              }
+            } else if (p.res_fp32) {
+              const float* rp = reinterpret_cast<const float*>(p.res) + rrow + coff;
+              _Pragma("unroll")
+              for (int j = 0; j < 16; ++j)
+                if (nb + j < p.n) v[j] += rp[j];
+            } else {
+              const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + rrow + coff;
+              _Pragma("unroll")
+              for (int j = 0; j < 16; ++j)
+                if (nb + j < p.n) v[j] += __bfloat162float(rp[j]);
+            }
+          }
+          if (p.col_scale) {
+            const float* cs = p.col_scale + static_cast<long long>(g4) * p.n + nb;
+            const float* cb = p.col_shift + static_cast<long long>(g4) * p.n + nb;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (full || nb + j < p.n) v[j] = v[j] * __ldg(cs + j) + __ldg(cb + j);
+          }
+          if (p.act) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
+          }
+          if (p.out_fp32) {
+            float* op = reinterpret_cast<float*>(p.out) + orow + coff;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+              _Pragma("unroll")
+              for (int j = 0; j < 16; ++j)
+                if (nb + j < p.n) op[j] = v[j];
             }
           } else {
-            for (int j = 0; j < 16 && nb + j < p.n; ++j) v[j] += rp[j];
-          }
-        } else {
-          const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + rrow + coff;
-          if (full) {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + orow + coff;
+            if (full) {
+              uint32_t pk[8];
 #pragma unroll
-            for (int j = 0; j < 16; j += 8) {
-              uint4 t = *reinterpret_cast<const uint4*>(rp + j);
-              float2 a = unpack_bf16(t.x), b = unpack_bf16(t.y), c = unpack_bf16(t.z), d = unpack_bf16(t.w);
-              v[j] += a.x; v[j + 1] += a.y; v[j + 2] += b.x; v[j + 3] += b.y;
-              v[j + 4] += c.x; v[j + 5] += c.y; v[j + 6] += d.x; v[j + 7] += d.y;
+              for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+              *reinterpret_cast<uint4*>(op) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              *reinterpret_cast<uint4*>(op + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+              if (GN) {
+                // statistics of the values as stored (bf16-rounded); group width = BN / 8 columns
+                constexpr int kCpg = BN / 8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float2 f = unpack_bf16(pk[j]);
+                  const int g = (ch * 16 + 2 * j) / (kCpg < 2 ? 2 : kCpg);
+                  gsum[g] += f.x + f.y;
+                  gsq[g] += f.x * f.x + f.y * f.y;
+                }
+              }
+            } else {
+              _Pragma("unroll")
+              for (int j = 0; j < 16; ++j)
+                if (nb + j < p.n) op[j] = __float2bfloat16(v[j]);
             }
-          } else {
-            for (int j = 0; j < 16 && nb + j < p.n; ++j) v[j] += __bfloat162float(rp[j]);
           }
         }
-      }
-      if (p.col_scale) {
-        const float* cs = p.col_scale + static_cast<long long>(g4) * p.n + nb;
-        const float* cb = p.col_shift + static_cast<long long>(g4) * p.n + nb;
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (full || nb + j < p.n) v[j] = v[j] * __ldg(cs + j) + __ldg(cb + j);
-      }
-      if (p.act) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
-      }
-      if (p.out_fp32) {
-        float* op = reinterpret_cast<float*>(p.out) + orow + coff;
-        if (full) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4)
-            *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        // next residual group (issued after this chunk's use of rpre)
+        if (p.res_fp32) {
+          if ((ch & 1) == 1 && ch + 1 < kChunks) prefetch_res(ch + 1);
         } else {
-          for (int j = 0; j < 16 && nb + j < p.n; ++j) op[j] = v[j];
+          if ((ch & 3) == 3 && ch + 1 < kChunks) prefetch_res(ch + 1);
         }
-      } else {
-        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + orow + coff;
-        if (full) {
+      }
+      // accumulator drained (all tcgen05.ld completed): hand it back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
+
+      if (GN) {
+        // fixed-order butterfly: 16 per-thread values -> lane l (even) holds the warp total of value index
+        // ((l>>4)&1)*8 + ((l>>3)&1)*4 + ((l>>2)&1)*2 + ((l>>1)&1)
+        float vals[16];
 #pragma unroll
-          for (int j = 0; j < 16; j += 8) {
-            uint4 t;
-            t.x = pack_bf16(v[j], v[j + 1]);
-            t.y = pack_bf16(v[j + 2], v[j + 3]);
-            t.z = pack_bf16(v[j + 4], v[j + 5]);
-            t.w = pack_bf16(v[j + 6], v[j + 7]);
-            *reinterpret_cast<uint4*>(op + j) = t;
+        for (int j = 0; j < 8; ++j) { vals[j] = gsum[j]; vals[8 + j] = gsq[j]; }
+#pragma unroll
+        for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+          const bool up = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < half; ++i) {
+            const float send = up ? vals[i] : vals[i + half];
+            const float keep = up ? vals[i + half] : vals[i];
+            vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
           }
-        } else {
-          for (int j = 0; j < 16 && nb + j < p.n; ++j) op[j] = __float2bfloat16(v[j]);
         }
+        vals[0] += __shfl_xor_sync(0xffffffffu, vals[0], 1);
+        float* sg = s_gn + as * 64;
+        if ((lane & 1) == 0) {
+          const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+          sg[q * 16 + idx] = vals[0];
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (m < 16) p.gn_part[static_cast<long long>(tc.m_tile) * 16 + m] = (sg[m] + sg[16 + m]) + (sg[32 + m] + sg[48 + m]);
       }
     }
   }
@@ -300,23 +427,37 @@ static int encode_a(CUtensorMap* map, const void* base, int channels, const long
   return encode_map(map, base, 5, dims, strides, bx, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
 }
 
-template <int BN, int STAGES>
-static int launch(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb, const GemmDev& dev,
-                  int m_tiles, cudaStream_t stream) {
+static int sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+template <int BN, int STAGES, bool GN>
+static int launch(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb, GemmDev& dev, int m_tiles,
+                  cudaStream_t stream) {
   constexpr int kStageBytes = kATileBytes + BN * kBlockK * 2;
-  constexpr int smem_bytes = STAGES * kStageBytes + (2 * STAGES + 1) * 8 + 16 + 1024;
+  constexpr int smem_bytes = STAGES * kStageBytes + (2 * STAGES + 4) * 8 + 16 + 2 * 4 * 16 * 4 + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, GN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) {
       extdm_set_error(cudaGetErrorString(e), __FILE__, __LINE__);
       return EXTDM_ERR_CUDA;
     }
     configured = true;
   }
-  dim3 grid(m_tiles, (dev.n + BN - 1) / BN);
-  conv_gemm_kernel<BN, STAGES><<<grid, kGemmThreads, smem_bytes, stream>>>(ma0, ma1, mb, dev);
+  dev.n_tiles_n = (dev.n + BN - 1) / BN;
+  dev.total_tiles = m_tiles * dev.n_tiles_n;
+  const int resident = sm_count() * (BN == 256 ? 1 : 2);
+  const int grid = dev.total_tiles < resident ? dev.total_tiles : resident;
+  conv_gemm_kernel<BN, STAGES, GN><<<grid, kGemmThreads, smem_bytes, stream>>>(ma0, ma1, mb, dev);
   EXTDM_CHECK_LAUNCH();
   return EXTDM_OK;
 }
@@ -369,6 +510,7 @@ extern "C" int extdm_conv_gemm(const ExtdmGemm* g, void* stream_) {
   dev.col_scale = g->col_scale;
   dev.col_shift = g->col_shift;
   dev.act = g->act;
+  dev.gn_part = g->gn_partials;
   if ((g->col_scale == nullptr) != (g->col_shift == nullptr)) {
     extdm_set_error("extdm_conv_gemm: col_scale and col_shift go together", __FILE__, __LINE__);
     return EXTDM_ERR_ARG;
@@ -397,10 +539,23 @@ extern "C" int extdm_conv_gemm(const ExtdmGemm* g, void* stream_) {
   rc = encode_map(&mb, g->w, 2, wd, ws, wb, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
   if (rc) return rc;
 
+  if (g->gn_partials) {
+    // per-tile GroupNorm partials: one n-tile covering all channels, 8 groups, bf16 dense rows, tile within a sample
+    if (g->n != bn || bn < 64 || g->out_fp32 || g->col_group < g->n || g->box[3] != 1) {
+      extdm_set_error("extdm_conv_gemm: gn_partials needs n in {64,128,256} (= block_n), bf16 output, box[3] == 1",
+                      __FILE__, __LINE__);
+      return EXTDM_ERR_ARG;
+    }
+    switch (bn) {
+      case 64: return launch<64, 4, true>(ma0, ma1, mb, dev, m_tiles, stream);
+      case 128: return launch<128, 3, true>(ma0, ma1, mb, dev, m_tiles, stream);
+      default: return launch<256, 4, true>(ma0, ma1, mb, dev, m_tiles, stream);
+    }
+  }
   switch (bn) {
-    case 16: return launch<16, 5>(ma0, ma1, mb, dev, m_tiles, stream);
-    case 64: return launch<64, 4>(ma0, ma1, mb, dev, m_tiles, stream);
-    case 128: return launch<128, 3>(ma0, ma1, mb, dev, m_tiles, stream);
-    default: return launch<256, 4>(ma0, ma1, mb, dev, m_tiles, stream);
+    case 16: return launch<16, 5, false>(ma0, ma1, mb, dev, m_tiles, stream);
+    case 64: return launch<64, 4, false>(ma0, ma1, mb, dev, m_tiles, stream);
+    case 128: return launch<128, 3, false>(ma0, ma1, mb, dev, m_tiles, stream);
+    default: return launch<256, 4, false>(ma0, ma1, mb, dev, m_tiles, stream);
   }
 }

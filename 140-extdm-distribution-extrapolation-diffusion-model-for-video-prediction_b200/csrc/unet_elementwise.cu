@@ -19,7 +19,9 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
 }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm
-// Partial sums per (sample, chunk, group): deterministic (no atomics); the apply kernel folds the chunks.
+// Partial sums per (sample, part, group): deterministic (no atomics); the apply kernel folds the parts.
+// Layout (shared with the conv_gemm epilogue's gn_partials): part[(b*n_part + i)*2G + g] = sum,
+// part[(b*n_part + i)*2G + G + g] = sum of squares.
 __global__ void __launch_bounds__(256) groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ x,
                                                               float* __restrict__ part, long long P, int C, int G) {
   const int b = blockIdx.y, chunk = blockIdx.x;
@@ -49,14 +51,14 @@ __global__ void __launch_bounds__(256) groupnorm_stats_kernel(const __nv_bfloat1
       const int slot = static_cast<int>((begin + t) % vecs);
       if (slot / cg8 == static_cast<int>(threadIdx.x)) { a += s_sum[t]; q += s_sq[t]; }
     }
-    float* o = part + ((static_cast<long long>(b) * kGnChunks + chunk) * G + threadIdx.x) * 2;
-    o[0] = a;
-    o[1] = q;
+    float* o = part + (static_cast<long long>(b) * gridDim.x + chunk) * 2 * G;
+    o[threadIdx.x] = a;
+    o[G + threadIdx.x] = q;
   }
 }
 
 __global__ void __launch_bounds__(256) groupnorm_apply_kernel(
-    const __nv_bfloat16* __restrict__ x, const float* __restrict__ part, const float* __restrict__ gamma,
+    const __nv_bfloat16* __restrict__ x, const float* __restrict__ part, int n_part, const float* __restrict__ gamma,
     const float* __restrict__ beta, const float* __restrict__ ss, long long ss_stride, int ss_off,
     const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ y, long long P, int C, int G, float eps) {
   extern __shared__ float s_aff[];         // a[C], d[C]
@@ -64,18 +66,24 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(
   float* s_d = s_aff + C;
   __shared__ float s_mean[64], s_rstd[64];
   const int b = blockIdx.y;
-  if (threadIdx.x < G) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // fold the partial sums: one warp per group, lanes stride over the parts, fixed-order butterfly
+  for (int g = warp; g < G; g += 8) {
     float sum = 0.f, sq = 0.f;
-    for (int c = 0; c < kGnChunks; ++c) {
-      const float* o = part + ((static_cast<long long>(b) * kGnChunks + c) * G + threadIdx.x) * 2;
-      sum += o[0];
-      sq += o[1];
+    for (int i = lane; i < n_part; i += 32) {
+      const float* o = part + (static_cast<long long>(b) * n_part + i) * 2 * G;
+      sum += o[g];
+      sq += o[G + g];
     }
-    const float cnt = static_cast<float>(P) * (C / G);
-    const float mean = sum / cnt;
-    const float var = fmaxf(sq / cnt - mean * mean, 0.f);
-    s_mean[threadIdx.x] = mean;
-    s_rstd[threadIdx.x] = rsqrtf(var + eps);
+    sum = warp_sum(sum);
+    sq = warp_sum(sq);
+    if (lane == 0) {
+      const float cnt = static_cast<float>(P) * (C / G);
+      const float mean = sum / cnt;
+      const float var = fmaxf(sq / cnt - mean * mean, 0.f);
+      s_mean[g] = mean;
+      s_rstd[g] = rsqrtf(var + eps);
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -611,15 +619,16 @@ extern "C" int extdm_groupnorm_stats(const void* x, float* part, int B, long lon
   return EXTDM_OK;
 }
 
-extern "C" int extdm_groupnorm_apply(const void* x, const float* part, const float* gamma, const float* beta,
-                                     const float* ss, long long ss_stride, int ss_off, const void* res, void* y,
-                                     int B, long long P, int C, int G, float eps, void* stream) {
-  if (C % (8 * G) || G > 64) return bad_arg("groupnorm_apply: need C % (8G) == 0");
+extern "C" int extdm_groupnorm_apply(const void* x, const float* part, int n_part, const float* gamma,
+                                     const float* beta, const float* ss, long long ss_stride, int ss_off,
+                                     const void* res, void* y, int B, long long P, int C, int G, float eps,
+                                     void* stream) {
+  if (C % (8 * G) || G > 64 || n_part < 1) return bad_arg("groupnorm_apply: need C % (8G) == 0, n_part >= 1");
   long long per_sample = P * (C / 8);
   int gx = grid_for(per_sample, 256, (148 * 8 + B - 1) / B);
   dim3 grid(gx, B);
-  groupnorm_apply_kernel<<<grid, 256, 2 * C * sizeof(float), STREAM>>>(BF(x), part, gamma, beta, ss, ss_stride, ss_off,
-                                                                     BF(res), BFW(y), P, C, G, eps);
+  groupnorm_apply_kernel<<<grid, 256, 2 * C * sizeof(float), STREAM>>>(BF(x), part, n_part, gamma, beta, ss, ss_stride,
+                                                                     ss_off, BF(res), BFW(y), P, C, G, eps);
   EXTDM_CHECK_LAUNCH();
   return EXTDM_OK;
 }

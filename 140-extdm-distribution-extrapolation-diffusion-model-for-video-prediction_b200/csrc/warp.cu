@@ -184,6 +184,27 @@ __global__ void __launch_bounds__(256) warp_image_kernel(const float* __restrict
   }
 }
 
+// Test/diagnostic view of the index math: per output pixel the resized flow (gx, gy), occlusion, the north-west
+// tap (x0, y0) and the four bilinear weights -- what "warp indexing bit-exact in fp32" is checked on.
+__global__ void __launch_bounds__(256) warp_taps_kernel(const float* __restrict__ flow, const float* __restrict__ occ,
+                                                        int* __restrict__ xy, float* __restrict__ wts,
+                                                        float* __restrict__ gflow, long long F, int H, int W, int h,
+                                                        int w) {
+  const long long total = F * H * W;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int X = i % W;
+    const int Y = (i / W) % H;
+    const long long f = i / (static_cast<long long>(H) * W);
+    float gx, gy, oc;
+    flow_occ_at(flow + f * h * w * 2, occ ? occ + f * h * w : nullptr, h, w, H, W, Y, X, gx, gy, oc);
+    const WarpTaps t = grid_taps(gx, gy, H, W);
+    xy[i * 2] = t.x0; xy[i * 2 + 1] = t.y0;
+    wts[i * 4] = t.nw; wts[i * 4 + 1] = t.ne; wts[i * 4 + 2] = t.sw; wts[i * 4 + 3] = t.se;
+    gflow[i * 3] = gx; gflow[i * 3 + 1] = gy; gflow[i * 3 + 2] = oc;
+  }
+}
+
 }  // namespace extdm
 
 using namespace extdm;
@@ -218,6 +239,18 @@ extern "C" int extdm_warp_image(const float* src, const float* dec, int dec_stri
   }
   warp_image_kernel<<<grid_of(F * H * W, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src, dec, dec_stride, flow, occ, prediction, deformed, F, static_cast<int>(F / Fs), H, W, h, w);
+  EXTDM_CHECK_LAUNCH();
+  return EXTDM_OK;
+}
+
+extern "C" int extdm_warp_taps(const float* flow, const float* occ, int* xy, float* weights, float* gflow, long long F,
+                               int H, int W, int h, int w, void* stream) {
+  if (!flow || !xy || !weights || !gflow) {
+    extdm_set_error("warp_taps: null operand", __FILE__, __LINE__);
+    return EXTDM_ERR_ARG;
+  }
+  warp_taps_kernel<<<grid_of(F * H * W, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(flow, occ, xy, weights,
+                                                                                            gflow, F, H, W, h, w);
   EXTDM_CHECK_LAUNCH();
   return EXTDM_OK;
 }

@@ -26,6 +26,7 @@ class ExtdmGemm(C.Structure):
         ("res", C.c_void_p), ("res_fp32", C.c_int), ("res_base", C.c_longlong), ("res_stride", C.c_longlong * 4),
         ("col_scale", C.c_void_p), ("col_shift", C.c_void_p),
         ("act", C.c_int), ("block_n", C.c_int),
+        ("gn_partials", C.c_void_p),
     ]
 
 
@@ -38,7 +39,7 @@ PROTOTYPES = {
     "extdm_sizeof_gemm": [],
     "extdm_conv_gemm": [C.POINTER(ExtdmGemm), _P],
     "extdm_groupnorm_stats": [_P, _P, _I, _L, _I, _I, _P],
-    "extdm_groupnorm_apply": [_P, _P, _P, _P, _P, _L, _I, _P, _P, _I, _L, _I, _I, _F, _P],
+    "extdm_groupnorm_apply": [_P, _P, _I, _P, _P, _P, _L, _I, _P, _P, _I, _L, _I, _I, _F, _P],
     "extdm_chan_layernorm": [_P, _L, _I, _P, _L, _I, _P, _P, _L, _L, _F, _P],
     "extdm_temporal_prenorm": [_P, _P, _P, _P, _P, _P, _L, _I, _F, _P],
     "extdm_adaptor_workspace_floats": [_I, _I],
@@ -50,12 +51,13 @@ PROTOTYPES = {
     "extdm_head_project": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "extdm_window_attention": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "extdm_stw_fused_supported": [_I, _I, _I, _I, _I, _I],
-    "extdm_stw_fused": [_P, _P, _P, _P, _P, _P, _P, _P, _P] + [_I] * 14 + [_F, _P],
+    "extdm_stw_fused": [_P, _P, _P, _P, _P, _P, _P, _P, _P] + [_I] * 13 + [_F, _P],
     "extdm_temporal_attention": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "extdm_ddim_threshold": [_P, _P, _F, _F, _F, _P, _I, _I, _P],
     "extdm_ddim_update": [_P, _P, _P, _P, _F, _F, _F, _F, _F, _P, _P, _I, _I, _P],
     "extdm_warp_blend_cl": [_P, _P, _P, _P, _P, _L, _L, _I, _I, _I, _I, _I, _I, _P],
     "extdm_warp_image": [_P, _P, _I, _P, _P, _P, _P, _L, _L, _I, _I, _I, _I, _P],
+    "extdm_warp_taps": [_P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
     "extdm_bn_relu_cl": [_P, _P, _P, _P, _L, _I, _P],
     "extdm_avgpool2_cl": [_P, _P, _L, _I, _I, _I, _P],
     "extdm_im2col7_image": [_P, _P, _L, _I, _I, _P],

@@ -132,7 +132,7 @@ def std_box(H, W):
 def gemm(rec, *, a0, c0, dims, strides0, box, start, count, taps, w, n, out, out_stride, out_base=0,
          a1=None, c1=0, strides1=None, out_fp32=False, col_group=None, col_group_stride=0, bias=None,
          res=None, res_fp32=False, res_base=0, res_stride=None, col_scale=None, col_shift=None, act=0,
-         block_n=0):
+         block_n=0, gn_partials=None):
     """Generic launch of extdm_conv_gemm.  dims/strides: extents and element strides of D1..D4 of the A
     tensor(s); box/start/count: tile geometry; taps: list of (o1,o2,o3)."""
     g = _lib.ExtdmGemm()
@@ -162,12 +162,14 @@ def gemm(rec, *, a0, c0, dims, strides0, box, start, count, taps, w, n, out, out
     g.col_scale = 0 if col_scale is None else col_scale.data_ptr()
     g.col_shift = 0 if col_shift is None else col_shift.data_ptr()
     g.act, g.block_n = act, block_n
+    g.gn_partials = 0 if gn_partials is None else gn_partials.data_ptr()
     rows = count[0] * count[1] * count[2] * count[3]
     ktot = len(taps) * (c0 + (c1 if a1 is not None else 0))
     meta = dict(flops=2.0 * rows * n * ktot, rows=rows, n=n, k=ktot, taps=len(taps),
                 bytes=2.0 * rows * (c0 + (c1 if a1 is not None else 0)) + 2.0 * n * ktot
                 + rows * n * (4.0 if out_fp32 else 2.0))
-    rec.emit("extdm_conv_gemm", (C.byref(g),), keep=(g, a0, a1, w, out, bias, res, col_scale, col_shift), meta=meta)
+    rec.emit("extdm_conv_gemm", (C.byref(g),), keep=(g, a0, a1, w, out, bias, res, col_scale, col_shift, gn_partials),
+             meta=meta)
 
 
 def linear_rows(rec, x, w, n, out, *, bias=None, res=None, res_fp32=False, act=0, out_fp32=False, x2=None,
@@ -185,7 +187,7 @@ def linear_rows(rec, x, w, n, out, *, bias=None, res=None, res_fp32=False, act=0
 
 def conv_cl(rec, x, w, n, k, out, *, x2=None, bias=None, res=None, res_fp32=False, act=0, out_fp32=False,
             t_range=None, col_scale=None, col_shift=None, out_t_offset=0, res_t_offset=0, taps=None,
-            out_scale=1, out_phase=(0, 0), block_n=0):
+            out_scale=1, out_phase=(0, 0), block_n=0, gn_partials=None):
     """k x k 'same' convolution over channels-last x (B, T, H, W, C) [channel-concatenated with x2].
     out: (B, To, Ho, Wo, n') with n' >= n.  t_range=(t0, t1) restricts the frames computed; the output
     frame index is t + out_t_offset.  out_scale/out_phase write a strided output (ConvTranspose phases)."""
@@ -208,19 +210,33 @@ def conv_cl(rec, x, w, n, k, out, *, x2=None, bias=None, res=None, res_fp32=Fals
          box=(bw, bh, bt, 1), start=(0, 0, t0, 0), count=(W, H, t1 - t0, B),
          taps=taps if taps is not None else conv_taps(k), w=w, n=n, out=out, out_stride=ostr, out_base=obase,
          out_fp32=out_fp32, bias=bias, res=res, res_fp32=res_fp32, res_base=rbase, res_stride=rstr,
-         col_scale=col_scale, col_shift=col_shift, act=act, block_n=block_n)
+         col_scale=col_scale, col_shift=col_shift, act=act, block_n=block_n, gn_partials=gn_partials)
+
+
+def conv_tiles_per_sample(T, H, W):
+    """Number of 128-row GEMM tiles conv_cl cuts one sample's (T, H, W) volume into (= GroupNorm partials per sample)."""
+    bw, bh, bt = std_box(H, W)
+    return -(-W // bw) * -(-H // bh) * -(-T // bt)
+
+
+GN_CHUNKS = 32          # EXTDM_GN_CHUNKS
 
 
 # ----------------------------------------------------------------------------- normalisation etc.
-def groupnorm_silu(rec, x, stats_ws, gamma, beta, y, *, groups=8, scale_shift=None, ss_off=0, res=None, eps=1e-5):
-    """x, y, res: (B, P..., C) bf16 channels-last.  stats_ws: float32 workspace >= B*32*groups*2."""
+def groupnorm_silu(rec, x, stats_ws, gamma, beta, y, *, groups=8, scale_shift=None, ss_off=0, res=None, eps=1e-5,
+                   n_part=None):
+    """x, y, res: (B, P..., C) bf16 channels-last.  With n_part=None the statistics are computed here
+    (stats_ws: float32 workspace >= B*32*groups*2); otherwise stats_ws already holds n_part partial sums per sample
+    written by the producing convolution's epilogue (conv_cl(..., gn_partials=stats_ws))."""
     B, Cc = x.shape[0], x.shape[-1]
     P = x.numel() // (B * Cc)
-    rec.emit("extdm_groupnorm_stats", (_p(x), _p(stats_ws), B, P, Cc, groups), keep=(x, stats_ws))
+    if n_part is None:
+        rec.emit("extdm_groupnorm_stats", (_p(x), _p(stats_ws), B, P, Cc, groups), keep=(x, stats_ws))
+        n_part = GN_CHUNKS
     ss_stride = 0 if scale_shift is None else scale_shift.shape[1]
-    rec.emit("extdm_groupnorm_apply", (_p(x), _p(stats_ws), _p(gamma), _p(beta), _p(scale_shift), ss_stride, ss_off,
-                                       _p(res), _p(y), B, P, Cc, groups, C.c_float(eps)),
-             keep=(x, gamma, beta, scale_shift, res, y))
+    rec.emit("extdm_groupnorm_apply", (_p(x), _p(stats_ws), n_part, _p(gamma), _p(beta), _p(scale_shift), ss_stride,
+                                       ss_off, _p(res), _p(y), B, P, Cc, groups, C.c_float(eps)),
+             keep=(x, stats_ws, gamma, beta, scale_shift, res, y), meta=dict(bytes=(6.0 if res is not None else 4.0) * x.numel(), tag=f"C={Cc} P={P}"))
 
 
 def chan_layernorm(rec, x, gamma, y, *, x2=None, t_range=None, t2_range=None, eps=1e-5):
@@ -296,7 +312,8 @@ def window_attention(rec, qkv, out, bias_table, rcos, rsin, heads, dh, window, s
     B, T, H, W, _ = qkv.shape
     rec.emit("extdm_window_attention", (_p(qkv), _p(out), _p(bias_table), _p(rcos), _p(rsin), B, T, H, W, heads, dh,
                                         window[0], window[1], window[2], shift[0], shift[1], shift[2]),
-             keep=(qkv, out, bias_table, rcos, rsin))
+             keep=(qkv, out, bias_table, rcos, rsin), meta=dict(bytes=8.0 * heads * dh * B * T * H * W,
+                                                                tag=f"hid={heads * dh} {T}x{H}x{W}"))
 
 
 def stw_fused_supported(C_, heads, dh, window):
@@ -309,7 +326,7 @@ def stw_fused(rec, x, y, gamma, wqkv, wproj, proj_bias, bias_table, rcos, rsin, 
                                  _p(rcos), _p(rsin), B, T, H, W, Cc, heads, dh, window[0], window[1], window[2],
                                  shift[0], shift[1], shift[2], C.c_float(eps)),
              keep=(x, y, gamma, wqkv, wproj, proj_bias, bias_table, rcos, rsin),
-             meta=dict(bytes=4.0 * x.numel()))
+             meta=dict(bytes=4.0 * x.numel(), tag=f"C={Cc} {T}x{H}x{W}"))
 
 
 def temporal_attention(rec, qkv, out, rel_bias, rcos, rsin, heads, dh):
@@ -348,6 +365,17 @@ def warp_image(rec, src, dec, flow, occ, prediction, deformed):
     dstride = 0 if dec is None else dec.shape[-1]
     rec.emit("extdm_warp_image", (_p(src), _p(dec), dstride, _p(flow), _p(occ), _p(prediction), _p(deformed), F, Fs,
                                   H, W, h, w), keep=(src, dec, flow, occ, prediction, deformed))
+
+
+def warp_taps(rec, flow, occ, H, W):
+    """Index math of the warp kernels as tensors: (xy int32 (F,H,W,2), weights (F,H,W,4), gflow (F,H,W,3))."""
+    F, h, w = flow.shape[:3]
+    xy = torch.empty(F, H, W, 2, dtype=torch.int32, device=flow.device)
+    wts = torch.empty(F, H, W, 4, dtype=torch.float32, device=flow.device)
+    gf = torch.empty(F, H, W, 3, dtype=torch.float32, device=flow.device)
+    rec.emit("extdm_warp_taps", (_p(flow), _p(occ), _p(xy), _p(wts), _p(gf), F, H, W, h, w),
+             keep=(flow, occ, xy, wts, gf))
+    return xy, wts, gf
 
 
 def bn_relu_cl(rec, x, scale, shift, y):

@@ -123,7 +123,7 @@ class UnetRunner:
         self.cond_fea = torch.zeros(B, 256, T, fea_hw, fea_hw, **f32)
         self.time = torch.zeros(B, dtype=torch.long, device=dev)
         self.out = torch.zeros(B, 3, tp, H, W, **f32)
-        self.gn_ws = torch.zeros(B * 32 * cfg.groups * 2, **f32)
+        self.gn_ws = torch.zeros(B * max(32, ops.conv_tiles_per_sample(T, H, W)) * cfg.groups * 2, **f32)
         self.ss = torch.zeros(B, packed.n_ss, **f32)
         self.prologue = ops.Recorder(record=True)
         self.step = ops.Recorder(record=True)
@@ -180,12 +180,18 @@ class UnetRunner:
         cfg, pk = self.cfg, self.pk
         B, T, H, W, _ = x.shape
         h1 = self.buf(B, T, H, W, cout)
-        ops.conv_cl(rec, x, pk.w[p + ".block1.proj.weight"], cout, 3, h1, x2=x2, bias=pk.f32[p + ".block1.proj.bias"])
+        # GroupNorm statistics come out of the convolution's epilogue (per-tile partial sums), not a second pass
+        fused = cfg.groups == 8 and cout in (64, 128, 256)
+        npart = ops.conv_tiles_per_sample(T, H, W) if fused else None
+        gnp = self.gn_ws if fused else None
+        ops.conv_cl(rec, x, pk.w[p + ".block1.proj.weight"], cout, 3, h1, x2=x2, bias=pk.f32[p + ".block1.proj.bias"],
+                    gn_partials=gnp)
         ops.groupnorm_silu(rec, h1, self.gn_ws, pk.f32[p + ".block1.norm.weight"], pk.f32[p + ".block1.norm.bias"], h1,
                            groups=cfg.groups, scale_shift=self.ss if time else None,
-                           ss_off=pk.ss_off[p] if time else 0)
+                           ss_off=pk.ss_off[p] if time else 0, n_part=npart)
         h2 = self.buf(B, T, H, W, cout)
-        ops.conv_cl(rec, h1, pk.w[p + ".block2.proj.weight"], cout, 3, h2, bias=pk.f32[p + ".block2.proj.bias"])
+        ops.conv_cl(rec, h1, pk.w[p + ".block2.proj.weight"], cout, 3, h2, bias=pk.f32[p + ".block2.proj.bias"],
+                    gn_partials=gnp)
         if (p + ".res_conv.weight") in pk.w:
             r = self.buf(B, T, H, W, cout)
             ops.conv_cl(rec, x, pk.w[p + ".res_conv.weight"], cout, 1, r, x2=x2, bias=pk.f32[p + ".res_conv.bias"])
@@ -193,7 +199,7 @@ class UnetRunner:
             r = x
         y = self.buf(B, T, H, W, cout)
         ops.groupnorm_silu(rec, h2, self.gn_ws, pk.f32[p + ".block2.norm.weight"], pk.f32[p + ".block2.norm.bias"], y,
-                           groups=cfg.groups, res=r)
+                           groups=cfg.groups, res=r, n_part=npart)
         return y
 
     def _adaptor(self, rec, x, p):

@@ -68,6 +68,11 @@ typedef struct ExtdmGemm {
   const float* col_shift;
   int act; /* 0 none, 1 relu, 2 silu, 3 sigmoid */
   int block_n; /* 0 = choose automatically (16/64/128/256) */
+  /* Optional GroupNorm(8) statistics of the stored (bf16) output, fused into the epilogue: per 128-row tile t (tiles
+   * ordered D1 fastest .. D4 slowest, so a sample's tiles are contiguous) 16 floats gn_partials[t*16 + g] = sum and
+   * [t*16 + 8 + g] = sum of squares over the tile's rows and the n/8 channels of group g.  Requires n == block_n in
+   * {64,128,256}, bf16 output, box[3] == 1.  Consumed by extdm_groupnorm_apply (n_part = tiles per sample). */
+  float* gn_partials;
 } ExtdmGemm;
 
 int extdm_conv_gemm(const ExtdmGemm* g, void* stream);
@@ -79,15 +84,19 @@ int extdm_sizeof_gemm(void);
  */
 
 /* GroupNorm statistics: per (sample, group) sum and sum of squares over (T,H,W,C/G), as EXTDM_GN_CHUNKS
- * deterministic partial sums.  x: (B, P, C) bf16 with P = T*H*W.  stats: (B, EXTDM_GN_CHUNKS, G, 2) fp32.
- * Reference: nn.GroupNorm in Block.forward, ...cross_multi.py:166-171. */
+ * deterministic partial sums.  x: (B, P, C) bf16 with P = T*H*W.  stats: (B, EXTDM_GN_CHUNKS, 2, G) fp32
+ * (sums then sums of squares).  Reference: nn.GroupNorm in Block.forward, ...cross_multi.py:166-171.
+ * (The UNet runner does not launch this: its convolutions emit the same partials from their epilogue,
+ * ExtdmGemm.gn_partials.) */
 #define EXTDM_GN_CHUNKS 32
 int extdm_groupnorm_stats(const void* x, float* stats, int B, long long P, int C, int G, void* stream);
 
 /* GroupNorm apply + optional (scale+1, shift) + SiLU (+ residual).  ...cross_multi.py:170-178, :203.
  * y = silu(gn(x)*gamma+beta [* (scale[b,c]+1) + shift[b,c]]) [+ res].  scale_shift: (B, ss_stride) fp32 rows,
- * scale at [ss_off + c], shift at [ss_off + C + c]; may be NULL.  x, res, y: (B, P, C) bf16; in-place allowed. */
-int extdm_groupnorm_apply(const void* x, const float* stats, const float* gamma, const float* beta,
+ * scale at [ss_off + c], shift at [ss_off + C + c]; may be NULL.  x, res, y: (B, P, C) bf16; in-place allowed.
+ * stats: (B, n_part, 2, G) partial sums from extdm_groupnorm_stats (n_part = EXTDM_GN_CHUNKS) or from a
+ * convolution's gn_partials (n_part = 128-row tiles per sample). */
+int extdm_groupnorm_apply(const void* x, const float* stats, int n_part, const float* gamma, const float* beta,
                           const float* scale_shift, long long ss_stride, int ss_off, const void* res, void* y,
                           int B, long long P, int C, int G, float eps, void* stream);
 
@@ -199,6 +208,13 @@ int extdm_warp_blend_cl(const void* skip, const void* prev, const float* flow, c
 int extdm_warp_image(const float* src, const float* dec, int dec_stride, const float* flow, const float* occ,
                      float* prediction, float* deformed, long long F, long long Fs, int H, int W, int h, int w,
                      void* stream);
+
+/* Diagnostic view of the warp index math used by the two kernels above (generator.py:63-71 + ATen GridSampler /
+ * UpSampleBilinear2d): for every pixel of the (H, W) target, the resized flow and occlusion gflow (F,H,W,3) =
+ * (gx, gy, occ), the north-west tap xy (F,H,W,2) = (x0, y0) and the bilinear weights (F,H,W,4) = (nw, ne, sw, se).
+ * Parity tests compare these bit-for-bit with the fp32 oracle. */
+int extdm_warp_taps(const float* flow, const float* occ, int* xy, float* weights, float* gflow, long long F, int H,
+                    int W, int h, int w, void* stream);
 
 /* Eval-mode BatchNorm + ReLU on channels-last bf16 (ResBlock2d pre-activation, util.py:83-89):
  * y = relu(x*scale[c] + shift[c]). */

@@ -475,6 +475,64 @@ def warp(inp, flow):
     return F.grid_sample(inp, flow, align_corners=True)
 
 
+def warp_index_math(flow, occ, H, W):
+    """numpy fp32 restatement (no FMA contraction) of the index arithmetic under deform_input / apply_optical:
+    F.interpolate(bilinear, align_corners=False) of flow (F,h,w,2) and occ (F,1,h,w) to (H,W)  [ATen
+    UpSampleBilinear2d: src = max(0, scale*(dst+0.5)-0.5), h0*(w0*a + w1*b) + h1*(w0*c + w1*d)], then the
+    F.grid_sample(align_corners=True) tap computation [ATen GridSampler: ix = ((x+1)/2)*(W-1), floor, weights
+    nw=(x1-ix)(y1-iy) ...].  Returns (xy int32 (F,H,W,2), weights (F,H,W,4), gflow (F,H,W,3))."""
+    import numpy as np
+    f32 = np.float32
+    fl = flow.detach().cpu().numpy().astype(f32)
+    Fn, h, w = fl.shape[:3]
+    oc = None if occ is None else occ.detach().cpu().numpy().astype(f32).reshape(Fn, h, w)
+
+    def src_index(n_out, n_in):
+        scale = f32(n_in) / f32(n_out)
+        s = scale * (np.arange(n_out, dtype=f32) + f32(0.5)) - f32(0.5)
+        s = np.maximum(s, f32(0))
+        i0 = s.astype(np.int32)
+        i1 = i0 + (i0 < n_in - 1)
+        l1 = (s - i0.astype(f32)).astype(f32)
+        return i0, i1, (f32(1) - l1).astype(f32), l1
+
+    def resize(plane):                      # (F,h,w) -> (F,H,W)
+        if h == H and w == W:
+            return plane
+        y0, y1, ly0, ly1 = src_index(H, h)
+        x0, x1, lx0, lx1 = src_index(W, w)
+        a, b = plane[:, y0][:, :, x0], plane[:, y0][:, :, x1]
+        c, d = plane[:, y1][:, :, x0], plane[:, y1][:, :, x1]
+        top = (lx0[None, None] * a + lx1[None, None] * b).astype(f32)
+        bot = (lx0[None, None] * c + lx1[None, None] * d).astype(f32)
+        return (ly0[None, :, None] * top + ly1[None, :, None] * bot).astype(f32)
+
+    gx, gy = resize(fl[..., 0]), resize(fl[..., 1])
+    go = np.ones_like(gx) if oc is None else resize(oc)
+    ix = ((gx + f32(1)) * f32(0.5)) * f32(W - 1)
+    iy = ((gy + f32(1)) * f32(0.5)) * f32(H - 1)
+    fx, fy = np.floor(ix), np.floor(iy)
+    ex, ey = (fx + f32(1)) - ix, (fy + f32(1)) - iy
+    wx, wy = ix - fx, iy - fy
+    wts = np.stack([ex * ey, wx * ey, ex * wy, wx * wy], -1).astype(f32)
+    xy = np.stack([fx.astype(np.int32), fy.astype(np.int32)], -1)
+    return torch.from_numpy(xy), torch.from_numpy(wts), torch.from_numpy(np.stack([gx, gy, go], -1).astype(f32))
+
+
+def warp_from_taps(inp, xy, wts):
+    """grid_sample(bilinear, zeros) evaluated from precomputed taps, ATen accumulation order nw, ne, sw, se."""
+    Fn, Cc, H, W = inp.shape
+    out = torch.zeros(Fn, Cc, H, W)
+    x0, y0 = xy[..., 0].long(), xy[..., 1].long()
+    fi = torch.arange(Fn)[:, None, None].expand(Fn, H, W)
+    for k, (dx, dy) in enumerate(((0, 0), (1, 0), (0, 1), (1, 1))):
+        xs, ys = x0 + dx, y0 + dy
+        ok = (xs >= 0) & (xs < W) & (ys >= 0) & (ys < H)
+        v = inp[fi, :, ys.clamp(0, H - 1), xs.clamp(0, W - 1)]           # (F,H,W,C)
+        out = out + (v * (wts[..., k] * ok)[..., None]).permute(0, 3, 1, 2)
+    return out
+
+
 def _blend(prev, skip, flow, occ):
     """apply_optical, generator.py:74-93."""
     skip = warp(skip, flow)

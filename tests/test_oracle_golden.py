@@ -80,3 +80,22 @@ def test_quantile_rank_is_fp32():
     w = pos - lo
     ref = torch.lerp(srt[:, lo], srt[:, lo + 1], w).clamp(min=1.0)
     assert torch.equal(s.flatten(), ref)
+
+
+@pytest.mark.parametrize("h,H", [(32, 64), (32, 32), (32, 16)])
+def test_warp_index_oracle_vs_aten(h, H):
+    """The numpy fp32 index-math oracle (what the CUDA warp kernels are compared with bit-for-bit) against ATen's
+    F.interpolate + F.grid_sample on CPU: identical up to the 1-ulp FMA-contraction difference of the flow resize."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(3)
+    flow = (torch.rand(2, h, h, 2, generator=g) * 2 - 1) * 1.2
+    occ = torch.rand(2, 1, h, h, generator=g)
+    src = torch.rand(2, 3, H, H, generator=g)
+    xy, wts, gf = O.warp_index_math(flow, occ, H, H)
+    fl = F.interpolate(flow.permute(0, 3, 1, 2), size=(H, H), mode="bilinear").permute(0, 2, 3, 1) if h != H else flow
+    oc = F.interpolate(occ, size=(H, H), mode="bilinear") if h != H else occ
+    assert (gf[..., :2] - fl).abs().max().item() <= 2.5e-7
+    assert (gf[..., 2] - oc[:, 0]).abs().max().item() <= 2.5e-7
+    ref = F.grid_sample(src, fl, align_corners=True)
+    got = O.warp_from_taps(src, xy, wts)
+    assert (got - ref).abs().max().item() <= (2e-5 if h != H else 5e-7)

@@ -30,7 +30,7 @@ for label, rec, mult in (("prologue", runner.prologue, 1), ("step", runner.step,
         if name == "extdm_conv_gemm":
             key = (label, f"gemm rows={meta['rows']} n={meta['n']} k={meta['k']} taps={meta['taps']}")
         else:
-            key = (label, name.replace("extdm_", ""))
+            key = (label, name.replace("extdm_", "") + (" " + meta["tag"] if "tag" in meta else ""))
         r = rows.setdefault(key, dict(ms=0.0, n=0, flops=0.0, bytes=0.0))
         r["ms"] += ms * mult
         r["n"] += mult

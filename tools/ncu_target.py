@@ -33,7 +33,7 @@ for label, rec in (("prologue", runner.prologue), ("step", runner.step), ("decod
         if name == "extdm_conv_gemm":
             key = f"{label} gemm rows={meta['rows']} n={meta['n']} k={meta['k']} taps={meta['taps']}"
         else:
-            key = f"{label} {name.replace('extdm_', '')}"
+            key = f"{label} {name.replace('extdm_', '')}" + (" " + meta["tag"] if "tag" in meta else "")
         launches.append((key, fn, a))
 stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 for want in args.keys:
@@ -41,7 +41,7 @@ for want in args.keys:
     if not hit:
         print("no launch matches", want)
         continue
-    key, fn, a = hit[len(hit) // 2]
+    key, fn, a = hit[0]
     fn(*a, stream)                       # warm (un-profiled)
     torch.cuda.synchronize()
     torch.cuda.profiler.start()
