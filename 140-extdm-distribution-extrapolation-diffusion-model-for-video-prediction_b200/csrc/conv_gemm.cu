@@ -196,6 +196,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                              g4 * p.out_stride[3];
       const long long rrow = p.res_base + g1 * p.res_stride[0] + g2 * p.res_stride[1] + g3 * p.res_stride[2] +
                              g4 * p.res_stride[3];
+      // The accumulator is drained in groups of 4 chunks (64 columns): the group body is unrolled (static register
+      // indices for the double-buffered tcgen05.ld and the prefetched residual), the group loop is not (code size).
       // residual prefetch: bf16 residuals 64 columns (8 x 16 B) at a time, fp32 residuals 32 columns
       uint4 rpre[8];
       const bool res_vec = p.res != nullptr && row_ok && p.col_group >= p.n && (n0 + BN <= p.n);
@@ -214,126 +216,159 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
         }
       };
       prefetch_res(0);
-      float gsum[8], gsq[8];
-      if (GN) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { gsum[j] = 0.f; gsq[j] = 0.f; }
-      }
 
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * kAccCols + (static_cast<uint32_t>(q * 32) << 16);
+      float* sg = s_gn + as * 64;
       uint32_t raw[2][16];
       tmem_ld16(taddr, raw[0]);
+      constexpr int kGroups = (kChunks + 3) / 4;
+      constexpr int kCpg = BN >= 64 ? BN / 8 : 8;          // GroupNorm(8) group width in columns
+      constexpr int kNV = 2 * (64 / kCpg);                 // statistics per 64-column group (sums, sums of squares)
+#pragma unroll 1
+      for (int grp = 0; grp < kGroups; ++grp) {
+        float gst[kNV];
+        if (GN) {
 #pragma unroll
-      for (int ch = 0; ch < kChunks; ++ch) {
-        tmem_ld_wait();
-        if (ch + 1 < kChunks) tmem_ld16(taddr + (ch + 1) * 16, raw[(ch + 1) & 1]);
-        const int nb = n0 + ch * 16;
-        if (row_ok && nb < p.n) {
-          float v[16];
+          for (int j = 0; j < kNV; ++j) gst[j] = 0.f;
+        }
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[ch & 1][j]);
-          const long long coff = static_cast<long long>(nb / p.col_group) * p.col_group_stride + (nb % p.col_group);
-          const bool full = (nb + 16 <= p.n);
-          if (p.bias) {
-            if (full) {
+        for (int c = 0; c < 4; ++c) {
+          if (c < kChunks) {
+            const int ch = grp * 4 + c;
+            tmem_ld_wait();
+            if (ch + 1 < kChunks) tmem_ld16(taddr + (ch + 1) * 16, raw[(c + 1) & 1]);
+            const int nb = n0 + ch * 16;
+            if (row_ok && nb < p.n) {
+              float v[16];
 #pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
-                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[c & 1][j]);
+              const long long coff =
+                  static_cast<long long>(nb / p.col_group) * p.col_group_stride + (nb % p.col_group);
+              const bool full = (nb + 16 <= p.n);
+              if (p.bias) {
+                if (full) {
+#pragma unroll
+                  for (int j = 0; j < 16; j += 4) {
+                    const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
+                    v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j)
+                    if (nb + j < p.n) v[j] += __ldg(p.bias + nb + j);
+                }
               }
-            } else {
-              _Pragma("unroll")
-              for (int j = 0; j < 16; ++j)
-                if (nb + j < p.n) v[j] += __ldg(p.bias + nb + j);
-            }
-          }
-          if (p.res) {
-            if (res_vec) {
-              if (p.res_fp32) {
-                const int j0 = (ch & 1) * 4;
+              if (p.res) {
+                if (res_vec) {
+                  if (p.res_fp32) {
+                    const int j0 = (c & 1) * 4;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const uint4 t = rpre[j0 + j];
-                  v[j * 4] += __uint_as_float(t.x); v[j * 4 + 1] += __uint_as_float(t.y);
-                  v[j * 4 + 2] += __uint_as_float(t.z); v[j * 4 + 3] += __uint_as_float(t.w);
+                    for (int j = 0; j < 4; ++j) {
+                      const uint4 t = rpre[j0 + j];
+                      v[j * 4] += __uint_as_float(t.x); v[j * 4 + 1] += __uint_as_float(t.y);
+                      v[j * 4 + 2] += __uint_as_float(t.z); v[j * 4 + 3] += __uint_as_float(t.w);
+                    }
+                  } else {
+                    const int j0 = c * 2;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                      const uint4 t = rpre[j0 + j];
+                      const float2 a = unpack_bf16(t.x), b2 = unpack_bf16(t.y), c2 = unpack_bf16(t.z),
+                                   d2 = unpack_bf16(t.w);
+                      v[j * 8] += a.x; v[j * 8 + 1] += a.y; v[j * 8 + 2] += b2.x; v[j * 8 + 3] += b2.y;
+                      v[j * 8 + 4] += c2.x; v[j * 8 + 5] += c2.y; v[j * 8 + 6] += d2.x; v[j * 8 + 7] += d2.y;
+                    }
+                  }
+                } else if (p.res_fp32) {
+                  const float* rp = reinterpret_cast<const float*>(p.res) + rrow + coff;
+#pragma unroll
+                  for (int j = 0; j < 16; ++j)
+                    if (nb + j < p.n) v[j] += rp[j];
+                } else {
+                  const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + rrow + coff;
+#pragma unroll
+                  for (int j = 0; j < 16; ++j)
+                    if (nb + j < p.n) v[j] += __bfloat162float(rp[j]);
+                }
+              }
+              if (p.col_scale) {
+                const float* cs = p.col_scale + static_cast<long long>(g4) * p.n + nb;
+                const float* cb = p.col_shift + static_cast<long long>(g4) * p.n + nb;
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (full || nb + j < p.n) v[j] = v[j] * __ldg(cs + j) + __ldg(cb + j);
+              }
+              if (p.act) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
+              }
+              if (p.out_fp32) {
+                float* op = reinterpret_cast<float*>(p.out) + orow + coff;
+                if (full) {
+#pragma unroll
+                  for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j)
+                    if (nb + j < p.n) op[j] = v[j];
                 }
               } else {
-                const int j0 = (ch & 3) * 2;
+                __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + orow + coff;
+                if (full) {
+                  uint32_t pk[8];
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                  const uint4 t = rpre[j0 + j];
-                  const float2 a = unpack_bf16(t.x), b = unpack_bf16(t.y), c = unpack_bf16(t.z), d = unpack_bf16(t.w);
-                  v[j * 8] += a.x; v[j * 8 + 1] += a.y; v[j * 8 + 2] += b.x; v[j * 8 + 3] += b.y;
-                  v[j * 8 + 4] += c.x; v[j * 8 + 5] += c.y; v[j * 8 + 6] += d.x; v[j * 8 + 7] += d.y;
+                  for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+                  *reinterpret_cast<uint4*>(op) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                  *reinterpret_cast<uint4*>(op + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                  if (GN) {
+                    // statistics of the values as stored (bf16-rounded)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                      const float2 f = unpack_bf16(pk[j]);
+                      const int g = (c * 16 + 2 * j) / kCpg;           // GroupNorm group within this 64-column group
+                      gst[g] += f.x + f.y;
+                      gst[kNV / 2 + g] += f.x * f.x + f.y * f.y;
+                    }
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j)
+                    if (nb + j < p.n) op[j] = __float2bfloat16(v[j]);
                 }
               }
-            } else if (p.res_fp32) {
-              const float* rp = reinterpret_cast<const float*>(p.res) + rrow + coff;
-              _Pragma("unroll")
-              for (int j = 0; j < 16; ++j)
-                if (nb + j < p.n) v[j] += rp[j];
-            } else {
-              const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + rrow + coff;
-              _Pragma("unroll")
-              for (int j = 0; j < 16; ++j)
-                if (nb + j < p.n) v[j] += __bfloat162float(rp[j]);
             }
-          }
-          if (p.col_scale) {
-            const float* cs = p.col_scale + static_cast<long long>(g4) * p.n + nb;
-            const float* cb = p.col_shift + static_cast<long long>(g4) * p.n + nb;
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (full || nb + j < p.n) v[j] = v[j] * __ldg(cs + j) + __ldg(cb + j);
-          }
-          if (p.act) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
-          }
-          if (p.out_fp32) {
-            float* op = reinterpret_cast<float*>(p.out) + orow + coff;
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 16; j += 4)
-                *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            // next residual group (issued after this chunk's use of rpre)
+            if (p.res_fp32) {
+              if ((c & 1) == 1 && ch + 1 < kChunks) prefetch_res(ch + 1);
             } else {
-              _Pragma("unroll")
-              for (int j = 0; j < 16; ++j)
-                if (nb + j < p.n) op[j] = v[j];
-            }
-          } else {
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + orow + coff;
-            if (full) {
-              uint32_t pk[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
-              *reinterpret_cast<uint4*>(op) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              *reinterpret_cast<uint4*>(op + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-              if (GN) {
-                // statistics of the values as stored (bf16-rounded); group width = BN / 8 columns
-                constexpr int kCpg = BN / 8;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float2 f = unpack_bf16(pk[j]);
-                  const int g = (ch * 16 + 2 * j) / (kCpg < 2 ? 2 : kCpg);
-                  gsum[g] += f.x + f.y;
-                  gsq[g] += f.x * f.x + f.y * f.y;
-                }
-              }
-            } else {
-              _Pragma("unroll")
-              for (int j = 0; j < 16; ++j)
-                if (nb + j < p.n) op[j] = __float2bfloat16(v[j]);
+              if (c == 3 && ch + 1 < kChunks) prefetch_res(ch + 1);
             }
           }
         }
-        // next residual group (issued after this chunk's use of rpre)
-        if (p.res_fp32) {
-          if ((ch & 1) == 1 && ch + 1 < kChunks) prefetch_res(ch + 1);
-        } else {
-          if ((ch & 3) == 3 && ch + 1 < kChunks) prefetch_res(ch + 1);
+        if (GN) {
+          // fixed-order butterfly over the warp: kNV per-thread values -> one total per value, held by the lanes
+          // whose high bits spell the value index (MSB first); lanes with zero low bits publish it.
+          int idx = 0, off = 16;
+#pragma unroll
+          for (int half = kNV / 2; half >= 1; half >>= 1, off >>= 1) {
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < half; ++i) {
+              const float send = up ? gst[i] : gst[i + half];
+              const float keep = up ? gst[i + half] : gst[i];
+              gst[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+            idx = idx * 2 + (up ? 1 : 0);
+          }
+          const int low_mask = 2 * off - 1;                 // offsets not consumed by the transposing steps
+          for (; off >= 1; off >>= 1) gst[0] += __shfl_xor_sync(0xffffffffu, gst[0], off);
+          if ((lane & low_mask) == 0) {
+            const int stat = idx / (kNV / 2), gl = idx % (kNV / 2);       // 0 = sum, 1 = sum of squares
+            sg[q * 16 + stat * 8 + grp * (kNV / 2) + gl] = gst[0];
+          }
         }
       }
       // accumulator drained (all tcgen05.ld completed): hand it back to the MMA issuer
@@ -342,29 +377,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
       if (lane == 0) mbar_arrive(&acc_empty[as]);
 
       if (GN) {
-        // fixed-order butterfly: 16 per-thread values -> lane l (even) holds the warp total of value index
-        // ((l>>4)&1)*8 + ((l>>3)&1)*4 + ((l>>2)&1)*2 + ((l>>1)&1)
-        float vals[16];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { vals[j] = gsum[j]; vals[8 + j] = gsq[j]; }
-#pragma unroll
-        for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
-          const bool up = (lane & off) != 0;
-#pragma unroll
-          for (int i = 0; i < half; ++i) {
-            const float send = up ? vals[i] : vals[i + half];
-            const float keep = up ? vals[i + half] : vals[i];
-            vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-          }
-        }
-        vals[0] += __shfl_xor_sync(0xffffffffu, vals[0], 1);
-        float* sg = s_gn + as * 64;
-        if ((lane & 1) == 0) {
-          const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-          sg[q * 16 + idx] = vals[0];
-        }
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (m < 16) p.gn_part[static_cast<long long>(tc.m_tile) * 16 + m] = (sg[m] + sg[16 + m]) + (sg[32 + m] + sg[48 + m]);
+        if (m < 16)
+          p.gn_part[static_cast<long long>(tc.m_tile) * 16 + m] = (sg[m] + sg[16 + m]) + (sg[32 + m] + sg[48 + m]);
       }
     }
   }
