@@ -4,12 +4,16 @@
 // :409-497 (WindowAttention3D), :499-560 (STWAttentionLayer: pad / roll / partition / mask / reverse).
 //
 // Un-fused, one layer moves x, LN(x), qkv (6x the size of x), attn-out and y through HBM (~21x |x| of traffic);
-// fused, it reads x once and writes y once.  Persistent CTAs (one per SM) keep Wqkv / Wproj / the bias table in
-// shared memory and loop over windows; the next window's tokens are prefetched with cp.async while the current
-// one is computed.  One warp per head: K/V/Q projections, rotary, QK^T, mask + bias, softmax and PV stay in
-// registers (mma.sync m16n8k16 bf16, accumulator->operand fragment re-use); only V, the head outputs and the
-// projected tile pass through shared memory.  (64-token x 64..128-channel tiles are below a tcgen05 tile of
-// M = 128 rows per CTA; the window is the natural unit, so the warp-level tensor path is used here.)
+// fused, it reads x once and writes y once.  Persistent CTAs (one per SM) loop over windows; the next window's
+// tokens are prefetched with cp.async while the current one is computed.  One warp per head:
+//   * the head's Wq/Wk/Wv tiles live in REGISTERS as mma B-fragments for the whole kernel (loop-invariant),
+//   * Q/K/V projections, rotary, QK^T, bias (+ shift mask), softmax and PV stay in registers
+//     (mma.sync m16n8k16 bf16, accumulator -> operand fragment re-use, ldmatrix for every smem operand),
+//   * the relative-position bias is expanded once per CTA into a [head][query][key] bf16 matrix (pre-multiplied by
+//     log2 e) that ldmatrix delivers directly in accumulator layout: it initialises the score accumulators,
+//   * the -100 shift mask is a 64-bit "different region" word per query row built with 8 ballots per window.
+// (64-token x 64..128-channel tiles are below a tcgen05 tile of M = 128 rows per CTA and the score work is
+// MUFU/issue bound, not MMA bound -- 537 M exponentials per level-0 launch -- so the warp-level tensor path is used.)
 #include "common.cuh"
 #include "../../include/extdm_b200.h"
 
@@ -21,6 +25,16 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes)
                : "memory");
@@ -28,6 +42,14 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_b
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// bf16 pair (packed) -> two floats, one ALU op each
+__device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
 struct StwParams {
   const __nv_bfloat16* x;
@@ -39,41 +61,47 @@ struct StwParams {
   const float* bias_table;     // [tbl_n][heads]
   const float* rcos;
   const float* rsin;           // [NTOK][DH/2]
-  int B, T, H, W, wd, wh, ww, sd, sh, sw, Dp, n_windows;
+  int B, T, H, W, sd, sh, sw, Dp, n_windows;
   float eps;
 };
+
+constexpr float kLog2e = 1.4426950408889634f;
 
 template <int NTOK, int DH, int C>
 struct StwSmem {
   static constexpr int HEADS = 8;
   static constexpr int HID = HEADS * DH;
-  static constexpr int XP = C + 8;        // pitch (bf16) of token x channel tiles
+  static constexpr int XP = C + 8;        // pitch (bf16) of token x channel tiles (16 B skew: conflict-free ldmatrix)
   static constexpr int HP = HID + 8;      // pitch of token x hidden tiles
-  static constexpr size_t wqkv = 0;
-  static constexpr size_t wproj = wqkv + size_t(3 * HID) * XP * 2;
-  static constexpr bool DB = (C <= 64);   // double-buffered token prefetch when it fits in 227 KB
-  static constexpr size_t raw = wproj + size_t(C) * HP * 2;            // (DB ? 2 : 1) x [NTOK][C] raw tokens (cp.async)
-  static constexpr size_t xn = raw + (DB ? 2 : 1) * size_t(NTOK) * C * 2;   // [NTOK][XP] normalised tokens / staging
-  static constexpr size_t v = xn + size_t(NTOK) * XP * 2;              // [NTOK][HP]
-  static constexpr size_t o = v + size_t(NTOK) * HP * 2;               // [NTOK][HP]
-  static constexpr size_t rope = o + size_t(NTOK) * HP * 2;            // cos, sin [NTOK][DH/2] fp32
-  static constexpr size_t misc = rope + 2 * size_t(NTOK) * (DH / 2) * 4;   // gamma[C], pbias[C]
-  static constexpr size_t idx = misc + 2 * size_t(C) * 4;              // 2 x { src[NTOK] (int), lin[NTOK], reg[NTOK] }
-  static constexpr size_t tbl = idx + 2 * 3 * size_t(NTOK) * 4;        // [HEADS][tbl_n] fp32 (dynamic length)
+  static constexpr int BP = NTOK + 8;     // pitch of the bias matrix rows
+  static constexpr size_t wproj = 0;                                          // [C][HP]
+  static constexpr size_t bias = wproj + size_t(C) * HP * 2;                  // [HEADS][NTOK][BP] bf16
+  static constexpr size_t raw = bias + size_t(HEADS) * NTOK * BP * 2;         // 2 x [NTOK][XP] raw tokens (cp.async)
+  static constexpr size_t xn = raw + 2 * size_t(NTOK) * XP * 2;               // [NTOK][XP] normalised tokens / staging
+  static constexpr size_t v = xn + size_t(NTOK) * XP * 2;                     // [NTOK][HP]
+  static constexpr size_t o = v + size_t(NTOK) * HP * 2;                      // [NTOK][HP]
+  static constexpr size_t rope = o + size_t(NTOK) * HP * 2;                   // cos, sin [NTOK][DH/2] fp32
+  static constexpr size_t misc = rope + 2 * size_t(NTOK) * (DH / 2) * 4;      // gamma[C], pbias[C]
+  static constexpr size_t emask = misc + 2 * size_t(C) * 4;                   // [2][8] u32 region-membership words
+  static constexpr size_t total = emask + 2 * 8 * 4;
 };
 
 template <int NTOK, int DH, int C>
 __global__ void __launch_bounds__(256, 1) stw_fused_kernel(const __grid_constant__ StwParams p) {
   using L = StwSmem<NTOK, DH, C>;
-  constexpr int HEADS = 8, HID = L::HID, XP = L::XP, HP = L::HP;
+  constexpr int HEADS = 8, HID = L::HID, XP = L::XP, HP = L::HP, BP = L::BP;
+  constexpr int WD = NTOK / 16;          // window = (WD, 4, 4)
   constexpr int MT = NTOK / 16;          // query / token m-tiles
   constexpr int DT = DH / 8;             // n-tiles over the head dim
   constexpr int KS = DH / 16;            // k-steps of Q K^T
   constexpr int NT = NTOK / 8;           // key n-tiles
   constexpr int CK = C / 16;             // k-steps of the projections from C
+  constexpr int TPT = 256 / NTOK;        // threads per token in the LayerNorm / copy phases
+  constexpr int CPT = C / TPT;           // channels per thread there
+  static_assert(CPT % 8 == 0, "LayerNorm slice must be a multiple of 8 channels");
   extern __shared__ __align__(16) uint8_t sm[];
-  __nv_bfloat16* s_wqkv = reinterpret_cast<__nv_bfloat16*>(sm + L::wqkv);
   __nv_bfloat16* s_wproj = reinterpret_cast<__nv_bfloat16*>(sm + L::wproj);
+  __nv_bfloat16* s_bias = reinterpret_cast<__nv_bfloat16*>(sm + L::bias);
   __nv_bfloat16* s_raw = reinterpret_cast<__nv_bfloat16*>(sm + L::raw);
   __nv_bfloat16* s_xn = reinterpret_cast<__nv_bfloat16*>(sm + L::xn);
   __nv_bfloat16* s_v = reinterpret_cast<__nv_bfloat16*>(sm + L::v);
@@ -82,232 +110,224 @@ __global__ void __launch_bounds__(256, 1) stw_fused_kernel(const __grid_constant
   float* s_sin = s_cos + NTOK * (DH / 2);
   float* s_gamma = reinterpret_cast<float*>(sm + L::misc);
   float* s_pbias = s_gamma + C;
-  int* s_idx = reinterpret_cast<int*>(sm + L::idx);
-  float* s_tbl = reinterpret_cast<float*>(sm + L::tbl);
+  uint32_t* s_E = reinterpret_cast<uint32_t*>(sm + L::emask);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
-  const int tbl_n = (2 * p.wd - 1) * (2 * p.wh - 1) * (2 * p.ww - 1);
   const bool shifted = (p.sd | p.sh | p.sw) != 0;
-  const int nWw = p.W / p.ww, nWh = p.H / p.wh, nWd = p.Dp / p.wd;
+  const int nWw = p.W / 4, nWh = p.H / 4, nWd = p.Dp / WD;
+  // ldmatrix row/column offsets of this lane inside a 16x16 tile
+  const int lrow = lane & 15, lcol = (lane >> 4) * 8;
 
-  // ---- one-time staging of the weights and tables
-  for (int i = tid; i < 3 * HID * (C / 8); i += 256) {
-    const int r = i / (C / 8), c8 = i % (C / 8);
-    *reinterpret_cast<uint4*>(s_wqkv + r * XP + c8 * 8) = *reinterpret_cast<const uint4*>(p.wqkv + r * C + c8 * 8);
-  }
+  // ---- one-time staging: proj weights, tables, the expanded bias matrix, this warp's Wq/Wk/Wv fragments
   for (int i = tid; i < C * (HID / 8); i += 256) {
     const int r = i / (HID / 8), c8 = i % (HID / 8);
     *reinterpret_cast<uint4*>(s_wproj + r * HP + c8 * 8) = *reinterpret_cast<const uint4*>(p.wproj + r * HID + c8 * 8);
   }
-  for (int i = tid; i < HEADS * tbl_n; i += 256) s_tbl[i] = p.bias_table[(i % tbl_n) * HEADS + i / tbl_n];
   for (int i = tid; i < NTOK * (DH / 2); i += 256) { s_cos[i] = p.rcos[i]; s_sin[i] = p.rsin[i]; }
   for (int i = tid; i < C; i += 256) { s_gamma[i] = p.gamma[i]; s_pbias[i] = p.proj_bias[i]; }
-
-  // per-window token bookkeeping (source pixel, bias-table linear index, mask region) into buffer `buf`
-  auto index_window = [&](int widx, int buf) {
-    if (tid < NTOK) {
-      int* src = s_idx + buf * 3 * NTOK;
-      int* lin = src + NTOK;
-      int* reg = lin + NTOK;
-      int w_ = widx;
-      const int iw = w_ % nWw; w_ /= nWw;
-      const int ih = w_ % nWh; w_ /= nWh;
-      const int id = w_ % nWd; w_ /= nWd;
-      const int b = w_;
-      const int n = tid;
-      const int tw = n % p.ww, th = (n / p.ww) % p.wh, td = n / (p.ww * p.wh);
-      lin[n] = (td * (2 * p.wh - 1) + th) * (2 * p.ww - 1) + tw;
-      const int zd = id * p.wd + td, zh = ih * p.wh + th, zw = iw * p.ww + tw;
-      int rd = 0, rh = 0, rw = 0;
-      if (p.sd) rd = zd < p.Dp - p.wd ? 0 : (zd < p.Dp - p.sd ? 1 : 2);
-      if (p.sh) rh = zh < p.H - p.wh ? 0 : (zh < p.H - p.sh ? 1 : 2);
-      if (p.sw) rw = zw < p.W - p.ww ? 0 : (zw < p.W - p.sw ? 1 : 2);
-      reg[n] = (rd * 3 + rh) * 3 + rw;
-      const int od = (zd + p.sd) % p.Dp, oh = (zh + p.sh) % p.H, ow = (zw + p.sw) % p.W;
-      src[n] = od < p.T ? ((b * p.T + od) * p.H + oh) * p.W + ow : -1;
+  for (int i = tid; i < HEADS * NTOK * NTOK; i += 256) {
+    const int j = i % NTOK, q = (i / NTOK) % NTOK, h = i / (NTOK * NTOK);
+    const int rel = (((q >> 4) - (j >> 4) + WD - 1) * 7 + (((q >> 2) & 3) - ((j >> 2) & 3) + 3)) * 7 +
+                    ((q & 3) - (j & 3) + 3);
+    s_bias[(h * NTOK + q) * BP + j] = __float2bfloat16(p.bias_table[rel * HEADS + h] * kLog2e);
+  }
+  const int head = warp;
+  uint32_t wq[CK][DT][2], wk[CK][DT][2], wv[CK][DT][2];
+#pragma unroll
+  for (int ks = 0; ks < CK; ++ks)
+#pragma unroll
+    for (int dt = 0; dt < DT; ++dt) {
+      const int row = head * DH + dt * 8 + g, col = ks * 16 + tg * 2;
+      const __nv_bfloat16* bq = p.wqkv + static_cast<long long>(row) * C + col;
+      const __nv_bfloat16* bk = p.wqkv + static_cast<long long>(HID + row) * C + col;
+      const __nv_bfloat16* bv = p.wqkv + static_cast<long long>(2 * HID + row) * C + col;
+      wq[ks][dt][0] = *reinterpret_cast<const uint32_t*>(bq);
+      wq[ks][dt][1] = *reinterpret_cast<const uint32_t*>(bq + 8);
+      wk[ks][dt][0] = *reinterpret_cast<const uint32_t*>(bk);
+      wk[ks][dt][1] = *reinterpret_cast<const uint32_t*>(bk + 8);
+      wv[ks][dt][0] = *reinterpret_cast<const uint32_t*>(bv);
+      wv[ks][dt][1] = *reinterpret_cast<const uint32_t*>(bv + 8);
     }
+
+  // window bookkeeping (all arithmetic, no shared state): source pixel of token n of window widx, or -1 (T padding)
+  struct Win { int b, id, ih, iw; };
+  auto decode = [&](int widx) {
+    Win w;
+    w.iw = widx % nWw; widx /= nWw;
+    w.ih = widx % nWh; widx /= nWh;
+    w.id = widx % nWd;
+    w.b = widx / nWd;
+    return w;
   };
-  auto prefetch_window = [&](int buf) {
-    const int* src = s_idx + buf * 3 * NTOK;
-    __nv_bfloat16* dst = s_raw + buf * NTOK * C;
+  auto src_pixel = [&](const Win& w, int n) -> int {
+    int od = w.id * WD + (n >> 4) + p.sd, oh = w.ih * 4 + ((n >> 2) & 3) + p.sh, ow = w.iw * 4 + (n & 3) + p.sw;
+    if (od >= p.Dp) od -= p.Dp;
+    if (oh >= p.H) oh -= p.H;
+    if (ow >= p.W) ow -= p.W;
+    return od < p.T ? ((w.b * p.T + od) * p.H + oh) * p.W + ow : -1;
+  };
+  // mask region code of token n: one bit per shifted dim, set for the wrapped part of the last window slab
+  auto region_code = [&](const Win& w, int n) -> int {
+    int c = 0;
+    if (p.sd && w.id == nWd - 1 && (n >> 4) >= WD - p.sd) c |= 1;
+    if (p.sh && w.ih == nWh - 1 && ((n >> 2) & 3) >= 4 - p.sh) c |= 2;
+    if (p.sw && w.iw == nWw - 1 && (n & 3) >= 4 - p.sw) c |= 4;
+    return c;
+  };
+  auto prefetch_window = [&](const Win& w, int buf) {
+    __nv_bfloat16* dst = s_raw + buf * NTOK * XP;
     for (int i = tid; i < NTOK * (C / 8); i += 256) {
       const int n = i / (C / 8), c8 = i % (C / 8);
-      const int s = src[n];
-      cp_async16(dst + n * C + c8 * 8, p.x + (s >= 0 ? static_cast<long long>(s) * C + c8 * 8 : 0), s >= 0 ? 16 : 0);
+      const int s = src_pixel(w, n);
+      cp_async16(dst + n * XP + c8 * 8, p.x + (s >= 0 ? static_cast<long long>(s) * C + c8 * 8 : 0), s >= 0 ? 16 : 0);
     }
     cp_async_commit();
   };
 
   int widx = blockIdx.x;
   int buf = 0;
-  if (widx < p.n_windows) index_window(widx, 0);
-  __syncthreads();
-  if (widx < p.n_windows) prefetch_window(0);
+  if (widx < p.n_windows) prefetch_window(decode(widx), 0);
 
-  const float qscale = rsqrtf(static_cast<float>(DH));
-  const int c0_tbl = ((p.wd - 1) * (2 * p.wh - 1) + (p.wh - 1)) * (2 * p.ww - 1) + (p.ww - 1);
+  const float qscale = rsqrtf(static_cast<float>(DH)) * kLog2e;
+  constexpr float kMask = -100.0f * kLog2e;
 
-  constexpr bool DB = L::DB;
   for (; widx < p.n_windows; widx += gridDim.x) {
+    const Win win = decode(widx);
     const int nxt = widx + gridDim.x;
-    if (DB && nxt < p.n_windows) index_window(nxt, buf ^ 1);
     cp_async_wait<0>();
-    __syncthreads();                                       // raw[buf] landed; idx[buf^1] visible
-    if (DB && nxt < p.n_windows) prefetch_window(buf ^ 1);
-    const int* s_src = s_idx + buf * 3 * NTOK;
-    const int* s_lin = s_src + NTOK;
-    const int* s_reg = s_lin + NTOK;
-    const __nv_bfloat16* raw = s_raw + buf * NTOK * C;
+    __syncthreads();                                       // S1: raw[buf] landed; previous window fully retired
+    if (nxt < p.n_windows) prefetch_window(decode(nxt), buf ^ 1);
+    const __nv_bfloat16* raw = s_raw + buf * NTOK * XP;
+    const bool has_mask = shifted && ((p.sd && win.id == nWd - 1) || (p.sh && win.ih == nWh - 1) ||
+                                      (p.sw && win.iw == nWw - 1));
 
-    // ---- channel LayerNorm (biased variance, gamma only); padding tokens stay exactly zero
-    for (int n = warp; n < NTOK; n += 8) {
-      constexpr int V = C / 32;
-      float v[V];
-      if constexpr (V == 2) {
-        const float2 t = unpack_bf16(*reinterpret_cast<const uint32_t*>(raw + n * C + lane * 2));
-        v[0] = t.x; v[1] = t.y;
-      } else {
-        const uint2 t = *reinterpret_cast<const uint2*>(raw + n * C + lane * 4);
-        const float2 a = unpack_bf16(t.x), b = unpack_bf16(t.y);
-        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    // ---- region-membership words: E[c] bit j = (code_j == c); query row i masks the keys in ~E[code_i]
+    if (has_mask && warp < NTOK / 32) {
+      const int code = region_code(win, warp * 32 + lane);
+      uint32_t mine = 0;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t bal = __ballot_sync(0xffffffffu, code == c);
+        if (lane == c) mine = bal;
+      }
+      if (lane < 8) s_E[warp * 8 + lane] = mine;
+    }
+
+    // ---- channel LayerNorm (biased variance, gamma only); TPT threads per token; padding tokens stay exactly zero
+    {
+      const int n = tid / TPT, part = tid % TPT;
+      float v[CPT];
+#pragma unroll
+      for (int k = 0; k < CPT; k += 8) {
+        const uint4 t = *reinterpret_cast<const uint4*>(raw + n * XP + part * CPT + k);
+        const float2 a = unpack_bf16(t.x), b = unpack_bf16(t.y), c = unpack_bf16(t.z), d = unpack_bf16(t.w);
+        v[k] = a.x; v[k + 1] = a.y; v[k + 2] = b.x; v[k + 3] = b.y;
+        v[k + 4] = c.x; v[k + 5] = c.y; v[k + 6] = d.x; v[k + 7] = d.y;
       }
       float sum = 0.f;
 #pragma unroll
-      for (int j = 0; j < V; ++j) sum += v[j];
-      const float mean = warp_sum(sum) * (1.0f / C);
+      for (int j = 0; j < CPT; ++j) sum += v[j];
+#pragma unroll
+      for (int o = 1; o < TPT; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float mean = sum * (1.0f / C);
       float sq = 0.f;
 #pragma unroll
-      for (int j = 0; j < V; ++j) { const float d = v[j] - mean; sq += d * d; }
-      const float rstd = s_src[n] >= 0 ? rsqrtf(warp_sum(sq) * (1.0f / C) + p.eps) : 0.f;
+      for (int j = 0; j < CPT; ++j) { const float d = v[j] - mean; sq += d * d; }
 #pragma unroll
-      for (int j = 0; j < V; ++j) v[j] = (v[j] - mean) * rstd * s_gamma[lane * V + j];
-      if constexpr (V == 2) {
-        *reinterpret_cast<uint32_t*>(s_xn + n * XP + lane * 2) = pack_bf16(v[0], v[1]);
-      } else {
-        uint2 t;
-        t.x = pack_bf16(v[0], v[1]); t.y = pack_bf16(v[2], v[3]);
-        *reinterpret_cast<uint2*>(s_xn + n * XP + lane * 4) = t;
+      for (int o = 1; o < TPT; o <<= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      const float rstd = src_pixel(win, n) >= 0 ? rsqrtf(sq * (1.0f / C) + p.eps) : 0.f;
+#pragma unroll
+      for (int k = 0; k < CPT; k += 8) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = part * CPT + k + 2 * j;
+          pk[j] = pack_bf16((v[k + 2 * j] - mean) * rstd * s_gamma[c], (v[k + 2 * j + 1] - mean) * rstd * s_gamma[c + 1]);
+        }
+        *reinterpret_cast<uint4*>(s_xn + n * XP + part * CPT + k) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
     }
-    __syncthreads();
+    __syncthreads();                                       // S2: s_xn, s_E ready
 
-    // ---- per-head projections: K, V for every token (registers), then Q per m-tile
-    const int head = warp;
-    const __nv_bfloat16* wq = s_wqkv + (head * DH) * XP;
-    const __nv_bfloat16* wk = s_wqkv + (HID + head * DH) * XP;
-    const __nv_bfloat16* wv = s_wqkv + (2 * HID + head * DH) * XP;
+    // ---- per-head projections (Wq/Wk/Wv fragments from registers): K -> B fragments, V -> smem, Q -> A fragments
     uint32_t kfrag[NT][KS][2];
-    {
-      float ak[MT][DT][4], av[MT][DT][4];
+    uint32_t qa[MT][KS][4];
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-        for (int dt = 0; dt < DT; ++dt)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { ak[mt][dt][j] = 0.f; av[mt][dt][j] = 0.f; }
-#pragma unroll
-      for (int ks = 0; ks < CK; ++ks) {
-        uint32_t bk[DT][2], bv[DT][2];
-#pragma unroll
-        for (int dt = 0; dt < DT; ++dt) {
-          const __nv_bfloat16* rk = wk + (dt * 8 + g) * XP + ks * 16 + tg * 2;
-          const __nv_bfloat16* rv = wv + (dt * 8 + g) * XP + ks * 16 + tg * 2;
-          bk[dt][0] = *reinterpret_cast<const uint32_t*>(rk);
-          bk[dt][1] = *reinterpret_cast<const uint32_t*>(rk + 8);
-          bv[dt][0] = *reinterpret_cast<const uint32_t*>(rv);
-          bv[dt][1] = *reinterpret_cast<const uint32_t*>(rv + 8);
-        }
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          uint32_t a[4];
-          const __nv_bfloat16* xr = s_xn + (mt * 16 + g) * XP + ks * 16 + tg * 2;
-          a[0] = *reinterpret_cast<const uint32_t*>(xr);
-          a[1] = *reinterpret_cast<const uint32_t*>(xr + 8 * XP);
-          a[2] = *reinterpret_cast<const uint32_t*>(xr + 8);
-          a[3] = *reinterpret_cast<const uint32_t*>(xr + 8 * XP + 8);
-#pragma unroll
-          for (int dt = 0; dt < DT; ++dt) {
-            mma16816(ak[mt][dt], a, bk[dt][0], bk[dt][1]);
-            mma16816(av[mt][dt], a, bv[dt][0], bv[dt][1]);
-          }
-        }
-      }
-      // rotary on K (pair = the two accumulator columns a thread owns), K -> B fragments, V -> smem
-#pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-#pragma unroll
-        for (int dt = 0; dt < DT; ++dt) {
-          const int pr = dt * 4 + tg;
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            const int tok = mt * 16 + hf * 8 + g;
-            const float c = s_cos[tok * (DH / 2) + pr], s = s_sin[tok * (DH / 2) + pr];
-            const float x0 = ak[mt][dt][hf * 2], x1 = ak[mt][dt][hf * 2 + 1];
-            // B fragment of key n-tile (2*mt + hf): k-step dt/2, register dt%2
-            kfrag[2 * mt + hf][dt / 2][dt % 2] = pack_bf16(x0 * c - x1 * s, x1 * c + x0 * s);
-            *reinterpret_cast<uint32_t*>(s_v + tok * HP + head * DH + dt * 8 + tg * 2) =
-                pack_bf16(av[mt][dt][hf * 2], av[mt][dt][hf * 2 + 1]);
-          }
-        }
-      }
-    }
-    __syncwarp();
-    const float* tb = s_tbl + head * tbl_n;
-    const unsigned short* Vs = reinterpret_cast<const unsigned short*>(s_v + head * DH);
-#pragma unroll 1
     for (int mt = 0; mt < MT; ++mt) {
-      float aq[DT][4];
+      float aq[DT][4], ak[DT][4], av[DT][4];
 #pragma unroll
-      for (int dt = 0; dt < DT; ++dt) { aq[dt][0] = aq[dt][1] = aq[dt][2] = aq[dt][3] = 0.f; }
+      for (int dt = 0; dt < DT; ++dt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { aq[dt][j] = 0.f; ak[dt][j] = 0.f; av[dt][j] = 0.f; }
 #pragma unroll
       for (int ks = 0; ks < CK; ++ks) {
         uint32_t a[4];
-        const __nv_bfloat16* xr = s_xn + (mt * 16 + g) * XP + ks * 16 + tg * 2;
-        a[0] = *reinterpret_cast<const uint32_t*>(xr);
-        a[1] = *reinterpret_cast<const uint32_t*>(xr + 8 * XP);
-        a[2] = *reinterpret_cast<const uint32_t*>(xr + 8);
-        a[3] = *reinterpret_cast<const uint32_t*>(xr + 8 * XP + 8);
+        ldsm_x4(a, s_xn + (mt * 16 + lrow) * XP + ks * 16 + lcol);
 #pragma unroll
         for (int dt = 0; dt < DT; ++dt) {
-          const __nv_bfloat16* rq = wq + (dt * 8 + g) * XP + ks * 16 + tg * 2;
-          mma16816(aq[dt], a, *reinterpret_cast<const uint32_t*>(rq), *reinterpret_cast<const uint32_t*>(rq + 8));
+          mma16816(aq[dt], a, wq[ks][dt][0], wq[ks][dt][1]);
+          mma16816(ak[dt], a, wk[ks][dt][0], wk[ks][dt][1]);
+          mma16816(av[dt], a, wv[ks][dt][0], wv[ks][dt][1]);
         }
       }
-      const int r0 = mt * 16 + g, r1 = r0 + 8;
-      uint32_t qa[KS][4];
+      // rotary on Q and K (pair = the two accumulator columns a thread owns)
 #pragma unroll
       for (int dt = 0; dt < DT; ++dt) {
         const int pr = dt * 4 + tg;
-        const float c0 = s_cos[r0 * (DH / 2) + pr], s0 = s_sin[r0 * (DH / 2) + pr];
-        const float c1 = s_cos[r1 * (DH / 2) + pr], s1 = s_sin[r1 * (DH / 2) + pr];
-        const float x0 = aq[dt][0] * qscale, x1 = aq[dt][1] * qscale, y0 = aq[dt][2] * qscale, y1 = aq[dt][3] * qscale;
-        // A fragment of k-step dt/2: registers (dt%2)*2 + {0: row g, 1: row g+8}
-        qa[dt / 2][(dt % 2) * 2 + 0] = pack_bf16(x0 * c0 - x1 * s0, x1 * c0 + x0 * s0);
-        qa[dt / 2][(dt % 2) * 2 + 1] = pack_bf16(y0 * c1 - y1 * s1, y1 * c1 + y0 * s1);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int tok = mt * 16 + hf * 8 + g;
+          const float c = s_cos[tok * (DH / 2) + pr], s = s_sin[tok * (DH / 2) + pr];
+          const float k0 = ak[dt][hf * 2], k1 = ak[dt][hf * 2 + 1];
+          // B fragment of key n-tile (2*mt + hf): k-step dt/2, register dt%2
+          kfrag[2 * mt + hf][dt / 2][dt % 2] = pack_bf16(k0 * c - k1 * s, k1 * c + k0 * s);
+          const float q0 = aq[dt][hf * 2] * qscale, q1 = aq[dt][hf * 2 + 1] * qscale;
+          // A fragment of k-step dt/2: registers (dt%2)*2 + {0: row g, 1: row g+8}
+          qa[mt][dt / 2][(dt % 2) * 2 + hf] = pack_bf16(q0 * c - q1 * s, q1 * c + q0 * s);
+          *reinterpret_cast<uint32_t*>(s_v + tok * HP + head * DH + dt * 8 + tg * 2) =
+              pack_bf16(av[dt][hf * 2], av[dt][hf * 2 + 1]);
+        }
       }
+    }
+    __syncwarp();                                          // this head's V columns are read back by this warp only
+
+    const __nv_bfloat16* bias_h = s_bias + head * NTOK * BP;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const int r0 = mt * 16 + g, r1 = r0 + 8;
+      // scores start from the bias matrix (ldmatrix delivers it in accumulator layout), then += Q K^T
       float s[NT][4];
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks) mma16816(s[nt], qa[ks], kfrag[nt][ks][0], kfrag[nt][ks][1]);
+      for (int np = 0; np < NT / 2; ++np) {
+        uint32_t bb[4];
+        ldsm_x4(bb, bias_h + (mt * 16 + lrow) * BP + np * 16 + lcol);
+        s[2 * np][0] = bf_lo(bb[0]); s[2 * np][1] = bf_hi(bb[0]);
+        s[2 * np][2] = bf_lo(bb[1]); s[2 * np][3] = bf_hi(bb[1]);
+        s[2 * np + 1][0] = bf_lo(bb[2]); s[2 * np + 1][1] = bf_hi(bb[2]);
+        s[2 * np + 1][2] = bf_lo(bb[3]); s[2 * np + 1][3] = bf_hi(bb[3]);
       }
-      const int li0 = s_lin[r0] + c0_tbl, li1 = s_lin[r1] + c0_tbl, rg0 = s_reg[r0], rg1 = s_reg[r1];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) mma16816(s[nt], qa[mt][ks], kfrag[nt][ks][0], kfrag[nt][ks][1]);
+      if (has_mask) {
+        const int c0 = region_code(win, r0), c1 = region_code(win, r1);
+        uint32_t e0[NTOK / 32], e1[NTOK / 32];
+#pragma unroll
+        for (int w = 0; w < NTOK / 32; ++w) { e0[w] = ~s_E[w * 8 + c0]; e1[w] = ~s_E[w * 8 + c1]; }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const int bit = (nt * 8) % 32 + tg * 2;
+          const uint32_t m0 = e0[nt / 4] >> bit, m1 = e1[nt / 4] >> bit;
+          if (m0 & 1) s[nt][0] += kMask;
+          if (m0 & 2) s[nt][1] += kMask;
+          if (m1 & 1) s[nt][2] += kMask;
+          if (m1 & 2) s[nt][3] += kMask;
+        }
+      }
       float m0 = -3.0e38f, m1 = -3.0e38f;
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int j = nt * 8 + tg * 2 + e;
-          const int lj = s_lin[j], rj = s_reg[j];
-          float b0 = tb[li0 - lj], b1 = tb[li1 - lj];
-          if (shifted) {
-            if (rg0 != rj) b0 += -100.0f;
-            if (rg1 != rj) b1 += -100.0f;
-          }
-          s[nt][e] += b0;
-          s[nt][2 + e] += b1;
-        }
         m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
         m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
       }
@@ -318,10 +338,10 @@ __global__ void __launch_bounds__(256, 1) stw_fused_kernel(const __grid_constant
       float l0 = 0.f, l1 = 0.f;
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
-        s[nt][0] = __expf(s[nt][0] - m0);
-        s[nt][1] = __expf(s[nt][1] - m0);
-        s[nt][2] = __expf(s[nt][2] - m1);
-        s[nt][3] = __expf(s[nt][3] - m1);
+        s[nt][0] = fast_exp2(s[nt][0] - m0);
+        s[nt][1] = fast_exp2(s[nt][1] - m0);
+        s[nt][2] = fast_exp2(s[nt][2] - m1);
+        s[nt][3] = fast_exp2(s[nt][3] - m1);
         l0 += s[nt][0] + s[nt][1];
         l1 += s[nt][2] + s[nt][3];
       }
@@ -340,15 +360,13 @@ __global__ void __launch_bounds__(256, 1) stw_fused_kernel(const __grid_constant
         a[1] = pack_bf16(s[2 * ps][2], s[2 * ps][3]);
         a[2] = pack_bf16(s[2 * ps + 1][0], s[2 * ps + 1][1]);
         a[3] = pack_bf16(s[2 * ps + 1][2], s[2 * ps + 1][3]);
-        const int k0 = ps * 16 + tg * 2;
 #pragma unroll
-        for (int dt = 0; dt < DT; ++dt) {
-          const int col = dt * 8 + g;
-          const uint32_t b0 = static_cast<uint32_t>(Vs[k0 * HP + col]) |
-                              (static_cast<uint32_t>(Vs[(k0 + 1) * HP + col]) << 16);
-          const uint32_t b1 = static_cast<uint32_t>(Vs[(k0 + 8) * HP + col]) |
-                              (static_cast<uint32_t>(Vs[(k0 + 9) * HP + col]) << 16);
-          mma16816(o[dt], a, b0, b1);
+        for (int dp = 0; dp < DT / 2; ++dp) {
+          // V^T fragments: tokens ps*16..+15 (k) x head dims dp*16..+15 (n), transposed on the fly by ldmatrix
+          uint32_t vb[4];
+          ldsm_x4_trans(vb, s_v + (ps * 16 + lrow) * HP + head * DH + dp * 16 + lcol);
+          mma16816(o[2 * dp], a, vb[0], vb[1]);
+          mma16816(o[2 * dp + 1], a, vb[2], vb[3]);
         }
       }
 #pragma unroll
@@ -359,7 +377,7 @@ __global__ void __launch_bounds__(256, 1) stw_fused_kernel(const __grid_constant
             pack_bf16(o[dt][2] * inv1, o[dt][3] * inv1);
       }
     }
-    __syncthreads();                                       // all heads' outputs in s_o; s_xn is dead
+    __syncthreads();                                       // S3: all heads' outputs in s_o; s_xn is dead
 
     // ---- output projection + bias + residual -> s_xn (staging), then coalesced stores
     {
@@ -370,24 +388,21 @@ __global__ void __launch_bounds__(256, 1) stw_fused_kernel(const __grid_constant
 #pragma unroll
         for (int q = 0; q < NPW; ++q) { acc[mt][q][0] = acc[mt][q][1] = acc[mt][q][2] = acc[mt][q][3] = 0.f; }
 #pragma unroll
-      for (int ks = 0; ks < HID / 16; ++ks) {
-        uint32_t b[NPW][2];
+      for (int kp = 0; kp < HID / 32; ++kp) {
+        // B fragments of this warp's n-tiles for two k-steps (32 hidden columns) per ldmatrix.x4
+        uint32_t b[NPW][4];
 #pragma unroll
-        for (int q = 0; q < NPW; ++q) {
-          const __nv_bfloat16* rw = s_wproj + ((warp * NPW + q) * 8 + g) * HP + ks * 16 + tg * 2;
-          b[q][0] = *reinterpret_cast<const uint32_t*>(rw);
-          b[q][1] = *reinterpret_cast<const uint32_t*>(rw + 8);
-        }
+        for (int q = 0; q < NPW; ++q)
+          ldsm_x4(b[q], s_wproj + ((warp * NPW + q) * 8 + (lane & 7)) * HP + kp * 32 + (lane >> 3) * 8);
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          uint32_t a[4];
-          const __nv_bfloat16* orow = s_o + (mt * 16 + g) * HP + ks * 16 + tg * 2;
-          a[0] = *reinterpret_cast<const uint32_t*>(orow);
-          a[1] = *reinterpret_cast<const uint32_t*>(orow + 8 * HP);
-          a[2] = *reinterpret_cast<const uint32_t*>(orow + 8);
-          a[3] = *reinterpret_cast<const uint32_t*>(orow + 8 * HP + 8);
+        for (int kk = 0; kk < 2; ++kk) {
 #pragma unroll
-          for (int q = 0; q < NPW; ++q) mma16816(acc[mt][q], a, b[q][0], b[q][1]);
+          for (int mt = 0; mt < MT; ++mt) {
+            uint32_t a[4];
+            ldsm_x4(a, s_o + (mt * 16 + lrow) * HP + (kp * 2 + kk) * 16 + lcol);
+#pragma unroll
+            for (int q = 0; q < NPW; ++q) mma16816(acc[mt][q], a, b[q][kk * 2], b[q][kk * 2 + 1]);
+          }
         }
       }
 #pragma unroll
@@ -399,46 +414,39 @@ __global__ void __launch_bounds__(256, 1) stw_fused_kernel(const __grid_constant
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
             const int tok = mt * 16 + hf * 8 + g;
-            const float2 r = unpack_bf16(*reinterpret_cast<const uint32_t*>(raw + tok * C + col));
+            const float2 r = unpack_bf16(*reinterpret_cast<const uint32_t*>(raw + tok * XP + col));
             *reinterpret_cast<uint32_t*>(s_xn + tok * XP + col) =
                 pack_bf16(acc[mt][q][hf * 2] + b0 + r.x, acc[mt][q][hf * 2 + 1] + b1 + r.y);
           }
         }
     }
-    __syncthreads();
+    __syncthreads();                                       // S4: projected tile staged
     for (int i = tid; i < NTOK * (C / 8); i += 256) {
       const int n = i / (C / 8), c8 = i % (C / 8);
-      const int d = s_src[n];
+      const int d = src_pixel(win, n);
       if (d >= 0)
         *reinterpret_cast<uint4*>(p.y + static_cast<long long>(d) * C + c8 * 8) =
             *reinterpret_cast<const uint4*>(s_xn + n * XP + c8 * 8);
     }
-    __syncthreads();                                       // s_xn / raw / idx of this window are dead from here on
-    if (DB) {
-      buf ^= 1;
-    } else if (nxt < p.n_windows) {
-      index_window(nxt, 0);
-      __syncthreads();
-      prefetch_window(0);
-    }
+    buf ^= 1;
   }
   cp_async_wait<0>();
 }
 
 template <int NTOK, int DH, int C>
-static int launch_stw(const StwParams& p, int tbl_n, cudaStream_t st) {
+static int launch_stw(const StwParams& p, cudaStream_t st) {
   using L = StwSmem<NTOK, DH, C>;
-  const size_t smem = L::tbl + static_cast<size_t>(8) * tbl_n * 4;
-  static size_t configured = 0;
+  constexpr size_t smem = L::total;
+  static bool configured = false;
   static int sms = 0;
-  if (smem > configured) {
+  if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(stw_fused_kernel<NTOK, DH, C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) {
       extdm_set_error(cudaGetErrorString(e), __FILE__, __LINE__);
       return EXTDM_ERR_CUDA;
     }
-    configured = smem;
+    configured = true;
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -455,7 +463,7 @@ using namespace extdm;
 
 extern "C" int extdm_stw_fused_supported(int C, int heads, int dh, int wd, int wh, int ww) {
   const int ntok = wd * wh * ww;
-  if (heads != 8) return 0;
+  if (heads != 8 || wh != 4 || ww != 4) return 0;
   if (ntok == 64 && dh == 16 && (C == 64 || C == 128)) return 1;
   if (ntok == 32 && dh == 32 && C == 64) return 1;
   return 0;
@@ -465,8 +473,9 @@ extern "C" int extdm_stw_fused(const void* x, void* y, const float* gamma, const
                                const float* proj_bias, const float* bias_table, const float* rope_cos,
                                const float* rope_sin, int B, int T, int H, int W, int C, int heads, int dh, int wd,
                                int wh, int ww, int sd, int sh, int sw, float eps, void* stream) {
-  if (!extdm_stw_fused_supported(C, heads, dh, wd, wh, ww) || H % wh || W % ww) {
-    extdm_set_error("stw_fused: unsupported (C, heads, dh, window) combination", __FILE__, __LINE__);
+  if (!extdm_stw_fused_supported(C, heads, dh, wd, wh, ww) || H % wh || W % ww || sd < 0 || sd >= wd || sh < 0 ||
+      sh >= wh || sw < 0 || sw >= ww) {
+    extdm_set_error("stw_fused: unsupported (C, heads, dh, window, shift) combination", __FILE__, __LINE__);
     return EXTDM_ERR_ARG;
   }
   StwParams p;
@@ -480,14 +489,13 @@ extern "C" int extdm_stw_fused(const void* x, void* y, const float* gamma, const
   p.rcos = rope_cos;
   p.rsin = rope_sin;
   p.B = B; p.T = T; p.H = H; p.W = W;
-  p.wd = wd; p.wh = wh; p.ww = ww; p.sd = sd; p.sh = sh; p.sw = sw;
+  p.sd = sd; p.sh = sh; p.sw = sw;
   p.Dp = (T + wd - 1) / wd * wd;
   p.n_windows = B * (p.Dp / wd) * (H / wh) * (W / ww);
   p.eps = eps;
-  const int tbl_n = (2 * wd - 1) * (2 * wh - 1) * (2 * ww - 1);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int ntok = wd * wh * ww;
-  if (ntok == 64 && C == 64) return launch_stw<64, 16, 64>(p, tbl_n, st);
-  if (ntok == 64 && C == 128) return launch_stw<64, 16, 128>(p, tbl_n, st);
-  return launch_stw<32, 32, 64>(p, tbl_n, st);
+  if (ntok == 64 && C == 64) return launch_stw<64, 16, 64>(p, st);
+  if (ntok == 64 && C == 128) return launch_stw<64, 16, 128>(p, st);
+  return launch_stw<32, 32, 64>(p, st);
 }
