@@ -52,6 +52,9 @@ PROTOTYPES = {
     "extdm_window_attention": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "extdm_stw_fused_supported": [_I, _I, _I, _I, _I, _I],
     "extdm_stw_fused": [_P, _P, _P, _P, _P, _P, _P, _P, _P] + [_I] * 13 + [_F, _P],
+    "extdm_cross_attention": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "extdm_maxpool2_frames_cl": [_P, _P, _I, _I, _L, _L, _I, _I, _I, _P],
+    "extdm_bilinear_resize_frames_cl": [_P, _P, _I, _I, _L, _L, _I, _I, _I, _I, _I, _P],
     "extdm_temporal_attention": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "extdm_ddim_threshold": [_P, _P, _F, _F, _F, _P, _I, _I, _P],
     "extdm_ddim_update": [_P, _P, _P, _P, _F, _F, _F, _F, _F, _P, _P, _I, _I, _P],

@@ -132,12 +132,12 @@ def std_box(H, W):
 def gemm(rec, *, a0, c0, dims, strides0, box, start, count, taps, w, n, out, out_stride, out_base=0,
          a1=None, c1=0, strides1=None, out_fp32=False, col_group=None, col_group_stride=0, bias=None,
          res=None, res_fp32=False, res_base=0, res_stride=None, col_scale=None, col_shift=None, act=0,
-         block_n=0, gn_partials=None):
+         block_n=0, gn_partials=None, a1_offset=0):
     """Generic launch of extdm_conv_gemm.  dims/strides: extents and element strides of D1..D4 of the A
     tensor(s); box/start/count: tile geometry; taps: list of (o1,o2,o3)."""
     g = _lib.ExtdmGemm()
     g.a0 = a0.data_ptr()
-    g.a1 = 0 if a1 is None else a1.data_ptr()
+    g.a1 = 0 if a1 is None else a1.data_ptr() + 2 * a1_offset
     g.a0_channels, g.a1_channels = c0, (c1 if a1 is not None else 0)
     for i in range(4):
         g.a0_dim[i], g.a0_stride[i] = dims[i], strides0[i]
@@ -187,7 +187,7 @@ def linear_rows(rec, x, w, n, out, *, bias=None, res=None, res_fp32=False, act=0
 
 def conv_cl(rec, x, w, n, k, out, *, x2=None, bias=None, res=None, res_fp32=False, act=0, out_fp32=False,
             t_range=None, col_scale=None, col_shift=None, out_t_offset=0, res_t_offset=0, taps=None,
-            out_scale=1, out_phase=(0, 0), block_n=0, gn_partials=None):
+            out_scale=1, out_phase=(0, 0), block_n=0, gn_partials=None, x2_t_offset=0):
     """k x k 'same' convolution over channels-last x (B, T, H, W, C) [channel-concatenated with x2].
     out: (B, To, Ho, Wo, n') with n' >= n.  t_range=(t0, t1) restricts the frames computed; the output
     frame index is t + out_t_offset.  out_scale/out_phase write a strided output (ConvTranspose phases)."""
@@ -204,7 +204,8 @@ def conv_cl(rec, x, w, n, k, out, *, x2=None, bias=None, res=None, res_fp32=Fals
         rB, rT, rH, rW, rC = res.shape
         rstr = (rC, rW * rC, rH * rW * rC, rT * rH * rW * rC)
         rbase = res_t_offset * rH * rW * rC
-    gemm(rec, a0=x, c0=c0, a1=x2, c1=c1, dims=(W, H, T, B),
+    # x2_t_offset: frame t of x pairs with frame t - x2_t_offset of x2 (a dense tensor holding only a frame range)
+    gemm(rec, a0=x, c0=c0, a1=x2, c1=c1, dims=(W, H, T, B), a1_offset=-x2_t_offset * H * W * c1,
          strides0=(c0, W * c0, H * W * c0, T * H * W * c0),
          strides1=None if x2 is None else (c1, W * c1, H * W * c1, x2.shape[1] * H * W * c1),
          box=(bw, bh, bt, 1), start=(0, 0, t0, 0), count=(W, H, t1 - t0, B),
@@ -333,6 +334,35 @@ def temporal_attention(rec, qkv, out, rel_bias, rcos, rsin, heads, dh):
     B, T, H, W, _ = qkv.shape
     rec.emit("extdm_temporal_attention", (_p(qkv), _p(out), _p(rel_bias), _p(rcos), _p(rsin), B, T, H * W, heads, dh),
              keep=(qkv, out, rel_bias, rcos, rsin))
+
+
+def cross_attention(rec, q, k, v, out, heads):
+    """q (B, Lq, hid), k / v (B, Lk, hid) (row views allowed: last-dim stride 1), out (B, Lq, hid); dh = hid/heads."""
+    B, Lq, hid = q.shape
+    Lk = k.shape[1]
+    rec.emit("extdm_cross_attention", (_p(q), _p(k), _p(v), _p(out), B, heads, hid // heads, Lq, Lk, q.stride(1),
+                                       k.stride(1), out.stride(1)), keep=(q, k, v, out),
+             meta=dict(flops=4.0 * B * Lq * Lk * hid, tag=f"Lq={Lq} Lk={Lk}"))
+
+
+def maxpool2_frames_cl(rec, x, y, t_range):
+    """MaxPool (1,2,2) of frames t_range of x (B, T, H, W, C) -> dense y (B, nt, H/2, W/2, C)."""
+    B, T, H, W, Cc = x.shape
+    t0, t1 = t_range
+    xp = C.c_void_p(x.data_ptr() + t0 * H * W * Cc * 2)
+    rec.emit("extdm_maxpool2_frames_cl", (xp, _p(y), B, t1 - t0, T * H * W * Cc, (t1 - t0) * (H // 2) * (W // 2) * Cc,
+                                          H, W, Cc), keep=(x, y))
+
+
+def bilinear_resize_frames_cl(rec, x, y, x_t_range, y_t0):
+    """Resize frames x_t_range of x (B, Tx, h, w, C) into frames [y_t0, ...) of y (B, Ty, H, W, C)."""
+    B, Tx, h, w, Cc = x.shape
+    Ty, H, W = y.shape[1:4]
+    t0, t1 = x_t_range
+    xp = C.c_void_p(x.data_ptr() + t0 * h * w * Cc * 2)
+    yp = C.c_void_p(y.data_ptr() + y_t0 * H * W * Cc * 2)
+    rec.emit("extdm_bilinear_resize_frames_cl", (xp, yp, B, t1 - t0, Tx * h * w * Cc, Ty * H * W * Cc, h, w, H, W, Cc),
+             keep=(x, y))
 
 
 # ----------------------------------------------------------------------------- sampler

@@ -80,6 +80,10 @@ class PackedUnet:
         if cfg.variant == "base":
             self.w["init_flow"] = pack7(ic[:, :3])
             self.w["init_fea"] = ops.pack_conv_weight(ic[:, 3:])
+        elif cfg.variant == "u12":
+            # TrajWarp makes the cond_fea half of init_conv depend on x_t: nothing to hoist, one conv over 512 channels
+            self.w["init_noise"] = pack7(self.f32["init_noise_conv.weight"])
+            self.w["init_full"] = ops.pack_conv_weight(ic)
         else:
             self.w["init_noise"] = pack7(self.f32["init_noise_conv.weight"])
             self.w["init_x"] = ops.pack_conv_weight(ic[:, :256])
@@ -110,9 +114,6 @@ class UnetRunner:
 
     def __init__(self, packed, B, H=32, W=32, fea_hw=16):
         cfg = packed.cfg
-        if cfg.variant == "u12":
-            raise NotImplementedError("TrajWarp (BAIR 'u12' variant) is not built yet -- SURVEY.md section 8f; "
-                                      "no fallback is provided")
         self.pk, self.cfg, self.B, self.H, self.W = packed, cfg, B, H, W
         dev = packed.dev
         self.dev = dev
@@ -286,6 +287,8 @@ class UnetRunner:
         fh = self.cond_fea.shape[-1]
         cf = self.buf(B, T, fh, fh, 256)
         ops.ncthw_to_cl(pro, self.cond_fea, cf)
+        if cfg.variant == "u12":
+            return self._build_u12_front(cf)
         if cfg.variant == "ada":
             cf = self._adaptor(pro, cf, "cond_adaptor")
             cf = self._temporal(pro, cf, "cond_temporal_attn")
@@ -319,6 +322,61 @@ class UnetRunner:
             self.taps["init_noise_conv"] = xn
         self.taps["init_conv"] = x0
 
+        self._build_body(x0)
+
+    def _build_u12_front(self, cf):
+        """BAIR variant (..._traj_u12.py:1017-1042): init_noise_conv -> TrajWarp (cross attention of the future
+        frames' pooled features over the conditioning frames' cond_fea) -> bilinear resize -> init_conv over
+        [x | cond_fea].  Hoisted to the prologue: K / V projections, and everything on the tc conditioning frames."""
+        cfg, pk, B, H, W = self.cfg, self.pk, self.B, self.H, self.W
+        T, tc, tp = cfg.T, cfg.tc, cfg.tp
+        hw = H * W
+        pro, st = self.prologue, self.step
+        d = cfg.dim
+        fh = cf.shape[2]
+        if H != 2 * fh or W != 2 * fh:
+            raise NotImplementedError("TrajWarp needs cond_fea at half the flow resolution (MaxPool (1,2,2))")
+        ca = "init_traj.cross_att."
+        kk, vv = self.buf(B, tc, fh, fh, 256), self.buf(B, tc, fh, fh, 256)
+        ops.conv_cl(pro, cf, pk.w[ca + "linear_k.weight"], 256, 1, kk, bias=pk.f32[ca + "linear_k.bias"], act=1,
+                    t_range=(0, tc))
+        ops.conv_cl(pro, cf, pk.w[ca + "linear_v.weight"], 256, 1, vv, bias=pk.f32[ca + "linear_v.bias"], act=1,
+                    t_range=(0, tc))
+        cfu = self.buf(B, T, H, W, 256)
+        ops.bilinear_resize_frames_cl(pro, cf, cfu, (0, tc), 0)
+        xn = self.buf(B, T, H, W, 256)
+        x0 = self.buf(B, T, H, W, d)
+        a_c, a_p = self.buf(B * tc * hw, 192), self.buf(B * tp * hw, 192)
+        nb = pk.f32["init_noise_conv.bias"]
+        ops.im2col7_flow(pro, self.cond_frames, self.x, a_c, 0, tc)
+        self._im2col_gemm(pro, a_c, pk.w["init_noise"], 256, xn, 0, tc, bias=nb)
+        ops.conv_cl(pro, xn, pk.w["init_full"], d, 7, x0, x2=cfu, t_range=(0, tc), bias=pk.f32["init_conv.bias"])
+        # ---- per DDIM step
+        ops.im2col7_flow(st, self.cond_frames, self.x, a_p, tc, tp)
+        self._im2col_gemm(st, a_p, pk.w["init_noise"], 256, xn, tc, tp, bias=nb)
+        self.taps["init_noise_conv"] = xn
+        xp = self.buf(B, tp, fh, fh, 256)
+        ops.maxpool2_frames_cl(st, xn, xp, (tc, T))
+        qq = self.buf(B, tp, fh, fh, 256)
+        ops.linear_rows(st, xp, pk.w[ca + "linear_q.weight"], 256, qq, bias=pk.f32[ca + "linear_q.bias"], act=1)
+        ao = self.buf(B, tp * fh * fh, 256)
+        ops.cross_attention(st, qq.view(B, -1, 256), kk.view(B, -1, 256), vv.view(B, -1, 256), ao, 8)
+        yo = self.buf(B, tp, fh, fh, 256)
+        ops.linear_rows(st, ao, pk.w[ca + "linear_o.weight"], 256, yo, bias=pk.f32[ca + "linear_o.bias"], act=1)
+        fpn = self.buf(B, tp, fh, fh, 256)
+        ops.conv_cl(st, cf, pk.w["init_traj.fuser.weight"], 256, 1, fpn, x2=yo, x2_t_offset=tc, t_range=(tc, T),
+                    out_t_offset=-tc, bias=pk.f32["init_traj.fuser.bias"])
+        ops.bilinear_resize_frames_cl(st, fpn, cfu, (0, tp), tc)
+        self.taps["cond_up"] = cfu
+        ops.conv_cl(st, xn, pk.w["init_full"], d, 7, x0, x2=cfu, t_range=(tc, T), bias=pk.f32["init_conv.bias"])
+        self.taps["init_conv"] = x0
+        self._build_body(x0)
+
+    def _build_body(self, x0):
+        cfg, pk, B, H, W = self.cfg, self.pk, self.B, self.H, self.W
+        T, tc, tp, tm = cfg.T, cfg.tc, cfg.tp, cfg.tm
+        st = self.step
+        d = cfg.dim
         x = self._temporal(st, x0, "init_temporal_attn")
         self.taps["init_temporal_attn"] = x
         ops.time_mlp(st, self.time, pk.f32["time_mlp.1.weight"], pk.f32["time_mlp.1.bias"],

@@ -169,6 +169,21 @@ int extdm_stw_fused(const void* x, void* y, const float* gamma, const void* wqkv
                     int B, int T, int H, int W, int C, int heads, int dh, int wd, int wh, int ww, int sd, int sh,
                     int sw, float eps, void* stream);
 
+/* TrajWarp (BAIR 'u12' variant, ..._traj_u12.py:719-827).  Multi-head cross attention core
+ * softmax(q k^T / sqrt(dh)) v (ScaledDotProductAttention :719-728, heads split as in _reshape_to_batches
+ * :783-789): q (B, Lq, ldq), k / v (B, Lk, ldk), out (B, Lq, ldo) bf16; head h = columns [h*dh, (h+1)*dh).
+ * dh must be 32, Lq and Lk multiples of 64.  The Linear+ReLU projections around it run on extdm_conv_gemm. */
+int extdm_cross_attention(const void* q, const void* k, const void* v, void* out, int B, int heads, int dh, int Lq,
+                          int Lk, int ldq, int ldk, int ldo, void* stream);
+/* MaxPool3d((1,2,2)) (TrajWarp.down :811) and F.interpolate(bilinear, align_corners=False) (:1036) on channels-last
+ * bf16 frames addressed as groups x frames_per_group: frame fi of group gi starts at
+ * base + gi*group_stride + fi*(H*W*C) elements (lets a caller touch frames [tc, T) of every sample). */
+int extdm_maxpool2_frames_cl(const void* x, void* y, int groups, int frames_per_group, long long x_group_stride,
+                             long long y_group_stride, int H, int W, int C, void* stream);
+int extdm_bilinear_resize_frames_cl(const void* x, void* y, int groups, int frames_per_group,
+                                    long long x_group_stride, long long y_group_stride, int h, int w, int H, int W,
+                                    int C, void* stream);
+
 /* Temporal attention core (Attention.forward ...cross_multi.py:269-302): sequence = T frames of one pixel.
  * qkv: (B, T, HW, 3*heads*dh); out: (B, T, HW, heads*dh); rel_bias: (heads, 2T-1) fp32 indexed by (j-i+T-1). */
 int extdm_temporal_attention(const void* qkv, void* out, const float* rel_bias, const float* rope_cos,

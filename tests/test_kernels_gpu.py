@@ -507,3 +507,39 @@ def test_stw_fused_layer(window, dh, C, T, H, shifted):
     with torch.no_grad():
         ref = O.stw_attention(xc.float().permute(0, 4, 1, 2, 3).cpu(), O.SD(sd), window, shift, heads, dh)
     close(from_cl(y).cpu(), ref, rel=2e-2, atol=5e-3, what="stw fused")
+
+
+# ------------------------------------------------------------------------------------------------ TrajWarp pieces
+@pytest.mark.parametrize("B,Lq,Lk", [(2, 256, 128), (1, 2560, 512), (3, 64, 64)])
+def test_cross_attention(B, Lq, Lk):
+    heads, dh = 8, 32
+    hid = heads * dh
+    q = rnd(B, Lq, hid, seed=1).to(BF)
+    k = rnd(B, Lk, hid, seed=2).to(BF)
+    v = rnd(B, Lk, hid, seed=3).to(BF)
+    out = torch.zeros(B, Lq, hid, device=DEV, dtype=BF)
+    ops.cross_attention(R, q, k, v, out, heads)
+
+    def split(t):
+        return t.float().reshape(B, -1, heads, dh).permute(0, 2, 1, 3)
+    att = (split(q) @ split(k).transpose(-1, -2) / math.sqrt(dh)).softmax(-1)
+    ref = (att @ split(v)).permute(0, 2, 1, 3).reshape(B, Lq, hid)
+    close(out, ref, rel=2e-2, atol=5e-3, what="cross attention")
+
+
+def test_frame_range_pool_and_resize():
+    B, T, H, C, t0 = 2, 5, 16, 64, 2
+    x = rnd(B, C, T, H, H, seed=1)
+    xc = to_cl(x)
+    y = torch.zeros(B, T - t0, H // 2, H // 2, C, device=DEV, dtype=BF)
+    ops.maxpool2_frames_cl(R, xc, y, (t0, T))
+    ref = F.max_pool3d(xc.float().permute(0, 4, 1, 2, 3)[:, :, t0:], (1, 2, 2), (1, 2, 2))
+    assert torch.equal(from_cl(y), ref)
+    z = torch.zeros(B, T, 2 * H, 2 * H, C, device=DEV, dtype=BF)
+    ops.bilinear_resize_frames_cl(R, xc, z, (0, t0), T - t0)          # frames [0,2) of x -> frames [3,5) of z
+    xin = xc.float().permute(0, 4, 1, 2, 3)[:, :, :t0]
+    ref = F.interpolate(xin.permute(0, 2, 1, 3, 4).reshape(B * t0, C, H, H), size=(2 * H, 2 * H), mode="bilinear")
+    ref = ref.reshape(B, t0, C, 2 * H, 2 * H).permute(0, 2, 1, 3, 4)
+    got = from_cl(z)
+    close(got[:, :, T - t0:], ref, rel=1e-2, what="resize frames")
+    assert got[:, :, :T - t0].abs().max() == 0

@@ -54,7 +54,7 @@ def build_unet(fx):
     return u, sd
 
 
-@pytest.mark.parametrize("name", ["unet_ada_c2p5", "unet_base_c3p2"])
+@pytest.mark.parametrize("name", ["unet_ada_c2p5", "unet_base_c3p2", "unet_u12_c2p3"])
 def test_unet_forward_matches_reference(name):
     fx = torch.load(os.path.join(GOLD, name + ".pt"))
     u, _ = build_unet(fx)
@@ -66,18 +66,20 @@ def test_unet_forward_matches_reference(name):
     assert r <= 2e-2, r
 
 
-def test_unet_layers_vs_oracle():
+@pytest.mark.parametrize("name", ["unet_ada_c2p5", "unet_u12_c2p3", "unet_base_c3p2"])
+def test_unet_layers_vs_oracle(name):
     """Layer-by-layer: every tapped activation of the CUDA runner against the oracle's (rel-L2 <= 3e-2)."""
     from oracle import extdm_oracle as O
-    fx = torch.load(os.path.join(GOLD, "unet_ada_c2p5.pt"))
+    fx = torch.load(os.path.join(GOLD, name + ".pt"))
     u, sd = build_unet(fx)
-    inp = unet_inputs("ada", fx["tc"], fx["tp"], fx["B"], fx["input_seed"])
+    v = fx["variant"]
+    inp = unet_inputs(v, fx["tc"], fx["tp"], fx["B"], fx["input_seed"])
     u(inp["x"].cuda(), inp["time"].cuda(), cond_frames=inp["cond_frames"].cuda(), cond_fea=inp["cond_fea"].cuda())
-    r = u.runner(1, 32, 32, 16)
+    r = u.runner(fx["B"], 32, 32, inp["cond_fea"].shape[-1])
     taps = {}
     with torch.no_grad():
-        O.unet_forward(O.SD(sd), O.unet_config("ada", fx["tc"], fx["tp"]), inp["x"], inp["time"], inp["cond_frames"],
-                       inp["cond_fea"], taps=taps)
+        O.unet_forward(O.SD(sd), O.unet_config(v, fx["tc"], fx["tp"], dim_mults=fx["dim_mults"]), inp["x"], inp["time"],
+                       inp["cond_frames"], inp["cond_fea"], taps=taps)
     worst = 0.0
     for name, buf in r.taps.items():
         if name not in taps:
@@ -166,3 +168,19 @@ def test_pipeline_matches_reference(request):
     # the fixture clip is white noise (torch.rand): a 0.3-pixel flow difference already costs ~30 dB there, so the
     # frame gate for this clip is 30 dB; the decoder alone (same flow) is gated at 35 dB in the test above
     assert p >= 30.0, p
+
+
+@pytest.mark.parametrize("name,B", [("smmnist", 1), ("bair", 2), ("ucf", 2), ("cityscapes", 1), ("kth", 1)])
+def test_every_dataset_config_samples(name, B):
+    """Every configuration BASELINE.json names builds and runs one sample_one_video round on the CUDA path:
+    output shapes as the reference's, finite values, frames in [0, 1]."""
+    from extdm_b200 import configs
+    model, cfg = configs.build_model(name, device="cuda")
+    tc, tp = model.cond_frame_num, model.pred_frame_num
+    hw = cfg["dataset_params"]["frame_shape"]
+    clip = torch.rand(B, 3, tc, hw, hw, generator=torch.Generator().manual_seed(7)).cuda()
+    ret = model.sample_one_video(cond_scale=1.0, real_vid=clip)
+    out = ret["sample_out_vid"]
+    assert tuple(out.shape) == (B, 3, tc + tp, hw, hw)
+    assert tuple(ret["sample_vid_grid"].shape) == (B, 2, tc + tp, 32, 32)
+    assert torch.isfinite(out).all() and out.min() >= 0 and out.max() <= 1
