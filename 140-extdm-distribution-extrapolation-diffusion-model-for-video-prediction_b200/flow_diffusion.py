@@ -86,7 +86,7 @@ class FlowDiffusion(nn.Module):
 
     # ------------------------------------------------------------------ (A) conditioning, torch
     @torch.no_grad()
-    def condition(self, real_vid):
+    def condition(self, real_vid, with_decode=False):
         """real_vid (B,3,tc,H,W) in [0,1] -> dict with x_cond, cond_fea and the 'real_*' entries of the reference
         result dict (VideoFlowDiffusion_multi_w_ref.py:231-278 / VideoFlowDiffusion_multi1248.py:221-264).
         The tc per-frame passes of the reference are batched into one pass over B*tc images."""
@@ -94,21 +94,29 @@ class FlowDiffusion(nn.Module):
         assert tc == self.cond_frame_num
         tp = self.pred_frame_num
         ref = real_vid[:, :, tc - 1]
-        frames = real_vid.permute(0, 2, 1, 3, 4).reshape(B * tc, 3, H, W)
+        frames = real_vid.permute(0, 2, 1, 3, 4).reshape(B * tc, 3, H, W).contiguous(memory_format=torch.channels_last)
         ref_rep = ref.repeat_interleave(tc, dim=0)
         src_params = self.region_predictor(ref)
         src_rep = {k: v.repeat_interleave(tc, dim=0) for k, v in src_params.items()}
         drv_params = self.region_predictor(frames)
         bg = self.bg_predictor(ref_rep, frames)
-        gen = self.generator(ref_rep, source_region_params=src_rep, driving_region_params=drv_params, bg_params=bg)
+        # Generator.forward = flow predictor + the same warp/blend decode as forward_with_flow (generator.py:105-144 vs
+        # :152-206): only the flow predictor runs here; the decoded conditioning frames ('real_out_vid',
+        # 'real_warped_vid') are the first tc frames of the decode in sample_one_video, which the reference
+        # computes a second time from identical inputs (VideoFlowDiffusion_multi_w_ref.py:295-306).
+        gen = self.generator.pixelwise_flow_predictor(source_image=ref_rep, driving_region_params=drv_params,
+                                                      source_region_params=src_rep, bg_params=bg)
         per_frame = lambda t: t.reshape(B, tc, *t.shape[1:]).transpose(1, 2)       # (B*tc, C, ..) -> (B, C, tc, ..)
         ret = {"real_vid_grid": per_frame(gen["optical_flow"].permute(0, 3, 1, 2)).contiguous()}
         if self.estimate_occlusion_map:
             ret["real_vid_conf"] = per_frame(gen["occlusion_map"]).contiguous()
         elif self.WRAPPER != "w_ref":
             raise KeyError("occlusion_map")         # VideoFlowDiffusion_multi1248.py:236 without estimate_occlusion_map
-        ret["real_out_vid"] = per_frame(gen["prediction"]).contiguous()
-        ret["real_warped_vid"] = per_frame(gen["deformed"]).contiguous()
+        if with_decode:
+            # the reference's own torch decode of the conditioning frames (used by the CPU parity test only)
+            full = self.generator(ref_rep, source_region_params=src_rep, driving_region_params=drv_params, bg_params=bg)
+            ret["real_out_vid"] = per_frame(full["prediction"]).contiguous()
+            ret["real_warped_vid"] = per_frame(full["deformed"]).contiguous()
         # bottleneck features: encoder of frames 0..tc-2, then the reference frame's repeated
         enc_frames = self.generator.forward_bottle(frames).reshape(B, tc, 256, H // 4, W // 4)
         ref_fea = enc_frames[:, tc - 1]
@@ -146,6 +154,8 @@ class FlowDiffusion(nn.Module):
             ret["sample_vid_conf"] = sample_vid_conf
         ret["sample_out_vid"] = out
         ret["sample_warped_vid"] = warped
+        ret["real_out_vid"] = out[:, :, :tc]
+        ret["real_warped_vid"] = warped[:, :, :tc]
         return ret
 
     def forward(self, real_vid):

@@ -33,12 +33,25 @@ class ConvNormAct(nn.Module):
         super().__init__()
         self.conv = nn.Conv2d(cin, cout, kernel, padding=pad)
         self.norm = nn.BatchNorm2d(cout, affine=True)
-        self.pool, self.upsample = pool, upsample
+        self.pool, self.upsample, self.pad = pool, upsample, pad
+        self._folded = None
+        self.register_load_state_dict_post_hook(lambda m, k: setattr(m, "_folded", None))
+
+    def _apply(self, fn, *a, **k):
+        self._folded = None                      # .to() / .cuda() move the parameters: re-fold on the new device
+        return super()._apply(fn, *a, **k)
 
     def forward(self, x):
         if self.upsample:
             x = F.interpolate(x, scale_factor=2)
-        x = F.relu(self.norm(self.conv(x)))
+        if self.training:
+            x = F.relu(self.norm(self.conv(x)))
+        else:
+            # eval-mode BatchNorm is an affine map per channel (sync_batchnorm/batchnorm.py:48-53): fold it into the conv
+            if self._folded is None:
+                w, b = _fold_bn(self.conv.weight, self.conv.bias, self.norm)
+                self._folded = (w.contiguous(memory_format=torch.channels_last), b.contiguous())
+            x = F.relu_(F.conv2d(x, self._folded[0], self._folded[1], padding=self.pad))
         return F.avg_pool2d(x, 2) if self.pool else x
 
 
@@ -179,14 +192,32 @@ class BGMotionPredictor(nn.Module):
         return out
 
 
+def _inv2x2(m):
+    """Closed-form inverse of (..., 2, 2) matrices (the reference calls torch.inverse; same values up to fp32
+    rounding, without a batched LU launch + host sync per call)."""
+    a, b, c, d = m[..., 0, 0], m[..., 0, 1], m[..., 1, 0], m[..., 1, 1]
+    det = a * d - b * c
+    return torch.stack((torch.stack((d, -b), -1), torch.stack((-c, a), -1)), -2) / det[..., None, None]
+
+
+def _mat2_apply(m, v):
+    """(b,k,2,2) applied to vectors v (b,k,h,w,2) -> (b,k,h,w,2), as two fused multiply-adds per component instead
+    of b*k*h*w tiny batched matmuls."""
+    m = m[:, :, None, None]
+    return torch.stack((m[..., 0, 0] * v[..., 0] + m[..., 0, 1] * v[..., 1],
+                        m[..., 1, 0] * v[..., 0] + m[..., 1, 1] * v[..., 1]), -1)
+
+
 def _gaussian_heatmap(center, covar, h, w):
     """region2gaussian (util.py:22-47) for a per-region 2x2 covariance or a scalar variance."""
     grid = coordinate_grid(h, w, center)[None, None]                  # 1 1 h w 2
     d = grid - center[:, :, None, None, :]
     if isinstance(covar, float):
         return torch.exp(-0.5 * (d ** 2).sum(-1) / covar)
-    inv = torch.inverse(covar)[:, :, None, None]                       # b k 1 1 2 2
-    q = (d.unsqueeze(-2) @ inv @ d.unsqueeze(-1)).sum(dim=(-1, -2))
+    inv = _inv2x2(covar)[:, :, None, None]                             # b k 1 1 2 2
+    d0, d1 = d[..., 0], d[..., 1]
+    # d^T inv d in the reference's association order: (d^T inv) d
+    q = (d0 * inv[..., 0, 0] + d1 * inv[..., 1, 0]) * d0 + (d0 * inv[..., 0, 1] + d1 * inv[..., 1, 1]) * d1
     return torch.exp(-0.5 * q)
 
 
@@ -223,16 +254,19 @@ class PixelwiseFlowPredictor(nn.Module):
         ident = coordinate_grid(h, w, src["shift"]).view(1, 1, h, w, 2)
         coords = ident - drv["shift"].view(bs, K, 1, 1, 2)
         if "affine" in drv:
-            aff = src["affine"] @ torch.inverse(drv["affine"])
+            aff = src["affine"] @ _inv2x2(drv["affine"])
             if self.revert_axis_swap:
                 aff = aff * torch.sign(aff[:, :, 0:1, 0:1])
-            coords = (aff[:, :, None, None] @ coords.unsqueeze(-1)).squeeze(-1)
+            coords = _mat2_apply(aff, coords)
         to_src = coords + src["shift"].view(bs, K, 1, 1, 2)
         bg = ident.repeat(bs, 1, 1, 1, 1)
         if bg_params is not None:
-            hom = torch.cat([bg, torch.ones_like(bg[..., :1])], dim=-1)
-            hom = (bg_params.view(bs, 1, 1, 1, 3, 3) @ hom.unsqueeze(-1)).squeeze(-1)
-            bg = hom[..., :2] / (hom[..., 2:3] + 1e-10)
+            m = bg_params.view(bs, 1, 1, 1, 3, 3)
+            bx, by = bg[..., 0], bg[..., 1]
+            hx = m[..., 0, 0] * bx + m[..., 0, 1] * by + m[..., 0, 2]
+            hy = m[..., 1, 0] * bx + m[..., 1, 1] * by + m[..., 1, 2]
+            hz = m[..., 2, 0] * bx + m[..., 2, 1] * by + m[..., 2, 2]
+            bg = torch.stack((hx, hy), -1) / (hz[..., None] + 1e-10)
         motions = torch.cat([bg, to_src], dim=1)                                # bs K+1 h w 2
         # warped copies of the source for every motion
         rep = source_image[:, None].expand(bs, K + 1, -1, h, w).reshape(bs * (K + 1), -1, h, w)
@@ -329,7 +363,27 @@ class Generator(nn.Module):
         return skips
 
     def forward_bottle(self, source_image):
+        """Bottleneck features (F,256,H/4,W/4).  On a CUDA device this runs the hand-written encoder kernels (bf16);
+        on CPU (parity fixtures only) the torch modules."""
+        if source_image.is_cuda:
+            return self.forward_bottle_cl(source_image).permute(0, 3, 1, 2).float()
         return self._encode(source_image)[-1]
+
+    @torch.no_grad()
+    def forward_bottle_cl(self, source_image):
+        """(F,3,H,W) fp32 on CUDA -> (F, H/4, W/4, 256) bf16 channels-last view of the runner's output buffer."""
+        F_, _, H, W = source_image.shape
+        dev = source_image.device
+        if self._packed is None or self._packed[0] != dev:
+            self._runners = {}
+            self._packed = (dev, self._pack(dev))
+        key = ("enc", F_, H, W)
+        if key not in self._runners:
+            self._runners[key] = EncodeRunner(self._packed[1], dev, F_, H, W)
+        r = self._runners[key]
+        r.src.copy_(source_image)
+        r.run()
+        return r.out
 
     def forward(self, source_image, driving_region_params, source_region_params, bg_params=None):
         skips = self._encode(source_image)
@@ -422,6 +476,39 @@ class Generator(nn.Module):
 
 
 # =============================================================================================== CUDA decode
+def _emit_encoder(rec, pk, src, buf, F_, H, W):
+    """Generator encoder (first 7x7 -> down0 -> down1, generator.py:153-157) of F_ fp32 NCHW images on the CUDA
+    kernels; returns the three skip tensors (channels-last bf16)."""
+    v5 = lambda t: t.view(t.shape[0], 1, *t.shape[1:])
+    a = buf(F_ * H * W, 192)
+    ops.im2col7_image(rec, src, a)
+    skip0 = buf(F_, H, W, 64)
+    ops.linear_rows(rec, a, pk["first"][0], 64, skip0, bias=pk["first"][1], act=1)
+    d0 = buf(F_, H, W, 128)
+    ops.conv_cl(rec, v5(skip0), pk["down0"][0], 128, 3, v5(d0), bias=pk["down0"][1], act=1)
+    skip1 = buf(F_, H // 2, W // 2, 128)
+    ops.avgpool2_cl(rec, d0, skip1)
+    d1 = buf(F_, H // 2, W // 2, 256)
+    ops.conv_cl(rec, v5(skip1), pk["down1"][0], 256, 3, v5(d1), bias=pk["down1"][1], act=1)
+    skip2 = buf(F_, H // 4, W // 4, 256)
+    ops.avgpool2_cl(rec, d1, skip2)
+    return skip0, skip1, skip2
+
+
+class EncodeRunner:
+    """Generator.forward_bottle (generator.py:95-103) for F frames on the CUDA kernels: (F,3,H,W) fp32 ->
+    bottleneck features (F, H/4, W/4, 256) bf16 channels-last."""
+
+    def __init__(self, pk, dev, F_, H, W):
+        self.rec = ops.Recorder(record=True)
+        self.src = torch.zeros(F_, 3, H, W, device=dev, dtype=torch.float32)
+        buf = lambda *s, dtype=BF16: torch.empty(*s, device=dev, dtype=dtype)
+        self.out = _emit_encoder(self.rec, pk, self.src, buf, F_, H, W)[2]
+
+    def run(self):
+        self.rec.run()
+
+
 class DecodeRunner:
     """Static buffers + launch list of the batched flow-warp / occlusion-blend decode of F = B*T frames."""
 
@@ -442,18 +529,7 @@ class DecodeRunner:
         buf = lambda *s, dtype=BF16: torch.empty(*s, device=dev, dtype=dtype)
         v5 = lambda t: t.view(t.shape[0], 1, *t.shape[1:])
         # ---- encoder, once per video
-        a = buf(B * H * W, 192)
-        ops.im2col7_image(rec, self.src, a)
-        skip0 = buf(B, H, W, 64)
-        ops.linear_rows(rec, a, pk["first"][0], 64, skip0, bias=pk["first"][1], act=1)
-        d0 = buf(B, H, W, 128)
-        ops.conv_cl(rec, v5(skip0), pk["down0"][0], 128, 3, v5(d0), bias=pk["down0"][1], act=1)
-        skip1 = buf(B, H // 2, W // 2, 128)
-        ops.avgpool2_cl(rec, d0, skip1)
-        d1 = buf(B, H // 2, W // 2, 256)
-        ops.conv_cl(rec, v5(skip1), pk["down1"][0], 256, 3, v5(d1), bias=pk["down1"][1], act=1)
-        skip2 = buf(B, H // 4, W // 4, 256)
-        ops.avgpool2_cl(rec, d1, skip2)
+        skip0, skip1, skip2 = _emit_encoder(rec, pk, self.src, buf, B, H, W)
         # ---- per-frame decode
         Hb, Wb = H // 4, W // 4
         out = buf(Fn, Hb, Wb, 256)

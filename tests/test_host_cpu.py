@@ -55,7 +55,7 @@ def test_conditioning_stage_matches_reference_on_cpu():
         m = getattr(fd, part)
         m.load_state_dict(synth_state_dict(fx["manifests"][part], seed, base=m.state_dict()), strict=True)
     real_vid = torch.rand((1, 1, 2, 64, 64), generator=torch.Generator().manual_seed(500)).expand(1, 3, 2, 64, 64)
-    ret, x_cond, fea, _ = fd.condition(real_vid.contiguous())
+    ret, x_cond, fea, _ = fd.condition(real_vid.contiguous(), with_decode=True)
     for k in ("real_vid_grid", "real_vid_conf", "real_out_vid", "real_warped_vid"):
         assert (ret[k] - fx["out"][k]).abs().max().item() < 2e-4, k
     assert x_cond.shape == (1, 3, 2, 32, 32) and fea.shape == (1, 256, 7, 16, 16)

@@ -156,8 +156,13 @@ def test_pipeline_matches_reference(request):
     torch.svd = lambda a, *args, **kw: tuple(t.to(a.device) for t in real_svd(a.cpu(), *args, **kw))
     request.addfinalizer(lambda: setattr(torch, "svd", real_svd))
     cret, x_cond, fea, _ = fd.condition(real_vid.contiguous().cuda())
-    for k in ("real_vid_grid", "real_vid_conf", "real_out_vid"):
-        print("conditioning", k, (cret[k].cpu() - fx["out"][k]).abs().max().item())
+    for k in ("real_vid_grid", "real_vid_conf"):
+        err = (cret[k].cpu() - fx["out"][k]).abs().max().item()
+        print("conditioning", k, err)
+        assert err <= 1e-3, (k, err)
+    print("cond_fea (CUDA bf16 encoder) vs reference-side fp32 encoder rel-L2",
+          rel_l2(fea, fd.generator._encode(real_vid.permute(0, 2, 1, 3, 4).reshape(-1, 3, 64, 64).contiguous().cuda())[-1]
+                 .reshape(B, 2, 256, 16, 16)[:, [0] + [1] * 6].transpose(1, 2)))
     ret = fd.sample_one_video(cond_scale=1.0, real_vid=real_vid.contiguous().cuda(), noise=noise.cuda())
     assert set(ret.keys()) == set(fx["out"].keys())
     for k, v in fx["out"].items():
@@ -168,6 +173,7 @@ def test_pipeline_matches_reference(request):
     # the fixture clip is white noise (torch.rand): a 0.3-pixel flow difference already costs ~30 dB there, so the
     # frame gate for this clip is 30 dB; the decoder alone (same flow) is gated at 35 dB in the test above
     assert p >= 30.0, p
+    assert psnr(ret["real_out_vid"].cpu(), fx["out"]["real_out_vid"]) >= 35.0
 
 
 @pytest.mark.parametrize("name,B", [("smmnist", 1), ("bair", 2), ("ucf", 2), ("cityscapes", 1), ("kth", 1)])
