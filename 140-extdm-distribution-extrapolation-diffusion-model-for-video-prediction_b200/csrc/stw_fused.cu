@@ -61,6 +61,8 @@ struct StwParams {
   const float* bias_table;     // [tbl_n][heads]
   const float* rcos;
   const float* rsin;           // [NTOK][DH/2]
+  const float* ln_w;           // temporal mode: nn.LayerNorm weight / bias applied after the channel LayerNorm
+  const float* ln_b;
   int B, T, H, W, sd, sh, sw, Dp, n_windows;
   float eps;
 };
@@ -86,8 +88,13 @@ struct StwSmem {
   static constexpr size_t total = emask + 2 * 8 * 4;
 };
 
-template <int NTOK, int DH, int C>
-__global__ void __launch_bounds__(256, 1) stw_fused_kernel(const __grid_constant__ StwParams p) {
+// TEMPORAL = false: a "window" is a (WD,4,4) block of the rolled volume (STWAttentionLayer).
+// TEMPORAL = true : a "window" is the T (<= NTOK) frames of one pixel -- the full temporal attention layer
+//   Residual(PreNorm(EinopsToAndFrom('b c t h w -> b (h w) t c', AttentionLayer))), ...cross_multi.py:253-328:
+//   z = chanLN(x); u = LayerNorm(z); y = x + z + to_out(attn(u)), rotary over the frame index, T5 relative-position
+//   bias (heads, 2T-1) in p.bias_table, no projection bias; key slots >= T are masked out.
+template <int NTOK, int DH, int C, bool TEMPORAL>
+__global__ void __launch_bounds__(256, TEMPORAL ? 2 : 1) stw_fused_kernel(const __grid_constant__ StwParams p) {
   using L = StwSmem<NTOK, DH, C>;
   constexpr int HEADS = 8, HID = L::HID, XP = L::XP, HP = L::HP, BP = L::BP;
   constexpr int WD = NTOK / 16;          // window = (WD, 4, 4)
@@ -124,12 +131,18 @@ __global__ void __launch_bounds__(256, 1) stw_fused_kernel(const __grid_constant
     *reinterpret_cast<uint4*>(s_wproj + r * HP + c8 * 8) = *reinterpret_cast<const uint4*>(p.wproj + r * HID + c8 * 8);
   }
   for (int i = tid; i < NTOK * (DH / 2); i += 256) { s_cos[i] = p.rcos[i]; s_sin[i] = p.rsin[i]; }
-  for (int i = tid; i < C; i += 256) { s_gamma[i] = p.gamma[i]; s_pbias[i] = p.proj_bias[i]; }
+  for (int i = tid; i < C; i += 256) { s_gamma[i] = p.gamma[i]; s_pbias[i] = p.proj_bias ? p.proj_bias[i] : 0.f; }
   for (int i = tid; i < HEADS * NTOK * NTOK; i += 256) {
     const int j = i % NTOK, q = (i / NTOK) % NTOK, h = i / (NTOK * NTOK);
-    const int rel = (((q >> 4) - (j >> 4) + WD - 1) * 7 + (((q >> 2) & 3) - ((j >> 2) & 3) + 3)) * 7 +
-                    ((q & 3) - (j & 3) + 3);
-    s_bias[(h * NTOK + q) * BP + j] = __float2bfloat16(p.bias_table[rel * HEADS + h] * kLog2e);
+    float bv;
+    if (TEMPORAL) {
+      bv = j >= p.T ? -1.0e30f : (q < p.T ? p.bias_table[h * (2 * p.T - 1) + (j - q + p.T - 1)] * kLog2e : 0.f);
+    } else {
+      const int rel = (((q >> 4) - (j >> 4) + WD - 1) * 7 + (((q >> 2) & 3) - ((j >> 2) & 3) + 3)) * 7 +
+                      ((q & 3) - (j & 3) + 3);
+      bv = p.bias_table[rel * HEADS + h] * kLog2e;
+    }
+    s_bias[(h * NTOK + q) * BP + j] = __float2bfloat16(bv);
   }
   const int head = warp;
   uint32_t wq[CK][DT][2], wk[CK][DT][2], wv[CK][DT][2];
@@ -153,6 +166,12 @@ __global__ void __launch_bounds__(256, 1) stw_fused_kernel(const __grid_constant
   struct Win { int b, id, ih, iw; };
   auto decode = [&](int widx) {
     Win w;
+    if (TEMPORAL) {                       // widx = (b, pixel): b in w.b, pixel in w.iw
+      w.iw = widx % (p.H * p.W);
+      w.b = widx / (p.H * p.W);
+      w.id = w.ih = 0;
+      return w;
+    }
     w.iw = widx % nWw; widx /= nWw;
     w.ih = widx % nWh; widx /= nWh;
     w.id = widx % nWd;
@@ -160,6 +179,7 @@ __global__ void __launch_bounds__(256, 1) stw_fused_kernel(const __grid_constant
     return w;
   };
   auto src_pixel = [&](const Win& w, int n) -> int {
+    if (TEMPORAL) return n < p.T ? (w.b * p.T + n) * (p.H * p.W) + w.iw : -1;
     int od = w.id * WD + (n >> 4) + p.sd, oh = w.ih * 4 + ((n >> 2) & 3) + p.sh, ow = w.iw * 4 + (n & 3) + p.sw;
     if (od >= p.Dp) od -= p.Dp;
     if (oh >= p.H) oh -= p.H;
@@ -198,7 +218,7 @@ __global__ void __launch_bounds__(256, 1) stw_fused_kernel(const __grid_constant
     __syncthreads();                                       // S1: raw[buf] landed; previous window fully retired
     if (nxt < p.n_windows) prefetch_window(decode(nxt), buf ^ 1);
     const __nv_bfloat16* raw = s_raw + buf * NTOK * XP;
-    const bool has_mask = shifted && ((p.sd && win.id == nWd - 1) || (p.sh && win.ih == nWh - 1) ||
+    const bool has_mask = !TEMPORAL && shifted && ((p.sd && win.id == nWd - 1) || (p.sh && win.ih == nWh - 1) ||
                                       (p.sw && win.iw == nWw - 1));
 
     // ---- region-membership words: E[c] bit j = (code_j == c); query row i masks the keys in ~E[code_i]
@@ -236,15 +256,52 @@ __global__ void __launch_bounds__(256, 1) stw_fused_kernel(const __grid_constant
 #pragma unroll
       for (int o = 1; o < TPT; o <<= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
       const float rstd = src_pixel(win, n) >= 0 ? rsqrtf(sq * (1.0f / C) + p.eps) : 0.f;
+      if (TEMPORAL) {
+        // z = chanLN(x); residual stream becomes x + z (written back over the raw tile); u = LayerNorm(z)*w + b
+        float z[CPT];
+        float s2 = 0.f;
 #pragma unroll
-      for (int k = 0; k < CPT; k += 8) {
-        uint32_t pk[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int c = part * CPT + k + 2 * j;
-          pk[j] = pack_bf16((v[k + 2 * j] - mean) * rstd * s_gamma[c], (v[k + 2 * j + 1] - mean) * rstd * s_gamma[c + 1]);
+        for (int j = 0; j < CPT; ++j) {
+          z[j] = (v[j] - mean) * rstd * s_gamma[part * CPT + j];
+          s2 += z[j];
         }
-        *reinterpret_cast<uint4*>(s_xn + n * XP + part * CPT + k) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+#pragma unroll
+        for (int o = 1; o < TPT; o <<= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        const float mean2 = s2 * (1.0f / C);
+        float q2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) { const float d = z[j] - mean2; q2 += d * d; }
+#pragma unroll
+        for (int o = 1; o < TPT; o <<= 1) q2 += __shfl_xor_sync(0xffffffffu, q2, o);
+        const float rstd2 = src_pixel(win, n) >= 0 ? rsqrtf(q2 * (1.0f / C) + p.eps) : 0.f;
+        __nv_bfloat16* rw = s_raw + buf * NTOK * XP + n * XP + part * CPT;
+#pragma unroll
+        for (int k = 0; k < CPT; k += 8) {
+          uint32_t pu[4], pr[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = part * CPT + k + 2 * j;
+            const float u0 = src_pixel(win, n) >= 0 ? (z[k + 2 * j] - mean2) * rstd2 * __ldg(p.ln_w + c) + __ldg(p.ln_b + c) : 0.f;
+            const float u1 = src_pixel(win, n) >= 0
+                                 ? (z[k + 2 * j + 1] - mean2) * rstd2 * __ldg(p.ln_w + c + 1) + __ldg(p.ln_b + c + 1)
+                                 : 0.f;
+            pu[j] = pack_bf16(u0, u1);
+            pr[j] = pack_bf16(v[k + 2 * j] + z[k + 2 * j], v[k + 2 * j + 1] + z[k + 2 * j + 1]);
+          }
+          *reinterpret_cast<uint4*>(s_xn + n * XP + part * CPT + k) = make_uint4(pu[0], pu[1], pu[2], pu[3]);
+          *reinterpret_cast<uint4*>(rw + k) = make_uint4(pr[0], pr[1], pr[2], pr[3]);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < CPT; k += 8) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = part * CPT + k + 2 * j;
+            pk[j] = pack_bf16((v[k + 2 * j] - mean) * rstd * s_gamma[c], (v[k + 2 * j + 1] - mean) * rstd * s_gamma[c + 1]);
+          }
+          *reinterpret_cast<uint4*>(s_xn + n * XP + part * CPT + k) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
       }
     }
     __syncthreads();                                       // S2: s_xn, s_E ready
@@ -433,14 +490,14 @@ __global__ void __launch_bounds__(256, 1) stw_fused_kernel(const __grid_constant
   cp_async_wait<0>();
 }
 
-template <int NTOK, int DH, int C>
+template <int NTOK, int DH, int C, bool TEMPORAL = false>
 static int launch_stw(const StwParams& p, cudaStream_t st) {
   using L = StwSmem<NTOK, DH, C>;
   constexpr size_t smem = L::total;
   static bool configured = false;
   static int sms = 0;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(stw_fused_kernel<NTOK, DH, C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(stw_fused_kernel<NTOK, DH, C, TEMPORAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) {
       extdm_set_error(cudaGetErrorString(e), __FILE__, __LINE__);
@@ -451,8 +508,9 @@ static int launch_stw(const StwParams& p, cudaStream_t st) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const int grid = p.n_windows < sms ? p.n_windows : sms;
-  stw_fused_kernel<NTOK, DH, C><<<grid, 256, smem, st>>>(p);
+  const int resident = sms * (TEMPORAL ? 2 : 1);
+  const int grid = p.n_windows < resident ? p.n_windows : resident;
+  stw_fused_kernel<NTOK, DH, C, TEMPORAL><<<grid, 256, smem, st>>>(p);
   EXTDM_CHECK_LAUNCH();
   return EXTDM_OK;
 }
@@ -488,6 +546,7 @@ extern "C" int extdm_stw_fused(const void* x, void* y, const float* gamma, const
   p.bias_table = bias_table;
   p.rcos = rope_cos;
   p.rsin = rope_sin;
+  p.ln_w = p.ln_b = nullptr;
   p.B = B; p.T = T; p.H = H; p.W = W;
   p.sd = sd; p.sh = sh; p.sw = sw;
   p.Dp = (T + wd - 1) / wd * wd;
@@ -498,4 +557,36 @@ extern "C" int extdm_stw_fused(const void* x, void* y, const float* gamma, const
   if (ntok == 64 && C == 64) return launch_stw<64, 16, 64>(p, st);
   if (ntok == 64 && C == 128) return launch_stw<64, 16, 128>(p, st);
   return launch_stw<32, 32, 64>(p, st);
+}
+
+extern "C" int extdm_temporal_fused_supported(int C, int heads, int dh, int T) {
+  return heads == 8 && dh == 16 && C == 64 && T >= 1 && T <= 32;
+}
+
+extern "C" int extdm_temporal_fused(const void* x, void* y, const float* gamma, const float* ln_w, const float* ln_b,
+                                    const void* wqkv, const void* wout, const float* rel_bias, const float* rope_cos,
+                                    const float* rope_sin, int B, int T, int HW, int C, int heads, int dh, float eps,
+                                    void* stream) {
+  if (!extdm_temporal_fused_supported(C, heads, dh, T)) {
+    extdm_set_error("temporal_fused: supported for C = 64, 8 heads x 16, T <= 32", __FILE__, __LINE__);
+    return EXTDM_ERR_ARG;
+  }
+  StwParams p;
+  p.x = reinterpret_cast<const __nv_bfloat16*>(x);
+  p.y = reinterpret_cast<__nv_bfloat16*>(y);
+  p.gamma = gamma;
+  p.wqkv = reinterpret_cast<const __nv_bfloat16*>(wqkv);
+  p.wproj = reinterpret_cast<const __nv_bfloat16*>(wout);
+  p.proj_bias = nullptr;
+  p.bias_table = rel_bias;
+  p.rcos = rope_cos;
+  p.rsin = rope_sin;
+  p.ln_w = ln_w;
+  p.ln_b = ln_b;
+  p.B = B; p.T = T; p.H = HW; p.W = 1;
+  p.sd = p.sh = p.sw = 0;
+  p.Dp = 32;
+  p.n_windows = B * HW;
+  p.eps = eps;
+  return launch_stw<32, 16, 64, true>(p, static_cast<cudaStream_t>(stream));
 }

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256) groupnorm_stats_kernel(const __nv_bfloat1
   }
 }
 
-__global__ void __launch_bounds__(256) groupnorm_apply_kernel(
+__global__ void __launch_bounds__(256, 3) groupnorm_apply_kernel(
     const __nv_bfloat16* __restrict__ x, const float* __restrict__ part, int n_part, const float* __restrict__ gamma,
     const float* __restrict__ beta, const float* __restrict__ ss, long long ss_stride, int ss_off,
     const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ y, long long P, int C, int G, float eps) {
@@ -67,23 +67,43 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(
   __shared__ float s_mean[64], s_rstd[64];
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // fold the partial sums: one warp per group, lanes stride over the parts, fixed-order butterfly
-  for (int g = warp; g < G; g += 8) {
+  // fold the partial sums (fixed order => bitwise reproducible): warp w takes parts w, w+8, ...; each lane sums its
+  // parts' 2G values, a butterfly adds the lanes, thread g adds the 8 warp totals.
+  __shared__ float s_part[8][128];
+  {
+    float acc[4];                                            // 2G <= 128 values: lane owns values lane, lane+32, ...
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = 0.f;
+    if (G == 8) {
+      // common case: 16 values per part; lane = (part slot l/16 .. , value l%16): two parts per warp iteration
+      float a0 = 0.f;
+      for (int i = warp * 2 + (lane >> 4); i < n_part; i += 16)
+        a0 += part[(static_cast<long long>(b) * n_part + i) * 16 + (lane & 15)];
+      a0 += __shfl_xor_sync(0xffffffffu, a0, 16);
+      if (lane < 16) s_part[warp][lane] = a0;
+    } else {
+      for (int i = warp; i < n_part; i += 8) {
+        const float* o = part + (static_cast<long long>(b) * n_part + i) * 2 * G;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (lane + 32 * j < 2 * G) acc[j] += o[lane + 32 * j];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (lane + 32 * j < 2 * G) s_part[warp][lane + 32 * j] = acc[j];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    const int g = threadIdx.x;
     float sum = 0.f, sq = 0.f;
-    for (int i = lane; i < n_part; i += 32) {
-      const float* o = part + (static_cast<long long>(b) * n_part + i) * 2 * G;
-      sum += o[g];
-      sq += o[G + g];
-    }
-    sum = warp_sum(sum);
-    sq = warp_sum(sq);
-    if (lane == 0) {
-      const float cnt = static_cast<float>(P) * (C / G);
-      const float mean = sum / cnt;
-      const float var = fmaxf(sq / cnt - mean * mean, 0.f);
-      s_mean[g] = mean;
-      s_rstd[g] = rsqrtf(var + eps);
-    }
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { sum += s_part[w][g]; sq += s_part[w][G + g]; }
+    const float cnt = static_cast<float>(P) * (C / G);
+    const float mean = sum / cnt;
+    const float var = fmaxf(sq / cnt - mean * mean, 0.f);
+    s_mean[g] = mean;
+    s_rstd[g] = rsqrtf(var + eps);
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -103,20 +123,40 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(
   const int vecs = C / 8;
   const long long total = P * vecs;
   const long long base = static_cast<long long>(b) * P * C;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c0 = static_cast<int>(i % vecs) * 8;
-    float v[8];
-    load8(x + base + i * 8, v);
+  // 4 independent 16-byte vectors per thread and iteration (all loads issued before the first use)
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
+    uint4 xv[4], rv[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = silu(v[j] * s_a[c0 + j] + s_d[c0 + j]);
-    if (res) {
-      float r[8];
-      load8(res + base + i * 8, r);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] += r[j];
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < total) {
+        xv[u] = *reinterpret_cast<const uint4*>(x + base + i * 8);
+        if (res) rv[u] = *reinterpret_cast<const uint4*>(res + base + i * 8);
+      }
     }
-    store8(y + base + i * 8, v);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= total) continue;
+      const int c0 = static_cast<int>(i % vecs) * 8;
+      const uint32_t xw[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+      const uint32_t rw[4] = {rv[u].x, rv[u].y, rv[u].z, rv[u].w};
+      uint32_t ow[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16(xw[j]);
+        float a0 = silu(f.x * s_a[c0 + 2 * j] + s_d[c0 + 2 * j]);
+        float a1 = silu(f.y * s_a[c0 + 2 * j + 1] + s_d[c0 + 2 * j + 1]);
+        if (res) {
+          const float2 r = unpack_bf16(rw[j]);
+          a0 += r.x;
+          a1 += r.y;
+        }
+        ow[j] = pack_bf16(a0, a1);
+      }
+      *reinterpret_cast<uint4*>(y + base + i * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
   }
 }
 
@@ -625,7 +665,9 @@ extern "C" int extdm_groupnorm_apply(const void* x, const float* part, int n_par
                                      void* stream) {
   if (C % (8 * G) || G > 64 || n_part < 1) return bad_arg("groupnorm_apply: need C % (8G) == 0, n_part >= 1");
   long long per_sample = P * (C / 8);
-  int gx = grid_for(per_sample, 256, (148 * 8 + B - 1) / B);
+  int cap = (148 * 3) / B;                                   // one resident wave (3 CTAs / SM by registers)
+  if (cap < 1) cap = 1;
+  int gx = grid_for(per_sample, 256 * 4, cap);
   dim3 grid(gx, B);
   groupnorm_apply_kernel<<<grid, 256, 2 * C * sizeof(float), STREAM>>>(BF(x), part, n_part, gamma, beta, ss, ss_stride,
                                                                      ss_off, BF(res), BFW(y), P, C, G, eps);

@@ -52,6 +52,8 @@ PROTOTYPES = {
     "extdm_window_attention": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "extdm_stw_fused_supported": [_I, _I, _I, _I, _I, _I],
     "extdm_stw_fused": [_P, _P, _P, _P, _P, _P, _P, _P, _P] + [_I] * 13 + [_F, _P],
+    "extdm_temporal_fused_supported": [_I, _I, _I, _I],
+    "extdm_temporal_fused": [_P] * 10 + [_I] * 6 + [_F, _P],
     "extdm_cross_attention": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "extdm_maxpool2_frames_cl": [_P, _P, _I, _I, _L, _L, _I, _I, _I, _P],
     "extdm_bilinear_resize_frames_cl": [_P, _P, _I, _I, _L, _L, _I, _I, _I, _I, _I, _P],

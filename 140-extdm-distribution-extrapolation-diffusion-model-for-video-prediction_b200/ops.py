@@ -330,6 +330,18 @@ def stw_fused(rec, x, y, gamma, wqkv, wproj, proj_bias, bias_table, rcos, rsin, 
              meta=dict(bytes=4.0 * x.numel(), tag=f"C={Cc} {T}x{H}x{W}"))
 
 
+def temporal_fused_supported(C_, heads, dh, T):
+    return bool(_lib.load().extdm_temporal_fused_supported(C_, heads, dh, T))
+
+
+def temporal_fused(rec, x, y, gamma, ln_w, ln_b, wqkv, wout, rel_bias, rcos, rsin, heads, dh, eps=1e-5):
+    B, T, H, W, Cc = x.shape
+    rec.emit("extdm_temporal_fused", (_p(x), _p(y), _p(gamma), _p(ln_w), _p(ln_b), _p(wqkv), _p(wout), _p(rel_bias),
+                                      _p(rcos), _p(rsin), B, T, H * W, Cc, heads, dh, C.c_float(eps)),
+             keep=(x, y, gamma, ln_w, ln_b, wqkv, wout, rel_bias, rcos, rsin),
+             meta=dict(bytes=4.0 * x.numel(), tag=f"C={Cc} {T}x{H}x{W}"))
+
+
 def temporal_attention(rec, qkv, out, rel_bias, rcos, rsin, heads, dh):
     B, T, H, W, _ = qkv.shape
     rec.emit("extdm_temporal_attention", (_p(qkv), _p(out), _p(rel_bias), _p(rcos), _p(rsin), B, T, H * W, heads, dh),

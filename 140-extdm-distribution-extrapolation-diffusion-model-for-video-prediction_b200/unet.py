@@ -138,6 +138,13 @@ class UnetRunner:
     def _temporal(self, rec, x, p):
         cfg, pk = self.cfg, self.pk
         B, T, H, W, C = x.shape
+        if self.fuse_stw and ops.temporal_fused_supported(C, cfg.heads, cfg.dim_head, T):
+            y = self.buf(B, T, H, W, C)
+            ops.temporal_fused(rec, x, y, pk.f32[p + ".fn.norm.gamma"], pk.f32[p + ".fn.fn.fn.norm.weight"],
+                               pk.f32[p + ".fn.fn.fn.norm.bias"], pk.w[p + ".fn.fn.fn.attn.to_qkv.weight"],
+                               pk.w[p + ".fn.fn.fn.attn.to_out.weight"], pk.rel_bias, pk.rope_t[0], pk.rope_t[1],
+                               cfg.heads, cfg.dim_head)
+            return y
         u, xz = self.buf(B, T, H, W, C), self.buf(B, T, H, W, C)
         ops.temporal_prenorm(rec, x, pk.f32[p + ".fn.norm.gamma"], pk.f32[p + ".fn.fn.fn.norm.weight"],
                              pk.f32[p + ".fn.fn.fn.norm.bias"], u, xz)

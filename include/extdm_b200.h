@@ -169,6 +169,16 @@ int extdm_stw_fused(const void* x, void* y, const float* gamma, const void* wqkv
                     int B, int T, int H, int W, int C, int heads, int dh, int wd, int wh, int ww, int sd, int sh,
                     int sw, float eps, void* stream);
 
+/* Whole temporal attention layer Residual(PreNorm(EinopsToAndFrom(AttentionLayer))) in one kernel for C = 64
+ * (init_temporal_attn, ...cross_multi.py:253-328, 794-795): y = x + z + to_out(attn(LayerNorm(z))), z = chanLN(x)*gamma;
+ * sequence = the T <= 32 frames of one pixel, rotary over the frame index, rel_bias (heads, 2T-1) as in
+ * extdm_temporal_attention.  x, y: (B, T, HW, C) bf16 (y must not alias x); wqkv (3*heads*dh, C), wout (C, heads*dh). */
+int extdm_temporal_fused_supported(int C, int heads, int dh, int T);
+int extdm_temporal_fused(const void* x, void* y, const float* gamma, const float* ln_w, const float* ln_b,
+                         const void* wqkv, const void* wout, const float* rel_bias, const float* rope_cos,
+                         const float* rope_sin, int B, int T, int HW, int C, int heads, int dh, float eps,
+                         void* stream);
+
 /* TrajWarp (BAIR 'u12' variant, ..._traj_u12.py:719-827).  Multi-head cross attention core
  * softmax(q k^T / sqrt(dh)) v (ScaledDotProductAttention :719-728, heads split as in _reshape_to_batches
  * :783-789): q (B, Lq, ldq), k / v (B, Lk, ldk), out (B, Lq, ldo) bf16; head h = columns [h*dh, (h+1)*dh).

@@ -543,3 +543,32 @@ def test_frame_range_pool_and_resize():
     got = from_cl(z)
     close(got[:, :, T - t0:], ref, rel=1e-2, what="resize frames")
     assert got[:, :, :T - t0].abs().max() == 0
+
+
+@pytest.mark.parametrize("T,H", [(30, 8), (12, 4), (7, 8), (32, 4)])
+def test_temporal_fused_layer(T, H):
+    """Whole temporal attention layer (chanLN -> LayerNorm -> qkv -> rotary/T5-bias attention over frames -> to_out ->
+    double residual) in one kernel vs the oracle's temporal_attention (CPU fp32)."""
+    from oracle import extdm_oracle as O
+    B, C, heads, dh = 2, 64, 8, 16
+    hid = heads * dh
+    x = rnd(B, C, T, H, H, seed=1)
+    rel_emb = rnd(32, heads, seed=7) * 0.5                   # T5 bucket embedding
+    sd = {"fn.norm.gamma": (rnd(1, C, 1, 1, 1, seed=2) * 0.1 + 1).cpu(),
+          "fn.fn.fn.norm.weight": (rnd(C, seed=3) * 0.1 + 1).cpu(), "fn.fn.fn.norm.bias": (rnd(C, seed=4) * 0.1).cpu(),
+          "fn.fn.fn.attn.to_qkv.weight": rnd(3 * hid, C, seed=5, scale=C ** -0.5).to(BF).float().cpu(),
+          "fn.fn.fn.attn.to_out.weight": rnd(C, hid, seed=6, scale=hid ** -0.5).to(BF).float().cpu()}
+    xc = to_cl(x)
+    y = torch.zeros_like(xc)
+    pos_bias = O.t5_bucket_bias(rel_emb.cpu(), T)                                  # (heads, T, T)
+    i = torch.arange(T)
+    folded = torch.zeros(heads, 2 * T - 1)
+    folded[:, (i[None, :] - i[:, None]) + T - 1] = pos_bias                        # index (j - i) + T - 1
+    rc, rs = _rope_tables(32, dh)
+    assert ops.temporal_fused_supported(C, heads, dh, T)
+    ops.temporal_fused(R, xc, y, sd["fn.norm.gamma"].reshape(-1).to(DEV), sd["fn.fn.fn.norm.weight"].to(DEV),
+                       sd["fn.fn.fn.norm.bias"].to(DEV), sd["fn.fn.fn.attn.to_qkv.weight"].to(DEV).to(BF),
+                       sd["fn.fn.fn.attn.to_out.weight"].to(DEV).to(BF), folded.to(DEV), rc, rs, heads, dh)
+    with torch.no_grad():
+        ref = O.temporal_attention(xc.float().permute(0, 4, 1, 2, 3).cpu(), O.SD(sd), pos_bias, heads, dh)
+    close(from_cl(y).cpu(), ref, rel=2e-2, atol=5e-3, what="temporal fused")
