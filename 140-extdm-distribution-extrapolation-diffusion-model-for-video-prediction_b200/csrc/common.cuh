@@ -59,6 +59,21 @@ __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// One lane of a converged warp (PTX elect.sync).  Keeping the surrounding control flow warp-uniform and electing
+// only around the issue keeps descriptors / addresses in uniform registers: ptxas otherwise wraps every UTCHMMA /
+// UTMALDG issued from a divergent `lane == 0` region in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- TMA (tiled mode)
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -76,6 +91,14 @@ __device__ __forceinline__ void tma_load_5d(const CUtensorMap* m, void* dst, uin
       "%7}], [%2];" ::"r"(smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
+}
+
+// L2 prefetch of a tensor-map box (no shared memory, no barrier): hides the DRAM latency of first-touch tiles
+__device__ __forceinline__ void tma_prefetch_5d(const CUtensorMap* m, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
 }
 
 // ---------------------------------------------------------------- tcgen05 / TMEM
@@ -150,6 +173,13 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
   return __bfloat1622float2(v);
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+// x*sigmoid(x) = 0.5*x*(1 + tanh(x/2)) with the single-MUFU tanh.approx (|rel err| ~ 2^-11: below bf16 resolution)
+__device__ __forceinline__ float silu_fast(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  const float h = 0.5f * x;
+  return fmaf(h, t, h);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -9,6 +9,7 @@
 
 #include <mutex>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace extdm {
@@ -37,6 +38,8 @@ struct GemmDev {
   const float* col_shift;
   int act;
   float* gn_part;
+  // halo kernel (k x k 'same' convolutions whose 128-row tile is bh full-width rows of one frame)
+  int kh, kw, stages, a_ext_bytes;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -65,12 +68,351 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmDev& p, int tile, int
   return t;
 }
 
+// Epilogue warps (4 x 32 threads; warp w owns TMEM lanes 32*(w%4)..+31 = tile rows): drain the accumulator of each
+// tile this CTA owns, apply bias / residual / affine / activation, store, optionally emit GroupNorm partials.
+// SIMPLE: bias (+ activation) -> bf16 rows, n % 16 == 0, no residual / column affine / column groups -- the
+// convolution + GroupNorm-statistics case, kept free of the general path's code (the epilogue is instruction-fetch
+// sensitive: with one CTA per SM only these four warps hide each other's latency).
+template <int BN, bool GN, bool SIMPLE>
+__device__ __forceinline__ void epilogue_loop(const GemmDev& p, uint64_t* acc_full, uint64_t* acc_empty, float* s_gn,
+                                              uint32_t tmem_base, int warp, int lane) {
+  float* s_bias = s_gn + 128;             // [BN] bias of the current n-tile (zeros when there is no bias)
+  int staged_n0 = -1;
+  constexpr uint32_t kAccCols = BN < 32 ? 32 : BN;
+  const int q = warp & 3;                 // TMEM lane quarter this warp may access
+  const int m = q * 32 + lane;            // tile row
+  int r = m;
+  const int i1 = r % p.box[0]; r /= p.box[0];
+  const int i2 = r % p.box[1]; r /= p.box[1];
+  const int i3 = r % p.box[2]; r /= p.box[2];
+  const int i4 = r;
+  constexpr int kChunks = (BN + 15) / 16;
+  int local = 0;
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+    const int as = local & 1;
+    const uint32_t aphase = (local >> 1) & 1;
+    const TileCoord tc = decode_tile(p, tile, BN);
+    const int n0 = tc.n0;
+    const int g1 = tc.c1 + i1, g2 = tc.c2 + i2, g3 = tc.c3 + i3, g4 = tc.c4 + i4;
+    const bool row_ok = g1 < p.start[0] + p.count[0] && g2 < p.start[1] + p.count[1] &&
+                        g3 < p.start[2] + p.count[2] && g4 < p.start[3] + p.count[3];
+    const long long orow = p.out_base + g1 * p.out_stride[0] + g2 * p.out_stride[1] + g3 * p.out_stride[2] +
+                           g4 * p.out_stride[3];
+    const long long rrow = p.res_base + g1 * p.res_stride[0] + g2 * p.res_stride[1] + g3 * p.res_stride[2] +
+                           g4 * p.res_stride[3];
+    // The accumulator is drained in groups of 4 chunks (64 columns): the group body is unrolled (static register
+    // indices for the double-buffered tcgen05.ld and the prefetched residual), the group loop is not (code size).
+    // residual prefetch: bf16 residuals 64 columns (8 x 16 B) at a time, fp32 residuals 32 columns
+    uint4 rpre[8];
+    const bool res_vec = !SIMPLE && p.res != nullptr && row_ok && p.col_group >= p.n && (n0 + BN <= p.n);
+    if (n0 != staged_n0) {                // uniform over the 128 epilogue threads
+      if (staged_n0 >= 0) asm volatile("bar.sync 2, 128;" ::: "memory");        // previous tile's readers are done
+#pragma unroll
+      for (int j = m; j < BN; j += 128) s_bias[j] = (p.bias && n0 + j < p.n) ? __ldg(p.bias + n0 + j) : 0.f;
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      staged_n0 = n0;
+    }
+    auto prefetch_res = [&](int ch) {
+      if (!res_vec) return;
+      if (p.res_fp32) {
+        const float* rp = reinterpret_cast<const float*>(p.res) + rrow + n0 + ch * 16;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (ch * 16 + j * 4 < BN) rpre[j] = *reinterpret_cast<const uint4*>(rp + j * 4);
+      } else {
+        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + rrow + n0 + ch * 16;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (ch * 16 + j * 8 < BN) rpre[j] = *reinterpret_cast<const uint4*>(rp + j * 8);
+      }
+    };
+    prefetch_res(0);
+
+    mbar_wait(&acc_full[as], aphase);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + as * kAccCols + (static_cast<uint32_t>(q * 32) << 16);
+    float* sg = s_gn + as * 64;
+    uint32_t raw[2][16];
+    tmem_ld16(taddr, raw[0]);
+    constexpr int kGroups = (kChunks + 3) / 4;
+    constexpr int kCpg = BN >= 64 ? BN / 8 : 8;          // GroupNorm(8) group width in columns
+    constexpr int kNV = 2 * (64 / kCpg);                 // statistics per 64-column group (sums, sums of squares)
+#pragma unroll 1
+    for (int grp = 0; grp < kGroups; ++grp) {
+      float gst[kNV];
+      if (GN) {
+#pragma unroll
+        for (int j = 0; j < kNV; ++j) gst[j] = 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c < kChunks) {
+          const int ch = grp * 4 + c;
+          tmem_ld_wait();
+          if (ch + 1 < kChunks) tmem_ld16(taddr + (ch + 1) * 16, raw[(c + 1) & 1]);
+          const int nb = n0 + ch * 16;
+          if (row_ok && nb < p.n) {
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[c & 1][j]);
+            const long long coff =
+                SIMPLE ? nb : static_cast<long long>(nb / p.col_group) * p.col_group_stride + (nb % p.col_group);
+            const bool full = SIMPLE || (nb + 16 <= p.n);
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 bb = *reinterpret_cast<const float4*>(s_bias + ch * 16 + j);
+              v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+            }
+            if (!SIMPLE && p.res) {
+              if (res_vec) {
+                if (p.res_fp32) {
+                  const int j0 = (c & 1) * 4;
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const uint4 t = rpre[j0 + j];
+                    v[j * 4] += __uint_as_float(t.x); v[j * 4 + 1] += __uint_as_float(t.y);
+                    v[j * 4 + 2] += __uint_as_float(t.z); v[j * 4 + 3] += __uint_as_float(t.w);
+                  }
+                } else {
+                  const int j0 = c * 2;
+#pragma unroll
+                  for (int j = 0; j < 2; ++j) {
+                    const uint4 t = rpre[j0 + j];
+                    const float2 a = unpack_bf16(t.x), b2 = unpack_bf16(t.y), c2 = unpack_bf16(t.z),
+                                 d2 = unpack_bf16(t.w);
+                    v[j * 8] += a.x; v[j * 8 + 1] += a.y; v[j * 8 + 2] += b2.x; v[j * 8 + 3] += b2.y;
+                    v[j * 8 + 4] += c2.x; v[j * 8 + 5] += c2.y; v[j * 8 + 6] += d2.x; v[j * 8 + 7] += d2.y;
+                  }
+                }
+              } else if (p.res_fp32) {
+                const float* rp = reinterpret_cast<const float*>(p.res) + rrow + coff;
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (nb + j < p.n) v[j] += rp[j];
+              } else {
+                const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + rrow + coff;
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (nb + j < p.n) v[j] += __bfloat162float(rp[j]);
+              }
+            }
+            if (!SIMPLE && p.col_scale) {
+              const float* cs = p.col_scale + static_cast<long long>(g4) * p.n + nb;
+              const float* cb = p.col_shift + static_cast<long long>(g4) * p.n + nb;
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (full || nb + j < p.n) v[j] = v[j] * __ldg(cs + j) + __ldg(cb + j);
+            }
+            if (p.act) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
+            }
+            if (!SIMPLE && p.out_fp32) {
+              float* op = reinterpret_cast<float*>(p.out) + orow + coff;
+              if (full) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                  *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (nb + j < p.n) op[j] = v[j];
+              }
+            } else {
+              __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + orow + coff;
+              if (full) {
+                uint32_t pk[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+                *reinterpret_cast<uint4*>(op) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                *reinterpret_cast<uint4*>(op + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                if (GN) {
+                  // statistics of the values as stored (bf16-rounded)
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    const float2 f = unpack_bf16(pk[j]);
+                    const int g = (c * 16 + 2 * j) / kCpg;           // GroupNorm group within this 64-column group
+                    gst[g] += f.x + f.y;
+                    gst[kNV / 2 + g] += f.x * f.x + f.y * f.y;
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (nb + j < p.n) op[j] = __float2bfloat16(v[j]);
+              }
+            }
+          }
+          // next residual group (issued after this chunk's use of rpre)
+          if (!SIMPLE) {
+            if (p.res_fp32) {
+              if ((c & 1) == 1 && ch + 1 < kChunks) prefetch_res(ch + 1);
+            } else {
+              if (c == 3 && ch + 1 < kChunks) prefetch_res(ch + 1);
+            }
+          }
+        }
+      }
+      if (GN) {
+        // fixed-order butterfly over the warp: kNV per-thread values -> one total per value, held by the lanes
+        // whose high bits spell the value index (MSB first); lanes with zero low bits publish it.
+        int idx = 0, off = 16;
+#pragma unroll
+        for (int half = kNV / 2; half >= 1; half >>= 1, off >>= 1) {
+          const bool up = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < half; ++i) {
+            const float send = up ? gst[i] : gst[i + half];
+            const float keep = up ? gst[i + half] : gst[i];
+            gst[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          }
+          idx = idx * 2 + (up ? 1 : 0);
+        }
+        const int low_mask = 2 * off - 1;                 // offsets not consumed by the transposing steps
+        for (; off >= 1; off >>= 1) gst[0] += __shfl_xor_sync(0xffffffffu, gst[0], off);
+        if ((lane & low_mask) == 0) {
+          const int stat = idx / (kNV / 2), gl = idx % (kNV / 2);       // 0 = sum, 1 = sum of squares
+          sg[q * 16 + stat * 8 + grp * (kNV / 2) + gl] = gst[0];
+        }
+      }
+    }
+    // accumulator drained (all tcgen05.ld completed): hand it back to the MMA issuer
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&acc_empty[as]);
+
+    if (GN) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (m < 16)
+        p.gn_part[static_cast<long long>(tc.m_tile) * 16 + m] = (sg[m] + sg[16 + m]) + (sg[32 + m] + sg[48 + m]);
+    }
+  }
+}
+
+
+// Multi-warp SIMPLE epilogue for the one-CTA-per-SM halo kernel: EPW warps share each TMEM lane quarter and take the
+// 16-column chunks round-robin (ncu: with a single epilogue warp per scheduler the ~900 dependent instructions per
+// tile issue at one per ~5 cycles and the epilogue, not the tensor pipe or L2, bounds the kernel).
+// bias (+ activation) -> bf16 rows; optional GroupNorm(8) partial sums of the stored values.
+template <int BN, bool GN, int EPW>
+__device__ __forceinline__ void epilogue_simple(const GemmDev& p, uint64_t* acc_full, uint64_t* acc_empty, float* s_gn,
+                                                uint32_t tmem_base, int warp, int lane) {
+  constexpr uint32_t kAccCols = BN < 32 ? 32 : BN;
+  constexpr int kChunks = BN / 16;
+  constexpr int kThreads = 128 * EPW;
+  float* s_bias = s_gn;                    // [BN]
+  float* s_part = s_gn + 256;              // [2][4 quarters][kChunks][4] : {sum lo8, sum hi8, sq lo8, sq hi8}
+  const int q = warp & 3;                  // TMEM lane quarter
+  const int e = (warp - 2) >> 2;           // which of the EPW warps of this quarter
+  const int et = (warp - 2) * 32 + lane;   // epilogue thread index
+  const int m = q * 32 + lane;             // tile row
+  int r = m;
+  const int i1 = r % p.box[0]; r /= p.box[0];
+  const int i2 = r % p.box[1]; r /= p.box[1];
+  const int i3 = r % p.box[2]; r /= p.box[2];
+  const int i4 = r;
+  int staged_n0 = -1;
+  int local = 0;
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+    const int as = local & 1;
+    const uint32_t aphase = (local >> 1) & 1;
+    const TileCoord tc = decode_tile(p, tile, BN);
+    const int n0 = tc.n0;
+    const int g1 = tc.c1 + i1, g2 = tc.c2 + i2, g3 = tc.c3 + i3, g4 = tc.c4 + i4;
+    const bool row_ok = g1 < p.start[0] + p.count[0] && g2 < p.start[1] + p.count[1] &&
+                        g3 < p.start[2] + p.count[2] && g4 < p.start[3] + p.count[3];
+    __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + p.out_base + g1 * p.out_stride[0] +
+                          g2 * p.out_stride[1] + g3 * p.out_stride[2] + g4 * p.out_stride[3] + n0;
+    if (n0 != staged_n0) {
+      if (staged_n0 >= 0) asm volatile("bar.sync 2, %0;" ::"n"(kThreads) : "memory");
+      for (int j = et; j < BN; j += kThreads) s_bias[j] = (p.bias && n0 + j < p.n) ? __ldg(p.bias + n0 + j) : 0.f;
+      asm volatile("bar.sync 2, %0;" ::"n"(kThreads) : "memory");
+      staged_n0 = n0;
+    }
+    mbar_wait(&acc_full[as], aphase);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + as * kAccCols + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+    for (int ch = e; ch < kChunks; ch += EPW) {
+      uint32_t raw[16];
+      tmem_ld16(taddr + ch * 16, raw);
+      tmem_ld_wait();
+      float gst[4] = {0.f, 0.f, 0.f, 0.f};
+      if (row_ok && n0 + ch * 16 < p.n) {
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 bb = *reinterpret_cast<const float4*>(s_bias + ch * 16 + j);
+          v[j] = __uint_as_float(raw[j]) + bb.x; v[j + 1] = __uint_as_float(raw[j + 1]) + bb.y;
+          v[j + 2] = __uint_as_float(raw[j + 2]) + bb.z; v[j + 3] = __uint_as_float(raw[j + 3]) + bb.w;
+        }
+        if (p.act) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
+        }
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+        *reinterpret_cast<uint4*>(orow + ch * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(orow + ch * 16 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        if (GN) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float2 f = unpack_bf16(pk[j]);
+            gst[j >> 2] += f.x + f.y;
+            gst[2 + (j >> 2)] += f.x * f.x + f.y * f.y;
+          }
+        }
+      }
+      if (GN) {
+        // 4 values per thread -> warp totals (fixed-order butterfly); lanes 0, 8, 16, 24 publish value (lane >> 3)
+        {
+          const bool up = (lane & 16) != 0;
+          const float s0 = up ? gst[0] : gst[2], k0 = up ? gst[2] : gst[0];
+          const float s1 = up ? gst[1] : gst[3], k1 = up ? gst[3] : gst[1];
+          gst[0] = k0 + __shfl_xor_sync(0xffffffffu, s0, 16);
+          gst[1] = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
+        }
+        {
+          const bool up = (lane & 8) != 0;
+          const float s0 = up ? gst[0] : gst[1], k0 = up ? gst[1] : gst[0];
+          gst[0] = k0 + __shfl_xor_sync(0xffffffffu, s0, 8);
+        }
+        gst[0] += __shfl_xor_sync(0xffffffffu, gst[0], 4);
+        gst[0] += __shfl_xor_sync(0xffffffffu, gst[0], 2);
+        gst[0] += __shfl_xor_sync(0xffffffffu, gst[0], 1);
+        if ((lane & 7) == 0) s_part[((as * 4 + q) * kChunks + ch) * 4 + (lane >> 3)] = gst[0];
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&acc_empty[as]);
+    if (GN) {
+      asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+      if (et < 16) {
+        // value et: stat = et / 8 (0 sum, 1 sum of squares), group g = et % 8 = 8-column units [g*U, (g+1)*U)
+        constexpr int U = BN / 64;           // 8-column units per GroupNorm group (BN/8 columns per group)
+        const int stat = et >> 3, g = et & 7;
+        float tot = 0.f;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int unit = g * U + u;
+          const int ch = unit >> 1, idx = stat * 2 + (unit & 1);
+          tot += (s_part[((as * 4 + 0) * kChunks + ch) * 4 + idx] + s_part[((as * 4 + 1) * kChunks + ch) * 4 + idx]) +
+                 (s_part[((as * 4 + 2) * kChunks + ch) * 4 + idx] + s_part[((as * 4 + 3) * kChunks + ch) * 4 + idx]);
+        }
+        p.gn_part[static_cast<long long>(tc.m_tile) * 16 + et] = tot;
+      }
+    }
+  }
+}
+
 // Persistent CTAs: each loops over output tiles (tile = blockIdx.x + i*gridDim.x, n-tile fastest).  The TMA
 // producer runs ahead through the smem ring across tile boundaries; the MMA issuer alternates between two TMEM
 // accumulators so the epilogue of tile i overlaps the main loop of tile i+1.
 // GN: the epilogue also emits per-tile GroupNorm partial sums (8 groups over the BN == n columns) of the
 // bf16-rounded output -- the statistics pass of Block.forward's GroupNorm costs no extra read of the tensor.
-template <int BN, int STAGES, bool GN>
+template <int BN, int STAGES, bool GN, bool SIMPLE>
 __global__ void __launch_bounds__(kGemmThreads, BN == 256 ? 1 : 2)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                  const __grid_constant__ CUtensorMap map_b, const __grid_constant__ GemmDev p) {
@@ -117,25 +459,40 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // =========================== TMA producer
-    if (lane == 0) {
+    // =========================== TMA producer (warp-uniform control flow, one elected lane issues)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile, BN);
+        // L2 prefetch of the (un-shifted) A tile this CTA will need two tiles from now
+        if (tc.n0 == 0 && tile + 2 * gridDim.x < p.total_tiles) {
+          const TileCoord tf = decode_tile(p, tile + 2 * gridDim.x, BN);
+          const int o3 = p.tap[p.ntaps / 2][2];
+          if (elect_one()) {
+            for (int kc = 0; kc < nk; ++kc) {
+              if (kc < p.nk0)
+                tma_prefetch_5d(&map_a0, kc * kBlockK, tf.c1, tf.c2, tf.c3 + o3, tf.c4);
+              else
+                tma_prefetch_5d(&map_a1, (kc - p.nk0) * kBlockK, tf.c1, tf.c2, tf.c3 + o3, tf.c4);
+            }
+          }
+        }
         for (int tap = 0; tap < p.ntaps; ++tap) {
           const int o1 = p.tap[tap][0], o2 = p.tap[tap][1], o3 = p.tap[tap][2];
           for (int kc = 0; kc < nk; ++kc) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem + stage * kStageBytes;
-            uint8_t* sb = sa + kATileBytes;
-            mbar_expect_tx(&full_bar[stage], kStageBytes);
-            if (kc < p.nk0)
-              tma_load_5d(&map_a0, sa, &full_bar[stage], kc * kBlockK, tc.c1 + o1, tc.c2 + o2, tc.c3 + o3, tc.c4);
-            else
-              tma_load_5d(&map_a1, sa, &full_bar[stage], (kc - p.nk0) * kBlockK, tc.c1 + o1, tc.c2 + o2, tc.c3 + o3,
-                          tc.c4);
-            tma_load_2d(&map_b, sb, &full_bar[stage], (tap * nk + kc) * kBlockK, tc.n0);
+            if (elect_one()) {
+              uint8_t* sa = smem + stage * kStageBytes;
+              uint8_t* sb = sa + kATileBytes;
+              mbar_expect_tx(&full_bar[stage], kStageBytes);
+              if (kc < p.nk0)
+                tma_load_5d(&map_a0, sa, &full_bar[stage], kc * kBlockK, tc.c1 + o1, tc.c2 + o2, tc.c3 + o3, tc.c4);
+              else
+                tma_load_5d(&map_a1, sa, &full_bar[stage], (kc - p.nk0) * kBlockK, tc.c1 + o1, tc.c2 + o2, tc.c3 + o3,
+                            tc.c4);
+              tma_load_2d(&map_b, sb, &full_bar[stage], (tap * nk + kc) * kBlockK, tc.n0);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -143,9 +500,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     }
     __syncwarp();
   } else if (warp == 1) {
-    // =========================== MMA issuer (single thread)
-    if (lane == 0) {
+    // =========================== MMA issuer (warp-uniform control flow, one elected lane issues)
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN < 16 ? 16 : BN);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -154,234 +512,203 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
         const uint32_t aphase = (local >> 1) & 1;
         mbar_wait(&acc_empty[as], aphase ^ 1);            // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * kAccCols;
+        const uint32_t tmem_d = tmem_u + as * kAccCols;
         for (int it = 0; it < total_k; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-          const uint64_t da = umma_desc_sw128(sa);
-          const uint64_t db = umma_desc_sw128(sa + kATileBytes);
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+            const uint64_t da = umma_desc_sw128(sa);
+            const uint64_t db = umma_desc_sw128(sa + kATileBytes);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // advance 16 bf16 = 32 B along K inside the 128B swizzle row: +2 in (addr >> 4) units
-            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              // advance 16 bf16 = 32 B along K inside the 128B swizzle row: +2 in (addr >> 4) units
+              umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);
           }
-          umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&acc_full[as]);
+        if (elect_one()) umma_commit(&acc_full[as]);
       }
     }
     __syncwarp();
   } else {
-    // =========================== epilogue warps
-    const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int m = q * 32 + lane;            // tile row
-    int r = m;
-    const int i1 = r % p.box[0]; r /= p.box[0];
-    const int i2 = r % p.box[1]; r /= p.box[1];
-    const int i3 = r % p.box[2]; r /= p.box[2];
-    const int i4 = r;
-    constexpr int kChunks = (BN + 15) / 16;
-    int local = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
-      const int as = local & 1;
-      const uint32_t aphase = (local >> 1) & 1;
-      const TileCoord tc = decode_tile(p, tile, BN);
-      const int n0 = tc.n0;
-      const int g1 = tc.c1 + i1, g2 = tc.c2 + i2, g3 = tc.c3 + i3, g4 = tc.c4 + i4;
-      const bool row_ok = g1 < p.start[0] + p.count[0] && g2 < p.start[1] + p.count[1] &&
-                          g3 < p.start[2] + p.count[2] && g4 < p.start[3] + p.count[3];
-      const long long orow = p.out_base + g1 * p.out_stride[0] + g2 * p.out_stride[1] + g3 * p.out_stride[2] +
-                             g4 * p.out_stride[3];
-      const long long rrow = p.res_base + g1 * p.res_stride[0] + g2 * p.res_stride[1] + g3 * p.res_stride[2] +
-                             g4 * p.res_stride[3];
-      // The accumulator is drained in groups of 4 chunks (64 columns): the group body is unrolled (static register
-      // indices for the double-buffered tcgen05.ld and the prefetched residual), the group loop is not (code size).
-      // residual prefetch: bf16 residuals 64 columns (8 x 16 B) at a time, fp32 residuals 32 columns
-      uint4 rpre[8];
-      const bool res_vec = p.res != nullptr && row_ok && p.col_group >= p.n && (n0 + BN <= p.n);
-      auto prefetch_res = [&](int ch) {
-        if (!res_vec) return;
-        if (p.res_fp32) {
-          const float* rp = reinterpret_cast<const float*>(p.res) + rrow + n0 + ch * 16;
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (ch * 16 + j * 4 < BN) rpre[j] = *reinterpret_cast<const uint4*>(rp + j * 4);
-        } else {
-          const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + rrow + n0 + ch * 16;
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (ch * 16 + j * 8 < BN) rpre[j] = *reinterpret_cast<const uint4*>(rp + j * 8);
-        }
-      };
-      prefetch_res(0);
+    epilogue_loop<BN, GN, SIMPLE>(p, acc_full, acc_empty, s_gn, tmem_base, warp, lane);
+  }
 
-      mbar_wait(&acc_full[as], aphase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + as * kAccCols + (static_cast<uint32_t>(q * 32) << 16);
-      float* sg = s_gn + as * 64;
-      uint32_t raw[2][16];
-      tmem_ld16(taddr, raw[0]);
-      constexpr int kGroups = (kChunks + 3) / 4;
-      constexpr int kCpg = BN >= 64 ? BN / 8 : 8;          // GroupNorm(8) group width in columns
-      constexpr int kNV = 2 * (64 / kCpg);                 // statistics per 64-column group (sums, sums of squares)
-#pragma unroll 1
-      for (int grp = 0; grp < kGroups; ++grp) {
-        float gst[kNV];
-        if (GN) {
-#pragma unroll
-          for (int j = 0; j < kNV; ++j) gst[j] = 0.f;
-        }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (c < kChunks) {
-            const int ch = grp * 4 + c;
-            tmem_ld_wait();
-            if (ch + 1 < kChunks) tmem_ld16(taddr + (ch + 1) * 16, raw[(c + 1) & 1]);
-            const int nb = n0 + ch * 16;
-            if (row_ok && nb < p.n) {
-              float v[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[c & 1][j]);
-              const long long coff =
-                  static_cast<long long>(nb / p.col_group) * p.col_group_stride + (nb % p.col_group);
-              const bool full = (nb + 16 <= p.n);
-              if (p.bias) {
-                if (full) {
-#pragma unroll
-                  for (int j = 0; j < 16; j += 4) {
-                    const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
-                    v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
-                  }
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 16; ++j)
-                    if (nb + j < p.n) v[j] += __ldg(p.bias + nb + j);
-                }
-              }
-              if (p.res) {
-                if (res_vec) {
-                  if (p.res_fp32) {
-                    const int j0 = (c & 1) * 4;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                      const uint4 t = rpre[j0 + j];
-                      v[j * 4] += __uint_as_float(t.x); v[j * 4 + 1] += __uint_as_float(t.y);
-                      v[j * 4 + 2] += __uint_as_float(t.z); v[j * 4 + 3] += __uint_as_float(t.w);
-                    }
-                  } else {
-                    const int j0 = c * 2;
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                      const uint4 t = rpre[j0 + j];
-                      const float2 a = unpack_bf16(t.x), b2 = unpack_bf16(t.y), c2 = unpack_bf16(t.z),
-                                   d2 = unpack_bf16(t.w);
-                      v[j * 8] += a.x; v[j * 8 + 1] += a.y; v[j * 8 + 2] += b2.x; v[j * 8 + 3] += b2.y;
-                      v[j * 8 + 4] += c2.x; v[j * 8 + 5] += c2.y; v[j * 8 + 6] += d2.x; v[j * 8 + 7] += d2.y;
-                    }
-                  }
-                } else if (p.res_fp32) {
-                  const float* rp = reinterpret_cast<const float*>(p.res) + rrow + coff;
-#pragma unroll
-                  for (int j = 0; j < 16; ++j)
-                    if (nb + j < p.n) v[j] += rp[j];
-                } else {
-                  const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.res) + rrow + coff;
-#pragma unroll
-                  for (int j = 0; j < 16; ++j)
-                    if (nb + j < p.n) v[j] += __bfloat162float(rp[j]);
-                }
-              }
-              if (p.col_scale) {
-                const float* cs = p.col_scale + static_cast<long long>(g4) * p.n + nb;
-                const float* cb = p.col_shift + static_cast<long long>(g4) * p.n + nb;
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                  if (full || nb + j < p.n) v[j] = v[j] * __ldg(cs + j) + __ldg(cb + j);
-              }
-              if (p.act) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
-              }
-              if (p.out_fp32) {
-                float* op = reinterpret_cast<float*>(p.out) + orow + coff;
-                if (full) {
-#pragma unroll
-                  for (int j = 0; j < 16; j += 4)
-                    *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 16; ++j)
-                    if (nb + j < p.n) op[j] = v[j];
-                }
-              } else {
-                __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + orow + coff;
-                if (full) {
-                  uint32_t pk[8];
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
-                  *reinterpret_cast<uint4*>(op) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                  *reinterpret_cast<uint4*>(op + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                  if (GN) {
-                    // statistics of the values as stored (bf16-rounded)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                      const float2 f = unpack_bf16(pk[j]);
-                      const int g = (c * 16 + 2 * j) / kCpg;           // GroupNorm group within this 64-column group
-                      gst[g] += f.x + f.y;
-                      gst[kNV / 2 + g] += f.x * f.x + f.y * f.y;
-                    }
-                  }
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 16; ++j)
-                    if (nb + j < p.n) op[j] = __float2bfloat16(v[j]);
-                }
-              }
-            }
-            // next residual group (issued after this chunk's use of rpre)
-            if (p.res_fp32) {
-              if ((c & 1) == 1 && ch + 1 < kChunks) prefetch_res(ch + 1);
-            } else {
-              if (c == 3 && ch + 1 < kChunks) prefetch_res(ch + 1);
-            }
-          }
-        }
-        if (GN) {
-          // fixed-order butterfly over the warp: kNV per-thread values -> one total per value, held by the lanes
-          // whose high bits spell the value index (MSB first); lanes with zero low bits publish it.
-          int idx = 0, off = 16;
-#pragma unroll
-          for (int half = kNV / 2; half >= 1; half >>= 1, off >>= 1) {
-            const bool up = (lane & off) != 0;
-#pragma unroll
-            for (int i = 0; i < half; ++i) {
-              const float send = up ? gst[i] : gst[i + half];
-              const float keep = up ? gst[i + half] : gst[i];
-              gst[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-            }
-            idx = idx * 2 + (up ? 1 : 0);
-          }
-          const int low_mask = 2 * off - 1;                 // offsets not consumed by the transposing steps
-          for (; off >= 1; off >>= 1) gst[0] += __shfl_xor_sync(0xffffffffu, gst[0], off);
-          if ((lane & low_mask) == 0) {
-            const int stat = idx / (kNV / 2), gl = idx % (kNV / 2);       // 0 = sum, 1 = sum of squares
-            sg[q * 16 + stat * 8 + grp * (kNV / 2) + gl] = gst[0];
-          }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------ halo variant
+// k x k convolution with A re-use across the taps of one kernel column.  The plain kernel above re-reads the
+// 128-row A tile from L2 once per tap (9x / 49x); ncu showed the level-0 convolutions pinned at the L2 throughput
+// cap.  Here one pipeline stage is (kernel column kx, 64-channel block): TMA loads ONE box of bh + kh - 1 image rows
+// shifted by kx; the kh taps of that column are the same smem tile read at row offsets ky*bw (multiples of 8 rows,
+// so the 128B-swizzle phase is preserved and the UMMA descriptor just advances by ky*bw*128 bytes).
+// RESB: the whole weight matrix (<= ~150 KB) is loaded once per CTA and stays resident, so a stage carries A only.
+constexpr int kHaloEpw = 4;                                   // epilogue warps per TMEM lane quarter
+constexpr int kHaloThreads = 64 + 128 * kHaloEpw;
+
+template <int BN, bool GN, bool RESB>
+__global__ void __launch_bounds__(kHaloThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                 const __grid_constant__ CUtensorMap map_b, const __grid_constant__ GemmDev p) {
+  constexpr int kBTileBytes = BN * kBlockK * 2;
+  constexpr uint32_t kAccCols = BN < 32 ? 32 : BN;
+  constexpr uint32_t kTmemCols = 2 * kAccCols;
+  constexpr int kMaxStages = 8;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nk = p.nk0 + p.nk1;
+  const int ntaps = p.kh * p.kw;
+  const int resb_bytes = RESB ? ntaps * nk * kBTileBytes : 0;
+  const int stage_bytes = p.a_ext_bytes + (RESB ? 0 : p.kh * kBTileBytes);
+  uint8_t* s_resb = smem;
+  uint8_t* s_stage = smem + resb_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_stage + p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* acc_full = empty_bar + kMaxStages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* resb_bar = acc_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resb_bar + 2);      // keeps s_gn / s_bias 16-byte aligned
+  float* s_gn = reinterpret_cast<float*>(tmem_slot + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a0);
+    if (p.nk1 > 0) tma_prefetch_desc(&map_a1);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4 * kHaloEpw);
+    }
+    mbar_init(resb_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== TMA producer (warp-uniform control flow, one elected lane issues)
+    {
+      if (RESB) {
+        if (elect_one()) {
+          mbar_expect_tx(resb_bar, resb_bytes);
+          for (int t = 0; t < ntaps * nk; ++t)
+            tma_load_2d(&map_b, s_resb + t * kBTileBytes, resb_bar, t * kBlockK, 0);
         }
       }
-      // accumulator drained (all tcgen05.ld completed): hand it back to the MMA issuer
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[as]);
-
-      if (GN) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (m < 16)
-          p.gn_part[static_cast<long long>(tc.m_tile) * 16 + m] = (sg[m] + sg[16 + m]) + (sg[32 + m] + sg[48 + m]);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile, BN);
+        // L2 prefetch of the rows this CTA will need two tiles from now (centre kernel column covers all but one
+        // pixel column of the other two boxes)
+        if (tile + 2 * gridDim.x < p.total_tiles) {
+          const TileCoord tf = decode_tile(p, tile + 2 * gridDim.x, BN);
+          if (elect_one()) {
+            for (int kc = 0; kc < nk; ++kc) {
+              if (kc < p.nk0)
+                tma_prefetch_5d(&map_a0, kc * kBlockK, tf.c1, tf.c2 - p.kh / 2, tf.c3, tf.c4);
+              else
+                tma_prefetch_5d(&map_a1, (kc - p.nk0) * kBlockK, tf.c1, tf.c2 - p.kh / 2, tf.c3, tf.c4);
+            }
+          }
+        }
+        for (int kx = 0; kx < p.kw; ++kx) {
+          for (int kc = 0; kc < nk; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (elect_one()) {
+              uint8_t* sa = s_stage + stage * stage_bytes;
+              mbar_expect_tx(&full_bar[stage], stage_bytes);
+              const int x0 = tc.c1 + kx - p.kw / 2, y0 = tc.c2 - p.kh / 2;
+              if (kc < p.nk0)
+                tma_load_5d(&map_a0, sa, &full_bar[stage], kc * kBlockK, x0, y0, tc.c3, tc.c4);
+              else
+                tma_load_5d(&map_a1, sa, &full_bar[stage], (kc - p.nk0) * kBlockK, x0, y0, tc.c3, tc.c4);
+              if (!RESB) {
+                uint8_t* sb = sa + p.a_ext_bytes;
+                for (int ky = 0; ky < p.kh; ++ky)
+                  tma_load_2d(&map_b, sb + ky * kBTileBytes, &full_bar[stage],
+                              ((ky * p.kw + kx) * nk + kc) * kBlockK, tc.n0);
+              }
+            }
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
       }
     }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =========================== MMA issuer (warp-uniform control flow, one elected lane issues)
+    {
+      constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN < 16 ? 16 : BN);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const int row_shift = p.box[0] * 128;            // bytes between the A views of consecutive kernel rows
+      if (RESB) {
+        mbar_wait(resb_bar, 0);
+        tc_fence_after();
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+        const int as = local & 1;
+        const uint32_t aphase = (local >> 1) & 1;
+        mbar_wait(&acc_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_u + as * kAccCols;
+        uint32_t accumulate = 0;
+        for (int kx = 0; kx < p.kw; ++kx) {
+          for (int kc = 0; kc < nk; ++kc) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t sa = smem_u32(s_stage + stage * stage_bytes);
+              uint32_t acc = accumulate;
+              for (int ky = 0; ky < p.kh; ++ky) {
+                const uint32_t sb = RESB ? smem_u32(s_resb + ((ky * p.kw + kx) * nk + kc) * kBTileBytes)
+                                         : sa + p.a_ext_bytes + ky * kBTileBytes;
+                const uint64_t da = umma_desc_sw128(sa + ky * row_shift);
+                const uint64_t db = umma_desc_sw128(sb);
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                  umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, acc);
+                  acc = 1;
+                }
+              }
+              umma_commit(&empty_bar[stage]);
+            }
+            accumulate = 1;
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+        if (elect_one()) umma_commit(&acc_full[as]);
+      }
+    }
+    __syncwarp();
+  } else {
+    epilogue_simple<BN, GN, kHaloEpw>(p, acc_full, acc_empty, s_gn, tmem_base, warp, lane);
   }
 
   tc_fence_before();
@@ -453,14 +780,38 @@ static int sm_count() {
   return sms;
 }
 
-template <int BN, int STAGES, bool GN>
+constexpr int kSmemBudget = 232448 - 4608;       // 227 KB minus alignment slack, barriers, bias and GN scratch
+
+template <int BN, bool GN, bool RESB>
+static int launch_halo(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb, GemmDev& dev, int m_tiles,
+                       int smem_bytes, cudaStream_t stream) {
+  static int configured = 0;
+  if (smem_bytes > configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, GN, RESB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         smem_bytes);
+    if (e != cudaSuccess) {
+      extdm_set_error(cudaGetErrorString(e), __FILE__, __LINE__);
+      return EXTDM_ERR_CUDA;
+    }
+    configured = smem_bytes;
+  }
+  dev.n_tiles_n = (dev.n + BN - 1) / BN;
+  dev.total_tiles = m_tiles * dev.n_tiles_n;
+  const int resident = sm_count();
+  const int grid = dev.total_tiles < resident ? dev.total_tiles : resident;
+  conv_halo_kernel<BN, GN, RESB><<<grid, kHaloThreads, smem_bytes, stream>>>(ma0, ma1, mb, dev);
+  EXTDM_CHECK_LAUNCH();
+  return EXTDM_OK;
+}
+
+template <int BN, int STAGES, bool GN, bool SIMPLE>
 static int launch(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb, GemmDev& dev, int m_tiles,
                   cudaStream_t stream) {
   constexpr int kStageBytes = kATileBytes + BN * kBlockK * 2;
-  constexpr int smem_bytes = STAGES * kStageBytes + (2 * STAGES + 4) * 8 + 16 + 2 * 4 * 16 * 4 + 1024;
+  constexpr int smem_bytes = STAGES * kStageBytes + (2 * STAGES + 4) * 8 + 16 + 2 * 4 * 16 * 4 + 1024 + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, GN>,
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, GN, SIMPLE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) {
       extdm_set_error(cudaGetErrorString(e), __FILE__, __LINE__);
@@ -472,7 +823,7 @@ static int launch(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensor
   dev.total_tiles = m_tiles * dev.n_tiles_n;
   const int resident = sm_count() * (BN == 256 ? 1 : 2);
   const int grid = dev.total_tiles < resident ? dev.total_tiles : resident;
-  conv_gemm_kernel<BN, STAGES, GN><<<grid, kGemmThreads, smem_bytes, stream>>>(ma0, ma1, mb, dev);
+  conv_gemm_kernel<BN, STAGES, GN, SIMPLE><<<grid, kGemmThreads, smem_bytes, stream>>>(ma0, ma1, mb, dev);
   EXTDM_CHECK_LAUNCH();
   return EXTDM_OK;
 }
@@ -538,11 +889,52 @@ extern "C" int extdm_conv_gemm(const ExtdmGemm* g, void* stream_) {
     return EXTDM_ERR_ARG;
   }
 
+  // ---- halo variant: a full k x k tap grid over tiles made of whole-width rows of a single frame
+  int kk = g->ntaps == 9 ? 3 : (g->ntaps == 49 ? 7 : 0);
+  if (kk) {
+    for (int t = 0; t < g->ntaps && kk; ++t)
+      if (g->tap[t][0] != t % kk - kk / 2 || g->tap[t][1] != t / kk - kk / 2 || g->tap[t][2] != 0) kk = 0;
+  }
+  const bool simple = !g->res && !g->col_scale && !g->out_fp32 && g->col_group >= g->n && g->n % 16 == 0;
+  static const bool halo_off = getenv("EXTDM_NO_HALO") != nullptr;
+  static const bool halo7_off = getenv("EXTDM_NO_HALO7") != nullptr;
+  // measured on B200: with a single 64-channel block per tap the plain kernel at two CTAs per
+  // SM is ~8% faster (113 vs 122 us on the level-0 3x3), with two or more blocks the halo kernel wins
+  static const bool halo_all = getenv("EXTDM_HALO_ALL") != nullptr;
+  bool halo = kk && simple && !halo_off && !(kk == 7 && halo7_off) && (halo_all || dev.nk0 + dev.nk1 >= 2) && g->box[2] == 1 && g->box[3] == 1 && g->box[0] % 8 == 0 &&
+              (bn == 64 || bn == 128);
+  int ebox[4] = {g->box[0], g->box[1] + kk - 1, 1, 1};
+  bool resb = false;
+  int halo_smem = 0;
+  if (halo) {
+    const int nk = dev.nk0 + dev.nk1;
+    const int a_ext = ebox[1] * ebox[0] * 128;
+    const int btile = bn * kBlockK * 2;
+    const long long resb_bytes = static_cast<long long>(g->ntaps) * nk * btile;
+    int stages;
+    if (g->n <= bn && resb_bytes + 3ll * a_ext <= kSmemBudget) {
+      resb = true;
+      stages = static_cast<int>((kSmemBudget - resb_bytes) / a_ext);
+    } else {
+      stages = kSmemBudget / (a_ext + kk * btile);
+    }
+    if (stages > 8) stages = 8;
+    if (stages < 2) {
+      halo = false;
+    } else {
+      dev.kh = dev.kw = kk;
+      dev.stages = stages;
+      dev.a_ext_bytes = a_ext;
+      halo_smem = static_cast<int>((resb ? resb_bytes : 0) + static_cast<long long>(stages) * (a_ext + (resb ? 0 : kk * btile))) +
+                  (2 * 8 + 6) * 8 + 16 + 2048 + 1024 + 1024;
+    }
+  }
+
   CUtensorMap ma0, ma1, mb;
-  int rc = encode_a(&ma0, g->a0, g->a0_channels, g->a0_dim, g->a0_stride, g->box);
+  int rc = encode_a(&ma0, g->a0, g->a0_channels, g->a0_dim, g->a0_stride, halo ? ebox : g->box);
   if (rc) return rc;
   if (dev.nk1 > 0) {
-    rc = encode_a(&ma1, g->a1, g->a1_channels, g->a1_dim, g->a1_stride, g->box);
+    rc = encode_a(&ma1, g->a1, g->a1_channels, g->a1_dim, g->a1_stride, halo ? ebox : g->box);
     if (rc) return rc;
   } else {
     ma1 = ma0;
@@ -554,23 +946,39 @@ extern "C" int extdm_conv_gemm(const ExtdmGemm* g, void* stream_) {
   rc = encode_map(&mb, g->w, 2, wd, ws, wb, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
   if (rc) return rc;
 
+  if (g->gn_partials && (g->n != bn || bn < 64 || g->out_fp32 || g->col_group < g->n || g->box[3] != 1)) {
+    extdm_set_error("extdm_conv_gemm: gn_partials needs n in {64,128,256} (= block_n), bf16 output, box[3] == 1",
+                    __FILE__, __LINE__);
+    return EXTDM_ERR_ARG;
+  }
+  if (halo) {
+    const bool gn = g->gn_partials != nullptr;
+#define HALO(BN_, GN_, RB_) return launch_halo<BN_, GN_, RB_>(ma0, ma1, mb, dev, m_tiles, halo_smem, stream)
+    if (bn == 64) {
+      if (gn) { if (resb) HALO(64, true, true); else HALO(64, true, false); }
+      else { if (resb) HALO(64, false, true); else HALO(64, false, false); }
+    } else {
+      if (gn) { if (resb) HALO(128, true, true); else HALO(128, true, false); }
+      else { if (resb) HALO(128, false, true); else HALO(128, false, false); }
+    }
+#undef HALO
+  }
   if (g->gn_partials) {
     // per-tile GroupNorm partials: one n-tile covering all channels, 8 groups, bf16 dense rows, tile within a sample
-    if (g->n != bn || bn < 64 || g->out_fp32 || g->col_group < g->n || g->box[3] != 1) {
-      extdm_set_error("extdm_conv_gemm: gn_partials needs n in {64,128,256} (= block_n), bf16 output, box[3] == 1",
-                      __FILE__, __LINE__);
-      return EXTDM_ERR_ARG;
-    }
+#define PLAIN(BN_, ST_, GN_)                                                                  \
+  return simple ? launch<BN_, ST_, GN_, true>(ma0, ma1, mb, dev, m_tiles, stream)            \
+                : launch<BN_, ST_, GN_, false>(ma0, ma1, mb, dev, m_tiles, stream)
     switch (bn) {
-      case 64: return launch<64, 4, true>(ma0, ma1, mb, dev, m_tiles, stream);
-      case 128: return launch<128, 3, true>(ma0, ma1, mb, dev, m_tiles, stream);
-      default: return launch<256, 4, true>(ma0, ma1, mb, dev, m_tiles, stream);
+      case 64: PLAIN(64, 4, true);
+      case 128: PLAIN(128, 3, true);
+      default: PLAIN(256, 4, true);
     }
   }
   switch (bn) {
-    case 16: return launch<16, 5, false>(ma0, ma1, mb, dev, m_tiles, stream);
-    case 64: return launch<64, 4, false>(ma0, ma1, mb, dev, m_tiles, stream);
-    case 128: return launch<128, 3, false>(ma0, ma1, mb, dev, m_tiles, stream);
-    default: return launch<256, 4, false>(ma0, ma1, mb, dev, m_tiles, stream);
+    case 16: PLAIN(16, 5, false);
+    case 64: PLAIN(64, 4, false);
+    case 128: PLAIN(128, 3, false);
+    default: PLAIN(256, 4, false);
   }
+#undef PLAIN
 }

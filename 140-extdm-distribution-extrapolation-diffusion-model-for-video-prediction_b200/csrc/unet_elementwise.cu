@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256) groupnorm_stats_kernel(const __nv_bfloat1
   }
 }
 
-__global__ void __launch_bounds__(256, 3) groupnorm_apply_kernel(
+__global__ void __launch_bounds__(256, 4) groupnorm_apply_kernel(
     const __nv_bfloat16* __restrict__ x, const float* __restrict__ part, int n_part, const float* __restrict__ gamma,
     const float* __restrict__ beta, const float* __restrict__ ss, long long ss_stride, int ss_off,
     const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ y, long long P, int C, int G, float eps) {
@@ -146,8 +146,8 @@ __global__ void __launch_bounds__(256, 3) groupnorm_apply_kernel(
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 f = unpack_bf16(xw[j]);
-        float a0 = silu(f.x * s_a[c0 + 2 * j] + s_d[c0 + 2 * j]);
-        float a1 = silu(f.y * s_a[c0 + 2 * j + 1] + s_d[c0 + 2 * j + 1]);
+        float a0 = silu_fast(f.x * s_a[c0 + 2 * j] + s_d[c0 + 2 * j]);
+        float a1 = silu_fast(f.y * s_a[c0 + 2 * j + 1] + s_d[c0 + 2 * j + 1]);
         if (res) {
           const float2 r = unpack_bf16(rw[j]);
           a0 += r.x;
@@ -665,7 +665,7 @@ extern "C" int extdm_groupnorm_apply(const void* x, const float* part, int n_par
                                      void* stream) {
   if (C % (8 * G) || G > 64 || n_part < 1) return bad_arg("groupnorm_apply: need C % (8G) == 0, n_part >= 1");
   long long per_sample = P * (C / 8);
-  int cap = (148 * 3) / B;                                   // one resident wave (3 CTAs / SM by registers)
+  int cap = (148 * 4) / B;                                   // one resident wave (4 CTAs / SM by registers)
   if (cap < 1) cap = 1;
   int gx = grid_for(per_sample, 256 * 4, cap);
   dim3 grid(gx, B);
