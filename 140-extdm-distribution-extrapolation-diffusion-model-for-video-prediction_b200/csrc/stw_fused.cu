@@ -14,6 +14,8 @@
 //   * the -100 shift mask is a 64-bit "different region" word per query row built with 8 ballots per window.
 // (64-token x 64..128-channel tiles are below a tcgen05 tile of M = 128 rows per CTA and the score work is
 // MUFU/issue bound, not MMA bound -- 537 M exponentials per level-0 launch -- so the warp-level tensor path is used.)
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/extdm_b200.h"
 
@@ -515,6 +517,397 @@ static int launch_stw(const StwParams& p, cudaStream_t st) {
   return EXTDM_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------ 16-warp variant
+// Same layer, 512 threads: TWO warps per head, each owning half of the query m-tiles of the window.  ncu on the
+// 8-warp kernel showed two warps per scheduler issuing one dependent instruction per ~7 cycles ("wait" / "selected"
+// stalls, 21% issue utilisation); doubling the warps per SM doubles the latency hiding.  To fit 128 registers per
+// thread the Wq/Wk/Wv tiles go back to shared memory (ldmatrix per use) and K is exchanged between the two warps of
+// a head through shared memory (one 64-thread named barrier per head).  C = 64 only (231 KB of shared memory).
+template <int NTOK, int DH, int C>
+struct Stw16Smem {
+  static constexpr int HEADS = 8;
+  static constexpr int HID = HEADS * DH;
+  static constexpr int XP = C + 8, HP = HID + 8, BP = NTOK + 8;
+  static constexpr size_t wproj = 0;                                          // [C][HP]
+  static constexpr size_t wqkv = wproj + size_t(C) * HP * 2;                  // [3*HID][XP]
+  static constexpr size_t bias = wqkv + size_t(3 * HID) * XP * 2;             // [HEADS][NTOK][BP]
+  static constexpr size_t raw = bias + size_t(HEADS) * NTOK * BP * 2;         // 2 x [NTOK][XP]
+  static constexpr size_t xn = raw + 2 * size_t(NTOK) * XP * 2;               // [NTOK][XP]
+  static constexpr size_t k = xn + size_t(NTOK) * XP * 2;                     // [NTOK][HP]
+  static constexpr size_t v = k + size_t(NTOK) * HP * 2;                      // [NTOK][HP]
+  static constexpr size_t o = v + size_t(NTOK) * HP * 2;                      // [NTOK][HP]
+  static constexpr size_t rope = o + size_t(NTOK) * HP * 2;
+  static constexpr size_t misc = rope + 2 * size_t(NTOK) * (DH / 2) * 4;
+  static constexpr size_t emask = misc + 2 * size_t(C) * 4;
+  static constexpr size_t total = emask + 2 * 8 * 4;
+};
+
+template <int NTOK, int DH, int C>
+__global__ void __launch_bounds__(512, 1) stw_fused16_kernel(const __grid_constant__ StwParams p) {
+  using L = Stw16Smem<NTOK, DH, C>;
+  constexpr int HEADS = 8, HID = L::HID, XP = L::XP, HP = L::HP, BP = L::BP;
+  constexpr int NTH = 512;
+  constexpr int WD = NTOK / 16;
+  constexpr int MT = NTOK / 16, MH = MT / 2;   // m-tiles per window / per warp
+  constexpr int DT = DH / 8, KS = DH / 16, NT = NTOK / 8, CK = C / 16;
+  constexpr int TPT = NTH / NTOK, CPT = C / TPT;
+  static_assert(MT % 2 == 0 && CPT == 8 || CPT == 4, "unsupported window / channel combination");
+  extern __shared__ __align__(16) uint8_t sm[];
+  __nv_bfloat16* s_wproj = reinterpret_cast<__nv_bfloat16*>(sm + L::wproj);
+  __nv_bfloat16* s_wqkv = reinterpret_cast<__nv_bfloat16*>(sm + L::wqkv);
+  __nv_bfloat16* s_bias = reinterpret_cast<__nv_bfloat16*>(sm + L::bias);
+  __nv_bfloat16* s_raw = reinterpret_cast<__nv_bfloat16*>(sm + L::raw);
+  __nv_bfloat16* s_xn = reinterpret_cast<__nv_bfloat16*>(sm + L::xn);
+  __nv_bfloat16* s_k = reinterpret_cast<__nv_bfloat16*>(sm + L::k);
+  __nv_bfloat16* s_v = reinterpret_cast<__nv_bfloat16*>(sm + L::v);
+  __nv_bfloat16* s_o = reinterpret_cast<__nv_bfloat16*>(sm + L::o);
+  float* s_cos = reinterpret_cast<float*>(sm + L::rope);
+  float* s_sin = s_cos + NTOK * (DH / 2);
+  float* s_gamma = reinterpret_cast<float*>(sm + L::misc);
+  float* s_pbias = s_gamma + C;
+  uint32_t* s_E = reinterpret_cast<uint32_t*>(sm + L::emask);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
+  const int head = warp & 7, half = warp >> 3;
+  const bool shifted = (p.sd | p.sh | p.sw) != 0;
+  const int nWw = p.W / 4, nWh = p.H / 4, nWd = p.Dp / WD;
+  const int lrow = lane & 15, lcol = (lane >> 4) * 8;
+
+  for (int i = tid; i < 3 * HID * (C / 8); i += NTH) {
+    const int r = i / (C / 8), c8 = i % (C / 8);
+    *reinterpret_cast<uint4*>(s_wqkv + r * XP + c8 * 8) = *reinterpret_cast<const uint4*>(p.wqkv + r * C + c8 * 8);
+  }
+  for (int i = tid; i < C * (HID / 8); i += NTH) {
+    const int r = i / (HID / 8), c8 = i % (HID / 8);
+    *reinterpret_cast<uint4*>(s_wproj + r * HP + c8 * 8) = *reinterpret_cast<const uint4*>(p.wproj + r * HID + c8 * 8);
+  }
+  for (int i = tid; i < NTOK * (DH / 2); i += NTH) { s_cos[i] = p.rcos[i]; s_sin[i] = p.rsin[i]; }
+  for (int i = tid; i < C; i += NTH) { s_gamma[i] = p.gamma[i]; s_pbias[i] = p.proj_bias ? p.proj_bias[i] : 0.f; }
+  for (int i = tid; i < HEADS * NTOK * NTOK; i += NTH) {
+    const int j = i % NTOK, q = (i / NTOK) % NTOK, h = i / (NTOK * NTOK);
+    const int rel = (((q >> 4) - (j >> 4) + WD - 1) * 7 + (((q >> 2) & 3) - ((j >> 2) & 3) + 3)) * 7 +
+                    ((q & 3) - (j & 3) + 3);
+    s_bias[(h * NTOK + q) * BP + j] = __float2bfloat16(p.bias_table[rel * HEADS + h] * kLog2e);
+  }
+
+  struct Win { int b, id, ih, iw; };
+  auto decode = [&](int widx) {
+    Win w;
+    w.iw = widx % nWw; widx /= nWw;
+    w.ih = widx % nWh; widx /= nWh;
+    w.id = widx % nWd;
+    w.b = widx / nWd;
+    return w;
+  };
+  auto src_pixel = [&](const Win& w, int n) -> int {
+    int od = w.id * WD + (n >> 4) + p.sd, oh = w.ih * 4 + ((n >> 2) & 3) + p.sh, ow = w.iw * 4 + (n & 3) + p.sw;
+    if (od >= p.Dp) od -= p.Dp;
+    if (oh >= p.H) oh -= p.H;
+    if (ow >= p.W) ow -= p.W;
+    return od < p.T ? ((w.b * p.T + od) * p.H + oh) * p.W + ow : -1;
+  };
+  auto region_code = [&](const Win& w, int n) -> int {
+    int c = 0;
+    if (p.sd && w.id == nWd - 1 && (n >> 4) >= WD - p.sd) c |= 1;
+    if (p.sh && w.ih == nWh - 1 && ((n >> 2) & 3) >= 4 - p.sh) c |= 2;
+    if (p.sw && w.iw == nWw - 1 && (n & 3) >= 4 - p.sw) c |= 4;
+    return c;
+  };
+  auto prefetch_window = [&](const Win& w, int buf) {
+    __nv_bfloat16* dst = s_raw + buf * NTOK * XP;
+    for (int i = tid; i < NTOK * (C / 8); i += NTH) {
+      const int n = i / (C / 8), c8 = i % (C / 8);
+      const int s = src_pixel(w, n);
+      cp_async16(dst + n * XP + c8 * 8, p.x + (s >= 0 ? static_cast<long long>(s) * C + c8 * 8 : 0), s >= 0 ? 16 : 0);
+    }
+    cp_async_commit();
+  };
+
+  int widx = blockIdx.x;
+  int buf = 0;
+  if (widx < p.n_windows) prefetch_window(decode(widx), 0);
+  const float qscale = rsqrtf(static_cast<float>(DH)) * kLog2e;
+  constexpr float kMask = -100.0f * kLog2e;
+
+  for (; widx < p.n_windows; widx += gridDim.x) {
+    const Win win = decode(widx);
+    const int nxt = widx + gridDim.x;
+    cp_async_wait<0>();
+    __syncthreads();                                       // S1
+    if (nxt < p.n_windows) prefetch_window(decode(nxt), buf ^ 1);
+    const __nv_bfloat16* raw = s_raw + buf * NTOK * XP;
+    const bool has_mask = shifted && ((p.sd && win.id == nWd - 1) || (p.sh && win.ih == nWh - 1) ||
+                                      (p.sw && win.iw == nWw - 1));
+    if (has_mask && warp < NTOK / 32) {
+      const int code = region_code(win, warp * 32 + lane);
+      uint32_t mine = 0;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t bal = __ballot_sync(0xffffffffu, code == c);
+        if (lane == c) mine = bal;
+      }
+      if (lane < 8) s_E[warp * 8 + lane] = mine;
+    }
+    // ---- channel LayerNorm: TPT threads per token, CPT channels each
+    {
+      const int n = tid / TPT, part = tid % TPT;
+      float v[CPT];
+      if constexpr (CPT == 8) {
+        const uint4 t = *reinterpret_cast<const uint4*>(raw + n * XP + part * CPT);
+        const float2 a = unpack_bf16(t.x), b = unpack_bf16(t.y), c = unpack_bf16(t.z), d = unpack_bf16(t.w);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+      } else {
+        const uint2 t = *reinterpret_cast<const uint2*>(raw + n * XP + part * CPT);
+        const float2 a = unpack_bf16(t.x), b = unpack_bf16(t.y);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) sum += v[j];
+#pragma unroll
+      for (int o = 1; o < TPT; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float mean = sum * (1.0f / C);
+      float sq = 0.f;
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) { const float d = v[j] - mean; sq += d * d; }
+#pragma unroll
+      for (int o = 1; o < TPT; o <<= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      const float rstd = src_pixel(win, n) >= 0 ? rsqrtf(sq * (1.0f / C) + p.eps) : 0.f;
+      uint32_t pk[CPT / 2];
+#pragma unroll
+      for (int j = 0; j < CPT / 2; ++j) {
+        const int c = part * CPT + 2 * j;
+        pk[j] = pack_bf16((v[2 * j] - mean) * rstd * s_gamma[c], (v[2 * j + 1] - mean) * rstd * s_gamma[c + 1]);
+      }
+      if constexpr (CPT == 8)
+        *reinterpret_cast<uint4*>(s_xn + n * XP + part * CPT) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      else
+        *reinterpret_cast<uint2*>(s_xn + n * XP + part * CPT) = make_uint2(pk[0], pk[1]);
+    }
+    __syncthreads();                                       // S2: s_xn, s_E ready
+
+    // ---- projections of this warp's m-tiles: Q -> registers, K (rotated) and V -> shared memory
+    uint32_t qa[MH][KS][4];
+    const __nv_bfloat16* wq = s_wqkv + (head * DH) * XP;
+    const __nv_bfloat16* wk = s_wqkv + (HID + head * DH) * XP;
+    const __nv_bfloat16* wv = s_wqkv + (2 * HID + head * DH) * XP;
+#pragma unroll
+    for (int mi = 0; mi < MH; ++mi) {
+      const int mt = half * MH + mi;
+      float aq[DT][4], ak[DT][4], av[DT][4];
+#pragma unroll
+      for (int dt = 0; dt < DT; ++dt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { aq[dt][j] = 0.f; ak[dt][j] = 0.f; av[dt][j] = 0.f; }
+#pragma unroll
+      for (int ks = 0; ks < CK; ++ks) {
+        uint32_t a[4];
+        ldsm_x4(a, s_xn + (mt * 16 + lrow) * XP + ks * 16 + lcol);
+#pragma unroll
+        for (int dp = 0; dp < DT / 2; ++dp) {
+          // weight rows dp*16..+15 (n) x channels ks*16..+15 (k): B fragments of two n-tiles
+          uint32_t bq[4], bk[4], bv[4];
+          const int wrow = dp * 16 + (lane & 7) + ((lane >> 4) & 1) * 8, wcol = ks * 16 + ((lane >> 3) & 1) * 8;
+          ldsm_x4(bq, wq + wrow * XP + wcol);
+          ldsm_x4(bk, wk + wrow * XP + wcol);
+          ldsm_x4(bv, wv + wrow * XP + wcol);
+          mma16816(aq[2 * dp], a, bq[0], bq[1]);
+          mma16816(aq[2 * dp + 1], a, bq[2], bq[3]);
+          mma16816(ak[2 * dp], a, bk[0], bk[1]);
+          mma16816(ak[2 * dp + 1], a, bk[2], bk[3]);
+          mma16816(av[2 * dp], a, bv[0], bv[1]);
+          mma16816(av[2 * dp + 1], a, bv[2], bv[3]);
+        }
+      }
+#pragma unroll
+      for (int dt = 0; dt < DT; ++dt) {
+        const int pr = dt * 4 + tg;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int tok = mt * 16 + hf * 8 + g;
+          const float c = s_cos[tok * (DH / 2) + pr], s = s_sin[tok * (DH / 2) + pr];
+          const float k0 = ak[dt][hf * 2], k1 = ak[dt][hf * 2 + 1];
+          *reinterpret_cast<uint32_t*>(s_k + tok * HP + head * DH + dt * 8 + tg * 2) =
+              pack_bf16(k0 * c - k1 * s, k1 * c + k0 * s);
+          const float q0 = aq[dt][hf * 2] * qscale, q1 = aq[dt][hf * 2 + 1] * qscale;
+          qa[mi][dt / 2][(dt % 2) * 2 + hf] = pack_bf16(q0 * c - q1 * s, q1 * c + q0 * s);
+          *reinterpret_cast<uint32_t*>(s_v + tok * HP + head * DH + dt * 8 + tg * 2) =
+              pack_bf16(av[dt][hf * 2], av[dt][hf * 2 + 1]);
+        }
+      }
+    }
+    // the two warps of this head exchange K / V halves
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + head) : "memory");
+    uint32_t kfrag[NT][KS][2];
+#pragma unroll
+    for (int np = 0; np < NT / 2; ++np)
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t kf[4];
+        ldsm_x4(kf, s_k + (np * 16 + (lane & 7) + ((lane >> 4) & 1) * 8) * HP + head * DH + ks * 16 +
+                        ((lane >> 3) & 1) * 8);
+        kfrag[2 * np][ks][0] = kf[0]; kfrag[2 * np][ks][1] = kf[1];
+        kfrag[2 * np + 1][ks][0] = kf[2]; kfrag[2 * np + 1][ks][1] = kf[3];
+      }
+
+    const __nv_bfloat16* bias_h = s_bias + head * NTOK * BP;
+#pragma unroll
+    for (int mi = 0; mi < MH; ++mi) {
+      const int mt = half * MH + mi;
+      const int r0 = mt * 16 + g, r1 = r0 + 8;
+      float s[NT][4];
+#pragma unroll
+      for (int np = 0; np < NT / 2; ++np) {
+        uint32_t bb[4];
+        ldsm_x4(bb, bias_h + (mt * 16 + lrow) * BP + np * 16 + lcol);
+        s[2 * np][0] = bf_lo(bb[0]); s[2 * np][1] = bf_hi(bb[0]);
+        s[2 * np][2] = bf_lo(bb[1]); s[2 * np][3] = bf_hi(bb[1]);
+        s[2 * np + 1][0] = bf_lo(bb[2]); s[2 * np + 1][1] = bf_hi(bb[2]);
+        s[2 * np + 1][2] = bf_lo(bb[3]); s[2 * np + 1][3] = bf_hi(bb[3]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) mma16816(s[nt], qa[mi][ks], kfrag[nt][ks][0], kfrag[nt][ks][1]);
+      if (has_mask) {
+        const int c0 = region_code(win, r0), c1 = region_code(win, r1);
+        uint32_t e0[NTOK / 32], e1[NTOK / 32];
+#pragma unroll
+        for (int w = 0; w < NTOK / 32; ++w) { e0[w] = ~s_E[w * 8 + c0]; e1[w] = ~s_E[w * 8 + c1]; }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const int bit = (nt * 8) % 32 + tg * 2;
+          const uint32_t m0 = e0[nt / 4] >> bit, m1 = e1[nt / 4] >> bit;
+          if (m0 & 1) s[nt][0] += kMask;
+          if (m0 & 2) s[nt][1] += kMask;
+          if (m1 & 1) s[nt][2] += kMask;
+          if (m1 & 2) s[nt][3] += kMask;
+        }
+      }
+      float m0 = -3.0e38f, m1 = -3.0e38f;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
+        m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
+      }
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        s[nt][0] = fast_exp2(s[nt][0] - m0);
+        s[nt][1] = fast_exp2(s[nt][1] - m0);
+        s[nt][2] = fast_exp2(s[nt][2] - m1);
+        s[nt][3] = fast_exp2(s[nt][3] - m1);
+        l0 += s[nt][0] + s[nt][1];
+        l1 += s[nt][2] + s[nt][3];
+      }
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+      const float inv0 = __frcp_rn(l0), inv1 = __frcp_rn(l1);
+      float o[DT][4];
+#pragma unroll
+      for (int dt = 0; dt < DT; ++dt) { o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f; }
+#pragma unroll
+      for (int ps = 0; ps < NTOK / 16; ++ps) {
+        uint32_t a[4];
+        a[0] = pack_bf16(s[2 * ps][0], s[2 * ps][1]);
+        a[1] = pack_bf16(s[2 * ps][2], s[2 * ps][3]);
+        a[2] = pack_bf16(s[2 * ps + 1][0], s[2 * ps + 1][1]);
+        a[3] = pack_bf16(s[2 * ps + 1][2], s[2 * ps + 1][3]);
+#pragma unroll
+        for (int dp = 0; dp < DT / 2; ++dp) {
+          uint32_t vb[4];
+          ldsm_x4_trans(vb, s_v + (ps * 16 + lrow) * HP + head * DH + dp * 16 + lcol);
+          mma16816(o[2 * dp], a, vb[0], vb[1]);
+          mma16816(o[2 * dp + 1], a, vb[2], vb[3]);
+        }
+      }
+#pragma unroll
+      for (int dt = 0; dt < DT; ++dt) {
+        *reinterpret_cast<uint32_t*>(s_o + r0 * HP + head * DH + dt * 8 + tg * 2) =
+            pack_bf16(o[dt][0] * inv0, o[dt][1] * inv0);
+        *reinterpret_cast<uint32_t*>(s_o + r1 * HP + head * DH + dt * 8 + tg * 2) =
+            pack_bf16(o[dt][2] * inv1, o[dt][3] * inv1);
+      }
+    }
+    __syncthreads();                                       // S3: s_o complete; s_xn dead
+
+    // ---- output projection: warp = (n-tile = warp & 7 [C = 64: 8 n-tiles], m-tiles of its half)
+    {
+      static_assert(C == 64, "16-warp variant: C = 64");
+      const int ntile = warp & 7;
+      float acc[MH][4];
+#pragma unroll
+      for (int mi = 0; mi < MH; ++mi) acc[mi][0] = acc[mi][1] = acc[mi][2] = acc[mi][3] = 0.f;
+#pragma unroll
+      for (int kp = 0; kp < HID / 32; ++kp) {
+        uint32_t b[4];
+        ldsm_x4(b, s_wproj + (ntile * 8 + (lane & 7)) * HP + kp * 32 + (lane >> 3) * 8);
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+          for (int mi = 0; mi < MH; ++mi) {
+            uint32_t a[4];
+            ldsm_x4(a, s_o + ((half * MH + mi) * 16 + lrow) * HP + (kp * 2 + kk) * 16 + lcol);
+            mma16816(acc[mi], a, b[kk * 2], b[kk * 2 + 1]);
+          }
+      }
+#pragma unroll
+      for (int mi = 0; mi < MH; ++mi) {
+        const int col = ntile * 8 + tg * 2;
+        const float b0 = s_pbias[col], b1 = s_pbias[col + 1];
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int tok = (half * MH + mi) * 16 + hf * 8 + g;
+          const float2 r = unpack_bf16(*reinterpret_cast<const uint32_t*>(raw + tok * XP + col));
+          *reinterpret_cast<uint32_t*>(s_xn + tok * XP + col) =
+              pack_bf16(acc[mi][hf * 2] + b0 + r.x, acc[mi][hf * 2 + 1] + b1 + r.y);
+        }
+      }
+    }
+    __syncthreads();                                       // S4
+    for (int i = tid; i < NTOK * (C / 8); i += NTH) {
+      const int n = i / (C / 8), c8 = i % (C / 8);
+      const int d = src_pixel(win, n);
+      if (d >= 0)
+        *reinterpret_cast<uint4*>(p.y + static_cast<long long>(d) * C + c8 * 8) =
+            *reinterpret_cast<const uint4*>(s_xn + n * XP + c8 * 8);
+    }
+    buf ^= 1;
+  }
+  cp_async_wait<0>();
+}
+
+template <int NTOK, int DH, int C>
+static int launch_stw16(const StwParams& p, cudaStream_t st) {
+  using L = Stw16Smem<NTOK, DH, C>;
+  constexpr size_t smem = L::total;
+  static bool configured = false;
+  static int sms = 0;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(stw_fused16_kernel<NTOK, DH, C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) {
+      extdm_set_error(cudaGetErrorString(e), __FILE__, __LINE__);
+      return EXTDM_ERR_CUDA;
+    }
+    configured = true;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int grid = p.n_windows < sms ? p.n_windows : sms;
+  stw_fused16_kernel<NTOK, DH, C><<<grid, 512, smem, st>>>(p);
+  EXTDM_CHECK_LAUNCH();
+  return EXTDM_OK;
+}
+
 }  // namespace extdm
 
 using namespace extdm;
@@ -554,9 +947,10 @@ extern "C" int extdm_stw_fused(const void* x, void* y, const float* gamma, const
   p.eps = eps;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int ntok = wd * wh * ww;
-  if (ntok == 64 && C == 64) return launch_stw<64, 16, 64>(p, st);
+  static const bool use8 = getenv("EXTDM_STW8") != nullptr;       // A/B switch: 8-warp kernel for every shape
+  if (ntok == 64 && C == 64) return use8 ? launch_stw<64, 16, 64>(p, st) : launch_stw16<64, 16, 64>(p, st);
   if (ntok == 64 && C == 128) return launch_stw<64, 16, 128>(p, st);
-  return launch_stw<32, 32, 64>(p, st);
+  return launch_stw<32, 32, 64>(p, st);       // (2,4,4) windows: the 16-warp layout would need 233 KB of shared memory
 }
 
 extern "C" int extdm_temporal_fused_supported(int C, int heads, int dh, int T) {
