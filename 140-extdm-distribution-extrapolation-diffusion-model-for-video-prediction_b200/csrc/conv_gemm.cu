@@ -412,8 +412,16 @@ __device__ __forceinline__ void epilogue_simple(const GemmDev& p, uint64_t* acc_
 // accumulators so the epilogue of tile i overlaps the main loop of tile i+1.
 // GN: the epilogue also emits per-tile GroupNorm partial sums (8 groups over the BN == n columns) of the
 // bf16-rounded output -- the statistics pass of Block.forward's GroupNorm costs no extra read of the tensor.
+// SIMPLE launches use the multi-warp epilogue: EPW warps per TMEM lane quarter (the epilogue, not the tensor pipe,
+// paces the short-K shapes), so the block is 64 + 128*EPW threads.
+template <int BN, bool SIMPLE>
+struct PlainCfg {
+  static constexpr int kEpw = SIMPLE ? (BN == 256 ? 4 : 2) : 1;
+  static constexpr int kThreads = 64 + 128 * kEpw;
+};
+
 template <int BN, int STAGES, bool GN, bool SIMPLE>
-__global__ void __launch_bounds__(kGemmThreads, BN == 256 ? 1 : 2)
+__global__ void __launch_bounds__(PlainCfg<BN, SIMPLE>::kThreads, BN == 256 ? 1 : 2)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                  const __grid_constant__ CUtensorMap map_b, const __grid_constant__ GemmDev p) {
   constexpr int kBTileBytes = BN * kBlockK * 2;
@@ -445,7 +453,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4);
+      mbar_init(&acc_empty[s], 4 * PlainCfg<BN, SIMPLE>::kEpw);
     }
     fence_barrier_init();
   }
@@ -534,7 +542,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     }
     __syncwarp();
   } else {
-    epilogue_loop<BN, GN, SIMPLE>(p, acc_full, acc_empty, s_gn, tmem_base, warp, lane);
+    if constexpr (SIMPLE)
+      epilogue_simple<BN, GN, PlainCfg<BN, SIMPLE>::kEpw>(p, acc_full, acc_empty, s_gn, tmem_base, warp, lane);
+    else
+      epilogue_loop<BN, GN, false>(p, acc_full, acc_empty, s_gn, tmem_base, warp, lane);
   }
 
   tc_fence_before();
@@ -808,7 +819,7 @@ template <int BN, int STAGES, bool GN, bool SIMPLE>
 static int launch(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb, GemmDev& dev, int m_tiles,
                   cudaStream_t stream) {
   constexpr int kStageBytes = kATileBytes + BN * kBlockK * 2;
-  constexpr int smem_bytes = STAGES * kStageBytes + (2 * STAGES + 4) * 8 + 16 + 2 * 4 * 16 * 4 + 1024 + 1024;
+  constexpr int smem_bytes = STAGES * kStageBytes + (2 * STAGES + 4) * 8 + 16 + 4096 + 1024;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, GN, SIMPLE>,
@@ -823,7 +834,8 @@ static int launch(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensor
   dev.total_tiles = m_tiles * dev.n_tiles_n;
   const int resident = sm_count() * (BN == 256 ? 1 : 2);
   const int grid = dev.total_tiles < resident ? dev.total_tiles : resident;
-  conv_gemm_kernel<BN, STAGES, GN, SIMPLE><<<grid, kGemmThreads, smem_bytes, stream>>>(ma0, ma1, mb, dev);
+  conv_gemm_kernel<BN, STAGES, GN, SIMPLE><<<grid, PlainCfg<BN, SIMPLE>::kThreads, smem_bytes, stream>>>(ma0, ma1, mb,
+                                                                                                     dev);
   EXTDM_CHECK_LAUNCH();
   return EXTDM_OK;
 }
@@ -926,7 +938,7 @@ extern "C" int extdm_conv_gemm(const ExtdmGemm* g, void* stream_) {
       dev.stages = stages;
       dev.a_ext_bytes = a_ext;
       halo_smem = static_cast<int>((resb ? resb_bytes : 0) + static_cast<long long>(stages) * (a_ext + (resb ? 0 : kk * btile))) +
-                  (2 * 8 + 6) * 8 + 16 + 2048 + 1024 + 1024;
+                  (2 * 8 + 6) * 8 + 16 + 4096 + 1024;
     }
   }
 

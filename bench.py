@@ -227,23 +227,41 @@ def main():
         rec_.run()
         torch.cuda.synchronize()
         for name, meta, ms in rec_.run_timed():
-            t = table.setdefault(name, {"ms": 0.0, "flops": 0.0, "n": 0})
+            t = table.setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
             t["ms"] += ms * mult
             t["flops"] += meta.get("flops", 0.0) * mult
+            t["bytes"] += meta.get("bytes", 0.0) * mult
             t["n"] += mult
             if name == "extdm_conv_gemm" and (top is None or ms * mult > top[2] * top[3]):
                 top = (name, meta, ms, mult)
     gemm = table["extdm_conv_gemm"]
     total_kernel_ms = sum(t["ms"] for t in table.values())
-    peak_tf = peaks["bf16_tflops"]
+    peak_tf, peak_bw = peaks["bf16_tflops"], peaks["hbm_gbs"]
+    traffic = None                                    # dram bytes per launch of the top GEMM shape, from the ncu capture
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    top_key = f"rows={top[1]['rows']} n={top[1]['n']} k={top[1]['k']} taps={top[1]['taps']}"
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(top_key)
+    # The dominant kernel of a round is the tcgen05 implicit-GEMM (conv_gemm_kernel / conv_halo_kernel templates,
+    # one C-ABI entry point): `achieved` is algorithmic FLOPs of ALL its launches in a round over their summed
+    # CUDA-event durations; `top_launch` is its single most expensive shape; `other_kernels` are the HBM-bound ones.
+    others = {}
+    for name, t in table.items():
+        if name != "extdm_conv_gemm" and t["bytes"] > 0:
+            gbs = t["bytes"] / (t["ms"] * 1e-3) / 1e9
+            others[name] = {"bound": "hbm", "achieved": gbs, "peak": peak_bw, "unit": "GB/s", "frac": gbs / peak_bw,
+                            "share_of_kernel_time": t["ms"] / total_kernel_ms}
     roofline = {
-        "bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM), launch with the largest time share of a round: "
-                                     f"rows={top[1]['rows']} n={top[1]['n']} k={top[1]['k']} taps={top[1]['taps']}",
-        "achieved": top[1]["flops"] / (top[2] * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
-        "frac": top[1]["flops"] / (top[2] * 1e-3) / 1e12 / peak_tf, "peak_source": peaks["source"] + " burst",
-        "traffic": None,
-        "all_gemm_launches": {"tflops": gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12, "share_of_kernel_time":
-                              gemm["ms"] / total_kernel_ms, "launches_per_round": gemm["n"]},
+        "bound": "tensor", "kernel": "extdm_conv_gemm (tcgen05 implicit GEMM: conv_gemm_kernel / conv_halo_kernel), all "
+                                     f"{gemm['n']} launches of one round",
+        "achieved": gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+        "frac": gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 / peak_tf, "peak_source": peaks["source"] + " burst",
+        "share_of_kernel_time": gemm["ms"] / total_kernel_ms,
+        "traffic": traffic,
+        "top_launch": {"shape": top_key, "achieved": top[1]["flops"] / (top[2] * 1e-3) / 1e12,
+                       "frac": top[1]["flops"] / (top[2] * 1e-3) / 1e12 / peak_tf,
+                       "algorithmic_bytes": top[1]["bytes"], "ms": top[2], "launches_per_round": top[3]},
+        "other_kernels": others,
     }
     if args.profile_kernels and rank == 0:
         for name, t in sorted(table.items(), key=lambda kv: -kv[1]["ms"]):
