@@ -912,6 +912,11 @@ static int launch_stw16(const StwParams& p, cudaStream_t st) {
 
 using namespace extdm;
 
+// tcgen05 edition of the C = 64, (4,4,4)-window layer (stw_tc.cu)
+int extdm_stw_tc_launch(const void* x, void* y, const float* gamma, const void* wqkv, const void* wproj,
+                        const float* proj_bias, const float* bias_table, const float* rope_cos, const float* rope_sin,
+                        int B, int T, int H, int W, int sd, int sh, int sw, float eps, void* stream);
+
 extern "C" int extdm_stw_fused_supported(int C, int heads, int dh, int wd, int wh, int ww) {
   const int ntok = wd * wh * ww;
   if (heads != 8 || wh != 4 || ww != 4) return 0;
@@ -947,8 +952,20 @@ extern "C" int extdm_stw_fused(const void* x, void* y, const float* gamma, const
   p.eps = eps;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int ntok = wd * wh * ww;
-  static const bool use8 = getenv("EXTDM_STW8") != nullptr;       // A/B switch: 8-warp kernel for every shape
-  if (ntok == 64 && C == 64) return use8 ? launch_stw<64, 16, 64>(p, st) : launch_stw16<64, 16, 64>(p, st);
+  // Three implementations of the C = 64 / 64-token layer, all parity-tested (tests/test_kernels_gpu.py runs each):
+  //   default       all-mma.sync, 16 warps            716 us per level-0 launch on B200 (HMMA-pipe bound)
+  //   EXTDM_STW8    all-mma.sync, 8 warps             716 us
+  //   EXTDM_STW_TC  projections on tcgen05 (stw_tc.cu) 815 us: 1/3 of the HMMA work but the per-window phase chain
+  //                 (LN -> MMA -> TMEM drain -> attention -> MMA -> epilogue) is latency bound at one window per
+  //                 iteration; two windows per iteration need 258 KB of shared memory
+  static const bool use8 = getenv("EXTDM_STW8") != nullptr, use_tc = getenv("EXTDM_STW_TC") != nullptr;
+  if (ntok == 64 && C == 64) {
+    if (use8) return launch_stw<64, 16, 64>(p, st);
+    if (use_tc)
+      return extdm_stw_tc_launch(x, y, gamma, wqkv, wproj, proj_bias, bias_table, rope_cos, rope_sin, B, T, H, W, sd,
+                                 sh, sw, eps, stream);
+    return launch_stw16<64, 16, 64>(p, st);
+  }
   if (ntok == 64 && C == 128) return launch_stw<64, 16, 128>(p, st);
   return launch_stw<32, 32, 64>(p, st);       // (2,4,4) windows: the 16-warp layout would need 233 KB of shared memory
 }

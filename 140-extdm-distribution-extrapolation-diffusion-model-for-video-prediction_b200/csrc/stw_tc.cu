@@ -1,0 +1,491 @@
+// Shifted-window attention layer, tcgen05 edition (C = 64, window (4,4,4) = 64 tokens, 8 heads x 16):
+//     y = x + proj( WindowAttention3D( chanLN(x) ) )          Residual(PreNorm(STWAttentionLayer))
+// reference: model/BaseDM_adaptor/DenoiseNet_STWAtt_w_wo_ref_adaptor_cross_multi.py:139-159, :409-560.
+//
+// ncu on the all-mma.sync kernel (stw_fused.cu) showed the legacy HMMA path saturated: on B200 mma.sync.m16n8k16
+// issues about once per 27 cycles per scheduler (~165 TFLOP/s chip-wide, 1/13 of tcgen05), and 2/3 of the layer's
+// matrix work are the two dense projections.  Here those run on the 5th-gen tensor cores:
+//   * QKV projection  D[128 x 384] = LN(x)[128 x 64] . Wqkv^T   -- 8 tcgen05.mma (M=128, N=256 + N=128, K=16 x 4),
+//     A = the window's normalised tokens written by the LayerNorm threads straight into a 128B-swizzled K-major
+//     tile, B = Wqkv resident in shared memory, accumulators in TMEM, drained with tcgen05.ld (thread = token),
+//     rotary + q-scale applied on the way to the bf16 Q/K/V tiles;
+//   * output projection D[128 x 64] = O[128 x 128] . Wproj^T    -- 8 tcgen05.mma (N = 64, 2 k-blocks x 4),
+//     A = the attention output written by the attention warps in swizzled K-major layout, epilogue (bias + residual)
+//     from TMEM straight to global memory.
+// Only rows 0..63 of the M = 128 tiles are real (one window per iteration); the other accumulator lanes are ignored.
+// The 64 x 64 x 16 per-head score / PV products (block-diagonal, below any tcgen05 tile) stay on mma.sync with
+// ldmatrix operands, bias-initialised accumulators and the ballot shift mask, two warps per head.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "../../include/extdm_b200.h"
+
+namespace extdm {
+namespace {
+
+__device__ __forceinline__ void t_mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void t_ldsm_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void t_ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void t_cp_async16(void* dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ float t_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float t_bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float t_bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+
+constexpr float kL2e = 1.4426950408889634f;
+constexpr int NTOK = 64, DH = 16, C = 64, HEADS = 8, HID = 128;
+constexpr int NTH = 512;
+
+// byte offset of 16-byte chunk j (0..7) of row r inside a K-major 128B-swizzled tile of 64 bf16 per row
+__device__ __forceinline__ int sw128(int r, int j) { return (r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4); }
+// byte offset of 16-byte chunk j (0..15) of row r in a [rows][128] bf16 tile with the low 3 chunk bits XOR-swizzled
+__device__ __forceinline__ int swrow256(int r, int j) { return r * 256 + ((j ^ (r & 7)) << 4); }
+
+struct Smem {
+  static constexpr int wqkv = 0;                       // [384][64] SW128             49152
+  static constexpr int wp = wqkv + 49152;              // 2 x [64][64] SW128          16384
+  static constexpr int a = wp + 16384;                 // [64 (+64 ignored)][64] SW128 8192
+  static constexpr int o = a + 8192;                   // 2 x [64 (+64)][64] SW128    16384
+  static constexpr int q = o + 16384;                  // [64][128] XOR-swizzled rows 16384
+  static constexpr int k = q + 16384;
+  static constexpr int v = k + 16384;
+  static constexpr int bias = v + 16384;               // [8][64][64] bf16, XOR-swizzled rows (128 B)  65536
+  static constexpr int raw = bias + 65536;             // 2 x [64][72] bf16           18432
+  static constexpr int rope = raw + 18432;             // cos, sin [64][8] fp32       4096
+  static constexpr int misc = rope + 4096;             // gamma[64], pbias[64] fp32   512
+  static constexpr int emask = misc + 512;             // [2][8] u32                  64
+  static constexpr int bars = emask + 64;              // 2 mbarriers + tmem slot     32
+  static constexpr int total = bars + 32;
+};
+constexpr int XPR = 72;                                // raw pitch (bf16)
+
+struct TcParams {
+  const __nv_bfloat16* x;
+  __nv_bfloat16* y;
+  const float* gamma;
+  const __nv_bfloat16* wqkv;
+  const __nv_bfloat16* wproj;
+  const float* proj_bias;
+  const float* bias_table;
+  const float* rcos;
+  const float* rsin;
+  int B, T, H, W, sd, sh, sw, Dp, n_windows;
+  float eps;
+};
+
+__global__ void __launch_bounds__(NTH, 1) stw_tc_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw_[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_wqkv = sm + Smem::wqkv;
+  uint8_t* s_wp = sm + Smem::wp;
+  uint8_t* s_a = sm + Smem::a;
+  uint8_t* s_o = sm + Smem::o;
+  uint8_t* s_q = sm + Smem::q;
+  uint8_t* s_k = sm + Smem::k;
+  uint8_t* s_v = sm + Smem::v;
+  uint8_t* s_bias = sm + Smem::bias;
+  __nv_bfloat16* s_raw = reinterpret_cast<__nv_bfloat16*>(sm + Smem::raw);
+  float* s_cos = reinterpret_cast<float*>(sm + Smem::rope);
+  float* s_sin = s_cos + NTOK * (DH / 2);
+  float* s_gamma = reinterpret_cast<float*>(sm + Smem::misc);
+  float* s_pbias = s_gamma + C;
+  uint32_t* s_E = reinterpret_cast<uint32_t*>(sm + Smem::emask);
+  uint64_t* bar_qkv = reinterpret_cast<uint64_t*>(sm + Smem::bars);
+  uint64_t* bar_o = bar_qkv + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_o + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
+  const int head = warp & 7, half = warp >> 3;
+  const bool shifted = (p.sd | p.sh | p.sw) != 0;
+  const int nWw = p.W / 4, nWh = p.H / 4, nWd = p.Dp / 4;
+  const int lrow = lane & 15, lhi = lane >> 4;
+
+  // ---- one-time staging
+  for (int i = tid; i < 384 * 8; i += NTH) {           // Wqkv [384][64] -> swizzled B tile
+    const int r = i >> 3, j = i & 7;
+    *reinterpret_cast<uint4*>(s_wqkv + sw128(r, j)) = *reinterpret_cast<const uint4*>(p.wqkv + r * C + j * 8);
+  }
+  for (int i = tid; i < 64 * 16; i += NTH) {           // Wproj [64][128] -> two swizzled k-blocks
+    const int r = i >> 4, j = i & 15;
+    *reinterpret_cast<uint4*>(s_wp + (j >> 3) * 8192 + sw128(r, j & 7)) =
+        *reinterpret_cast<const uint4*>(p.wproj + r * HID + j * 8);
+  }
+  for (int i = tid; i < NTOK * (DH / 2); i += NTH) { s_cos[i] = p.rcos[i]; s_sin[i] = p.rsin[i]; }
+  for (int i = tid; i < C; i += NTH) { s_gamma[i] = p.gamma[i]; s_pbias[i] = p.proj_bias ? p.proj_bias[i] : 0.f; }
+  for (int i = tid; i < HEADS * NTOK * NTOK; i += NTH) {
+    const int j = i & 63, q = (i >> 6) & 63, h = i >> 12;
+    const int rel = (((q >> 4) - (j >> 4) + 3) * 7 + (((q >> 2) & 3) - ((j >> 2) & 3) + 3)) * 7 + ((q & 3) - (j & 3) + 3);
+    const int off = h * 8192 + q * 128 + (((j >> 3) ^ (q & 7)) << 4) + (j & 7) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(s_bias + off) = __float2bfloat16(p.bias_table[rel * HEADS + h] * kL2e);
+  }
+  if (tid == 0) {
+    mbar_init(bar_qkv, 1);
+    mbar_init(bar_o, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async();                                  // weight tiles were written through the generic proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+
+  struct Win { int b, id, ih, iw; };
+  auto decode = [&](int widx) {
+    Win w;
+    w.iw = widx % nWw; widx /= nWw;
+    w.ih = widx % nWh; widx /= nWh;
+    w.id = widx % nWd;
+    w.b = widx / nWd;
+    return w;
+  };
+  auto src_pixel = [&](const Win& w, int n) -> int {
+    int od = w.id * 4 + (n >> 4) + p.sd, oh = w.ih * 4 + ((n >> 2) & 3) + p.sh, ow = w.iw * 4 + (n & 3) + p.sw;
+    if (od >= p.Dp) od -= p.Dp;
+    if (oh >= p.H) oh -= p.H;
+    if (ow >= p.W) ow -= p.W;
+    return od < p.T ? ((w.b * p.T + od) * p.H + oh) * p.W + ow : -1;
+  };
+  auto region_code = [&](const Win& w, int n) -> int {
+    int c = 0;
+    if (p.sd && w.id == nWd - 1 && (n >> 4) >= 4 - p.sd) c |= 1;
+    if (p.sh && w.ih == nWh - 1 && ((n >> 2) & 3) >= 4 - p.sh) c |= 2;
+    if (p.sw && w.iw == nWw - 1 && (n & 3) >= 4 - p.sw) c |= 4;
+    return c;
+  };
+  auto prefetch_window = [&](const Win& w, int buf) {
+    __nv_bfloat16* dst = s_raw + buf * NTOK * XPR;
+    {
+      const int n = tid >> 3, c8 = tid & 7;            // 64 tokens x 8 chunks = 512 threads
+      const int s = src_pixel(w, n);
+      t_cp_async16(dst + n * XPR + c8 * 8, p.x + (s >= 0 ? static_cast<long long>(s) * C + c8 * 8 : 0), s >= 0 ? 16 : 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int widx = blockIdx.x;
+  int buf = 0;
+  uint32_t it = 0;
+  if (widx < p.n_windows) prefetch_window(decode(widx), 0);
+  const float qscale = 0.25f * kL2e;                    // dh^-1/2 * log2(e)
+  constexpr float kMask = -100.0f * kL2e;
+  constexpr uint32_t idesc256 = umma_idesc_bf16(128, 256), idesc128 = umma_idesc_bf16(128, 128),
+                     idesc64 = umma_idesc_bf16(128, 64);
+
+  for (; widx < p.n_windows; widx += gridDim.x, ++it) {
+    const Win win = decode(widx);
+    const int nxt = widx + gridDim.x;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                    // S1: raw[buf] landed; previous window fully retired
+    if (nxt < p.n_windows) prefetch_window(decode(nxt), buf ^ 1);
+    const __nv_bfloat16* raw = s_raw + buf * NTOK * XPR;
+    const bool has_mask = shifted && ((p.sd && win.id == nWd - 1) || (p.sh && win.ih == nWh - 1) ||
+                                      (p.sw && win.iw == nWw - 1));
+    if (has_mask && warp < 2) {
+      const int code = region_code(win, warp * 32 + lane);
+      uint32_t mine = 0;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t bal = __ballot_sync(0xffffffffu, code == c);
+        if (lane == c) mine = bal;
+      }
+      if (lane < 8) s_E[warp * 8 + lane] = mine;
+    }
+    // ---- channel LayerNorm: 8 threads per token, one 16-byte chunk each -> swizzled A tile
+    {
+      const int n = tid >> 3, part = tid & 7;
+      const uint4 t = *reinterpret_cast<const uint4*>(raw + n * XPR + part * 8);
+      const float2 a = unpack_bf16(t.x), b = unpack_bf16(t.y), c = unpack_bf16(t.z), d = unpack_bf16(t.w);
+      float v[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += v[j];
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+      const float mean = sum * (1.0f / C);
+      float sq = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float dd = v[j] - mean; sq += dd * dd; }
+      sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+      sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+      sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+      const float rstd = src_pixel(win, n) >= 0 ? rsqrtf(sq * (1.0f / C) + p.eps) : 0.f;
+      uint32_t pk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int cc = part * 8 + 2 * j;
+        pk[j] = pack_bf16((v[2 * j] - mean) * rstd * s_gamma[cc], (v[2 * j + 1] - mean) * rstd * s_gamma[cc + 1]);
+      }
+      *reinterpret_cast<uint4*>(s_a + sw128(n, part)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+    fence_proxy_async();                                // A tile -> visible to the tensor-core (async) proxy
+    __syncthreads();                                    // S2
+
+    // ---- QKV projection on tcgen05: D[:, 0:256] (Q | K) and D[:, 256:384] (V)
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t da = umma_desc_sw128(smem_u32(s_a));
+        const uint64_t db0 = umma_desc_sw128(smem_u32(s_wqkv));
+        const uint64_t db1 = umma_desc_sw128(smem_u32(s_wqkv) + 256 * 128);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          umma_bf16(tmem_u, da + 2 * k, db0 + 2 * k, idesc256, k > 0 ? 1u : 0u);
+          umma_bf16(tmem_u + 256, da + 2 * k, db1 + 2 * k, idesc128, k > 0 ? 1u : 0u);
+        }
+        umma_commit(bar_qkv);
+      }
+      __syncwarp();
+    }
+    mbar_wait(bar_qkv, it & 1);
+    tc_fence_after();
+
+    // ---- drain: warps of TMEM lane quarters 0 / 1 (tokens 0..63), thread = token, 96 columns per warp
+    if ((warp & 3) < 2) {
+      const int tok = (warp & 3) * 32 + lane;
+      const int e = warp >> 2;                          // 0..3 -> columns [96e, 96e + 96)
+      const uint32_t taddr = tmem_u + (static_cast<uint32_t>((warp & 3) * 32) << 16) + e * 96;
+      const bool live = src_pixel(win, tok) >= 0;       // T-padding tokens stay exactly zero (q = k = v = 0)
+#pragma unroll 1
+      for (int c = 0; c < 6; ++c) {
+        uint32_t rr[16];
+        tmem_ld16(taddr + c * 16, rr);
+        tmem_ld_wait();
+        const int col = e * 96 + c * 16;                // 16 columns = one head of Q, K or V
+        const int region = col >> 7, hd = (col & 127) >> 4;
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = live ? __uint_as_float(rr[j]) : 0.f;
+        if (region < 2) {
+          const float sc = region == 0 ? qscale : 1.0f;
+#pragma unroll
+          for (int pr = 0; pr < 8; ++pr) {
+            const float cs = s_cos[tok * 8 + pr], sn = s_sin[tok * 8 + pr];
+            const float x0 = f[2 * pr] * sc, x1 = f[2 * pr + 1] * sc;
+            f[2 * pr] = x0 * cs - x1 * sn;
+            f[2 * pr + 1] = x1 * cs + x0 * sn;
+          }
+        }
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
+        uint8_t* dst = region == 0 ? s_q : (region == 1 ? s_k : s_v);
+        *reinterpret_cast<uint4*>(dst + swrow256(tok, hd * 2)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(dst + swrow256(tok, hd * 2 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();                                    // S3: Q / K / V tiles complete
+
+    // ---- attention core (mma.sync): warp = (head, half of the query m-tiles)
+    uint32_t kfrag[8][2];
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t kf[4];
+      const int r = np * 16 + (lane & 7) + ((lane >> 4) & 1) * 8;
+      t_ldsm_x4(kf, s_k + swrow256(r, head * 2 + ((lane >> 3) & 1)));
+      kfrag[2 * np][0] = kf[0]; kfrag[2 * np][1] = kf[1];
+      kfrag[2 * np + 1][0] = kf[2]; kfrag[2 * np + 1][1] = kf[3];
+    }
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+      const int mt = half * 2 + mi;
+      const int r0 = mt * 16 + g, r1 = r0 + 8;
+      uint32_t qa[4];
+      t_ldsm_x4(qa, s_q + swrow256(mt * 16 + lrow, head * 2 + lhi));
+      float s[8][4];
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t bb[4];
+        const int r = mt * 16 + lrow;
+        t_ldsm_x4(bb, s_bias + head * 8192 + r * 128 + (((np * 2 + lhi) ^ (r & 7)) << 4));
+        s[2 * np][0] = t_bf_lo(bb[0]); s[2 * np][1] = t_bf_hi(bb[0]);
+        s[2 * np][2] = t_bf_lo(bb[1]); s[2 * np][3] = t_bf_hi(bb[1]);
+        s[2 * np + 1][0] = t_bf_lo(bb[2]); s[2 * np + 1][1] = t_bf_hi(bb[2]);
+        s[2 * np + 1][2] = t_bf_lo(bb[3]); s[2 * np + 1][3] = t_bf_hi(bb[3]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) t_mma16816(s[nt], qa, kfrag[nt][0], kfrag[nt][1]);
+      if (has_mask) {
+        const int c0 = region_code(win, r0), c1 = region_code(win, r1);
+        const uint32_t e0[2] = {~s_E[c0], ~s_E[8 + c0]}, e1[2] = {~s_E[c1], ~s_E[8 + c1]};
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const int bit = (nt * 8) % 32 + tg * 2;
+          const uint32_t m0 = e0[nt / 4] >> bit, m1 = e1[nt / 4] >> bit;
+          if (m0 & 1) s[nt][0] += kMask;
+          if (m0 & 2) s[nt][1] += kMask;
+          if (m1 & 1) s[nt][2] += kMask;
+          if (m1 & 2) s[nt][3] += kMask;
+        }
+      }
+      float m0 = -3.0e38f, m1 = -3.0e38f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
+        m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
+      }
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        s[nt][0] = t_exp2(s[nt][0] - m0);
+        s[nt][1] = t_exp2(s[nt][1] - m0);
+        s[nt][2] = t_exp2(s[nt][2] - m1);
+        s[nt][3] = t_exp2(s[nt][3] - m1);
+        l0 += s[nt][0] + s[nt][1];
+        l1 += s[nt][2] + s[nt][3];
+      }
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+      const float inv0 = __frcp_rn(l0), inv1 = __frcp_rn(l1);
+      float o[2][4];
+#pragma unroll
+      for (int dt = 0; dt < 2; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+#pragma unroll
+      for (int ps = 0; ps < 4; ++ps) {
+        uint32_t a[4];
+        a[0] = pack_bf16(s[2 * ps][0], s[2 * ps][1]);
+        a[1] = pack_bf16(s[2 * ps][2], s[2 * ps][3]);
+        a[2] = pack_bf16(s[2 * ps + 1][0], s[2 * ps + 1][1]);
+        a[3] = pack_bf16(s[2 * ps + 1][2], s[2 * ps + 1][3]);
+        uint32_t vb[4];
+        t_ldsm_x4_trans(vb, s_v + swrow256(ps * 16 + lrow, head * 2 + lhi));
+        t_mma16816(o[0], a, vb[0], vb[1]);
+        t_mma16816(o[1], a, vb[2], vb[3]);
+      }
+      // head output -> swizzled K-major A tile of the output projection: hidden column head*16 + dt*8 + tg*2
+#pragma unroll
+      for (int dt = 0; dt < 2; ++dt) {
+        const int chunk = (head * 2 + dt) & 7, kb = head >> 2;
+        *reinterpret_cast<uint32_t*>(s_o + kb * 8192 + sw128(r0, chunk) + tg * 4) = pack_bf16(o[dt][0] * inv0, o[dt][1] * inv0);
+        *reinterpret_cast<uint32_t*>(s_o + kb * 8192 + sw128(r1, chunk) + tg * 4) = pack_bf16(o[dt][2] * inv1, o[dt][3] * inv1);
+      }
+    }
+    fence_proxy_async();
+    __syncthreads();                                    // S4: O tile complete
+
+    // ---- output projection on tcgen05: D_o[128 x 64] at TMEM column 384
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          const uint64_t da = umma_desc_sw128(smem_u32(s_o) + kb * 8192);
+          const uint64_t db = umma_desc_sw128(smem_u32(s_wp) + kb * 8192);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem_u + 384, da + 2 * k, db + 2 * k, idesc64, (kb | k) ? 1u : 0u);
+        }
+        umma_commit(bar_o);
+      }
+      __syncwarp();
+    }
+    mbar_wait(bar_o, it & 1);
+    tc_fence_after();
+    if ((warp & 3) < 2) {
+      const int tok = (warp & 3) * 32 + lane;
+      const int e = warp >> 2;                          // 16-column chunk of the 64 output channels
+      uint32_t rr[16];
+      tmem_ld16(tmem_u + (static_cast<uint32_t>((warp & 3) * 32) << 16) + 384 + e * 16, rr);
+      tmem_ld_wait();
+      const int d = src_pixel(win, tok);
+      if (d >= 0) {
+        const uint4 r0v = *reinterpret_cast<const uint4*>(raw + tok * XPR + e * 16);
+        const uint4 r1v = *reinterpret_cast<const uint4*>(raw + tok * XPR + e * 16 + 8);
+        const uint32_t rw[8] = {r0v.x, r0v.y, r0v.z, r0v.w, r1v.x, r1v.y, r1v.z, r1v.w};
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float2 rv = unpack_bf16(rw[j]);
+          pk[j] = pack_bf16(__uint_as_float(rr[2 * j]) + s_pbias[e * 16 + 2 * j] + rv.x,
+                            __uint_as_float(rr[2 * j + 1]) + s_pbias[e * 16 + 2 * j + 1] + rv.y);
+        }
+        __nv_bfloat16* yp = p.y + static_cast<long long>(d) * C + e * 16;
+        *reinterpret_cast<uint4*>(yp) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(yp + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+    }
+    tc_fence_before();
+    buf ^= 1;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+}  // namespace extdm
+
+using namespace extdm;
+
+// Launch the tcgen05 window-attention layer (C = 64, (4,4,4) windows, 8 heads x 16).  Called by extdm_stw_fused.
+int extdm_stw_tc_launch(const void* x, void* y, const float* gamma, const void* wqkv, const void* wproj,
+                        const float* proj_bias, const float* bias_table, const float* rope_cos, const float* rope_sin,
+                        int B, int T, int H, int W, int sd, int sh, int sw, float eps, void* stream) {
+  TcParams p;
+  p.x = reinterpret_cast<const __nv_bfloat16*>(x);
+  p.y = reinterpret_cast<__nv_bfloat16*>(y);
+  p.gamma = gamma;
+  p.wqkv = reinterpret_cast<const __nv_bfloat16*>(wqkv);
+  p.wproj = reinterpret_cast<const __nv_bfloat16*>(wproj);
+  p.proj_bias = proj_bias;
+  p.bias_table = bias_table;
+  p.rcos = rope_cos;
+  p.rsin = rope_sin;
+  p.B = B; p.T = T; p.H = H; p.W = W;
+  p.sd = sd; p.sh = sh; p.sw = sw;
+  p.Dp = (T + 3) / 4 * 4;
+  p.n_windows = B * (p.Dp / 4) * (H / 4) * (W / 4);
+  p.eps = eps;
+  constexpr int smem = Smem::total + 1024;
+  static bool configured = false;
+  static int sms = 0;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(stw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      extdm_set_error(cudaGetErrorString(e), __FILE__, __LINE__);
+      return EXTDM_ERR_CUDA;
+    }
+    configured = true;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int grid = p.n_windows < sms ? p.n_windows : sms;
+  stw_tc_kernel<<<grid, NTH, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  EXTDM_CHECK_LAUNCH();
+  return EXTDM_OK;
+}

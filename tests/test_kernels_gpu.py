@@ -483,8 +483,21 @@ def test_lfae_helpers():
 @pytest.mark.parametrize("window,dh,C,T,H,shifted", [((4, 4, 4), 16, 64, 7, 16, True), ((4, 4, 4), 16, 64, 7, 16, False),
                                                      ((4, 4, 4), 16, 128, 6, 8, True), ((2, 4, 4), 32, 64, 5, 8, True),
                                                      ((4, 4, 4), 16, 64, 30, 32, True)])
-def test_stw_fused_layer(window, dh, C, T, H, shifted):
-    """Whole Residual(PreNorm(STWAttentionLayer)) in one kernel vs the oracle's stw_attention (CPU fp32)."""
+@pytest.mark.parametrize("impl", ["default", "EXTDM_STW8", "EXTDM_STW_TC"])
+def test_stw_fused_layer(window, dh, C, T, H, shifted, impl):
+    """Whole Residual(PreNorm(STWAttentionLayer)) in one kernel vs the oracle's stw_attention (CPU fp32), for each of
+    the three implementations of the C = 64 / 64-token layer (16-warp mma.sync, 8-warp mma.sync, tcgen05
+    projections).  The library reads the switch once per process, so the non-default ones run in a child process."""
+    if impl != "default":
+        if not (window == (4, 4, 4) and C == 64):
+            pytest.skip("alternative implementations exist for C = 64 / (4,4,4) only")
+        import subprocess, sys, os
+        env = dict(os.environ, **{impl: "1"})
+        shifted_id = {(7, True): "window0", (7, False): "window1", (30, True): "window4"}[(T, shifted)]
+        r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-k",
+                            f"test_stw_fused_layer and {shifted_id} and default"], env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        return
     from oracle import extdm_oracle as O
     B, heads = 2, 8
     hid = heads * dh
