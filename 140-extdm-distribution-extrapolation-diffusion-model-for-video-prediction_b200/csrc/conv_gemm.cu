@@ -567,8 +567,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
 constexpr int kHaloEpw = 4;                                   // epilogue warps per TMEM lane quarter
 constexpr int kHaloThreads = 64 + 128 * kHaloEpw;
 
-template <int BN, bool GN, bool RESB>
-__global__ void __launch_bounds__(kHaloThreads, 1)
+template <int BN, bool GN, bool RESB, bool SIMPLE>
+__global__ void __launch_bounds__(SIMPLE ? kHaloThreads : kGemmThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                  const __grid_constant__ CUtensorMap map_b, const __grid_constant__ GemmDev p) {
   constexpr int kBTileBytes = BN * kBlockK * 2;
@@ -605,7 +605,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4 * kHaloEpw);
+      mbar_init(&acc_empty[s], SIMPLE ? 4 * kHaloEpw : 4);
     }
     mbar_init(resb_bar, 1);
     fence_barrier_init();
@@ -719,7 +719,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     }
     __syncwarp();
   } else {
-    epilogue_simple<BN, GN, kHaloEpw>(p, acc_full, acc_empty, s_gn, tmem_base, warp, lane);
+    if constexpr (SIMPLE)
+      epilogue_simple<BN, GN, kHaloEpw>(p, acc_full, acc_empty, s_gn, tmem_base, warp, lane);
+    else
+      epilogue_loop<BN, GN, false>(p, acc_full, acc_empty, s_gn, tmem_base, warp, lane);
   }
 
   tc_fence_before();
@@ -793,12 +796,12 @@ static int sm_count() {
 
 constexpr int kSmemBudget = 232448 - 4608;       // 227 KB minus alignment slack, barriers, bias and GN scratch
 
-template <int BN, bool GN, bool RESB>
+template <int BN, bool GN, bool RESB, bool SIMPLE>
 static int launch_halo(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb, GemmDev& dev, int m_tiles,
                        int smem_bytes, cudaStream_t stream) {
   static int configured = 0;
   if (smem_bytes > configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, GN, RESB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, GN, RESB, SIMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          smem_bytes);
     if (e != cudaSuccess) {
       extdm_set_error(cudaGetErrorString(e), __FILE__, __LINE__);
@@ -810,7 +813,7 @@ static int launch_halo(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUt
   dev.total_tiles = m_tiles * dev.n_tiles_n;
   const int resident = sm_count();
   const int grid = dev.total_tiles < resident ? dev.total_tiles : resident;
-  conv_halo_kernel<BN, GN, RESB><<<grid, kHaloThreads, smem_bytes, stream>>>(ma0, ma1, mb, dev);
+  conv_halo_kernel<BN, GN, RESB, SIMPLE><<<grid, SIMPLE ? kHaloThreads : kGemmThreads, smem_bytes, stream>>>(ma0, ma1, mb, dev);
   EXTDM_CHECK_LAUNCH();
   return EXTDM_OK;
 }
@@ -913,7 +916,8 @@ extern "C" int extdm_conv_gemm(const ExtdmGemm* g, void* stream_) {
   // measured on B200: with a single 64-channel block per tap the plain kernel at two CTAs per
   // SM is ~8% faster (113 vs 122 us on the level-0 3x3), with two or more blocks the halo kernel wins
   static const bool halo_all = getenv("EXTDM_HALO_ALL") != nullptr;
-  bool halo = kk && simple && !halo_off && !(kk == 7 && halo7_off) && (halo_all || dev.nk0 + dev.nk1 >= 2) && g->box[2] == 1 && g->box[3] == 1 && g->box[0] % 8 == 0 &&
+  bool halo = kk && (simple || kk == 7) && !halo_off && !(kk == 7 && halo7_off) &&
+              (halo_all || dev.nk0 + dev.nk1 >= 2) && g->box[2] == 1 && g->box[3] == 1 && g->box[0] % 8 == 0 &&
               (bn == 64 || bn == 128);
   int ebox[4] = {g->box[0], g->box[1] + kk - 1, 1, 1};
   bool resb = false;
@@ -965,7 +969,9 @@ extern "C" int extdm_conv_gemm(const ExtdmGemm* g, void* stream_) {
   }
   if (halo) {
     const bool gn = g->gn_partials != nullptr;
-#define HALO(BN_, GN_, RB_) return launch_halo<BN_, GN_, RB_>(ma0, ma1, mb, dev, m_tiles, halo_smem, stream)
+#define HALO(BN_, GN_, RB_)                                                                             \
+  return simple ? launch_halo<BN_, GN_, RB_, true>(ma0, ma1, mb, dev, m_tiles, halo_smem, stream)      \
+                : launch_halo<BN_, GN_, RB_, false>(ma0, ma1, mb, dev, m_tiles, halo_smem, stream)
     if (bn == 64) {
       if (gn) { if (resb) HALO(64, true, true); else HALO(64, true, false); }
       else { if (resb) HALO(64, false, true); else HALO(64, false, false); }
