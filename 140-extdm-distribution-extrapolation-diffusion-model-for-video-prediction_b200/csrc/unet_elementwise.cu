@@ -388,43 +388,48 @@ __global__ void __launch_bounds__(256) space_to_depth_kernel(const __nv_bfloat16
   }
 }
 
-// one thread per (row, tap-pair): rows of 192 bf16 = 24 uint4; we build them 8 elements at a time
+// One CTA per (sample, frame, image row): the 3 x 7 x (W+6) fp32 halo is staged in shared memory (zero padded), then
+// the W rows of 192 bf16 (K index = (ky*7+kx)*3 + c, 147 used) are written as coalesced 16-byte chunks.
 __global__ void __launch_bounds__(256) im2col7_flow_kernel(const float* __restrict__ cond,
                                                            const float* __restrict__ xin,
                                                            __nv_bfloat16* __restrict__ a, int B, int tc, int tp,
                                                            int t0, int nt, int H, int W) {
-  const long long rows = static_cast<long long>(B) * nt * H * W;
-  const long long total = rows * 24;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int v = i % 24;
-    long long r = i / 24;
-    const int xx = r % W; r /= W;
-    const int yy = r % H; r /= H;
-    const int t = t0 + static_cast<int>(r % nt);
-    const int b = static_cast<int>(r / nt);
-    const float* src;
-    long long cstride;
-    if (t < tc) {
-      src = cond + ((static_cast<long long>(b) * 3 * tc + t) * H) * W;
-      cstride = static_cast<long long>(tc) * H * W;
-    } else {
-      src = xin + ((static_cast<long long>(b) * 3 * tp + (t - tc)) * H) * W;
-      cstride = static_cast<long long>(tp) * H * W;
-    }
+  extern __shared__ float s_halo[];        // [3][7][W+6], then short lut[192]
+  const int WP = W + 6;
+  short* s_lut = reinterpret_cast<short*>(s_halo + 3 * 7 * WP);
+  const int yy = blockIdx.x % H;
+  const int tt = (blockIdx.x / H) % nt;
+  const int b = blockIdx.x / (H * nt);
+  const int t = t0 + tt;
+  const float* src;
+  long long cstride;
+  if (t < tc) {
+    src = cond + ((static_cast<long long>(b) * 3 * tc + t) * H) * W;
+    cstride = static_cast<long long>(tc) * H * W;
+  } else {
+    src = xin + ((static_cast<long long>(b) * 3 * tp + (t - tc)) * H) * W;
+    cstride = static_cast<long long>(tp) * H * W;
+  }
+  for (int i = threadIdx.x; i < 3 * 7 * WP; i += blockDim.x) {
+    const int xh = i % WP, ky = (i / WP) % 7, c = i / (7 * WP);
+    const int y2 = yy + ky - 3, x2 = xh - 3;
+    s_halo[i] = (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) ? __ldg(src + c * cstride + y2 * W + x2) : 0.f;
+  }
+  for (int k = threadIdx.x; k < 192; k += blockDim.x) {
+    const int tap = k / 3, c = k % 3;
+    s_lut[k] = k < 147 ? static_cast<short>((c * 7 + tap / 7) * WP + tap % 7) : static_cast<short>(-1);
+  }
+  __syncthreads();
+  const long long row0 = ((static_cast<long long>(b) * nt + tt) * H + yy) * W;
+  for (int i = threadIdx.x; i < W * 24; i += blockDim.x) {
+    const int xx = i / 24, v = i % 24;
     float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int k = v * 8 + j;
-      float val = 0.f;
-      if (k < 147) {
-        const int tap = k / 3, c = k % 3;
-        const int y2 = yy + tap / 7 - 3, x2 = xx + tap % 7 - 3;
-        if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) val = __ldg(src + c * cstride + y2 * W + x2);
-      }
-      o[j] = val;
+      const int off = s_lut[v * 8 + j];
+      o[j] = off >= 0 ? s_halo[off + xx] : 0.f;
     }
-    store8(a + i * 8, o);
+    store8(a + (row0 + xx) * 192 + v * 8, o);
   }
 }
 
@@ -493,16 +498,17 @@ __global__ void __launch_bounds__(256) bilinear_resize_cl_kernel(const __nv_bflo
 }
 
 // ------------------------------------------------------------------------------------------------ time MLP
+// Stage 1 (one CTA per sample): sinusoidal embedding -> Linear -> GELU -> Linear -> SiLU, warp-per-row dot products
+// (coalesced weight reads); result st[b][4*dim] goes to a scratch buffer.
 __global__ void __launch_bounds__(256) time_mlp_kernel(const long long* __restrict__ time,
                                                        const float* __restrict__ w1, const float* __restrict__ b1,
                                                        const float* __restrict__ w2, const float* __restrict__ b2,
-                                                       const float* __restrict__ wss, const float* __restrict__ bss,
-                                                       float* __restrict__ out, int dim, int n_ss) {
-  extern __shared__ float s_t[];           // e[dim], h[4dim], st[4dim]
+                                                       float* __restrict__ st, int dim) {
+  extern __shared__ float s_t[];           // e[dim], h[4dim]
   float* s_e = s_t;
   float* s_h = s_t + dim;
-  float* s_s = s_h + 4 * dim;
   const int b = blockIdx.x, td = 4 * dim, half = dim / 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const float t = static_cast<float>(time[b]);
   for (int i = threadIdx.x; i < half; i += blockDim.x) {
     const float f = expf(static_cast<float>(i) * -(logf(10000.0f) / (half - 1)));
@@ -510,24 +516,43 @@ __global__ void __launch_bounds__(256) time_mlp_kernel(const long long* __restri
     s_e[half + i] = cosf(t * f);
   }
   __syncthreads();
-  for (int r = threadIdx.x; r < td; r += blockDim.x) {
-    float acc = b1[r];
-    for (int k = 0; k < dim; ++k) acc += w1[r * dim + k] * s_e[k];
-    s_h[r] = 0.5f * acc * (1.0f + erff(acc * 0.70710678118654752440f));   // exact GELU
+  for (int r = warp; r < td; r += nw) {
+    float acc = 0.f;
+    for (int k = lane; k < dim; k += 32) acc += w1[r * dim + k] * s_e[k];
+    acc = warp_sum(acc) + b1[r];
+    if (lane == 0) s_h[r] = 0.5f * acc * (1.0f + erff(acc * 0.70710678118654752440f));   // exact GELU
   }
   __syncthreads();
-  for (int r = threadIdx.x; r < td; r += blockDim.x) {
-    float acc = b2[r];
-    for (int k = 0; k < td; ++k) acc += w2[r * td + k] * s_h[k];
-    s_s[r] = acc / (1.0f + expf(-acc));                                   // SiLU feeding every block's Linear
+  for (int r = warp; r < td; r += nw) {
+    float acc = 0.f;
+    for (int k = lane; k < td; k += 32) acc += w2[r * td + k] * s_h[k];
+    acc = warp_sum(acc) + b2[r];
+    if (lane == 0) st[static_cast<long long>(b) * td + r] = acc / (1.0f + expf(-acc));   // SiLU feeding every block's Linear
   }
+}
+
+// Stage 2: every ResnetBlock's Linear(4*dim -> 2*Cout) for all samples: out[b][r] = wss[r] . st[b] + bss[r].
+// One warp per weight row, the row is read once and dotted with every sample's vector (td == 256 -> 8 floats per lane).
+__global__ void __launch_bounds__(256) time_ss_kernel(const float* __restrict__ st, const float* __restrict__ wss,
+                                                      const float* __restrict__ bss, float* __restrict__ out, int B,
+                                                      int td, int n_ss) {
+  extern __shared__ float s_st[];          // [B][td]
+  for (int i = threadIdx.x; i < B * td; i += blockDim.x) s_st[i] = st[i];
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int r = blockIdx.y * nw + warp; r < n_ss; r += gridDim.y * nw) {
-    float acc = 0.f;
-    for (int k = lane; k < td; k += 32) acc += wss[static_cast<long long>(r) * td + k] * s_s[k];
-    acc = warp_sum(acc);
-    if (lane == 0) out[static_cast<long long>(b) * n_ss + r] = acc + bss[r];
+  for (int r = blockIdx.x * nw + warp; r < n_ss; r += gridDim.x * nw) {
+    float w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[j] = lane + 32 * j < td ? wss[static_cast<long long>(r) * td + lane + 32 * j] : 0.f;
+    const float bias = bss[r];
+    for (int b = 0; b < B; ++b) {
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (lane + 32 * j < td) acc += w[j] * s_st[b * td + lane + 32 * j];
+      acc = warp_sum(acc);
+      if (lane == 0) out[static_cast<long long>(b) * n_ss + r] = acc + bias;
+    }
   }
 }
 
@@ -752,8 +777,8 @@ extern "C" int extdm_space_to_depth(const void* x, void* z, long long F, int H, 
 
 extern "C" int extdm_im2col7_flow(const float* cond, const float* x, void* a, int B, int tc, int tp, int t0, int nt,
                                   int H, int W, void* stream) {
-  const long long total = static_cast<long long>(B) * nt * H * W * 24;
-  im2col7_flow_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(cond, x, BFW(a), B, tc, tp, t0, nt, H, W);
+  const size_t smem = 3 * 7 * (W + 6) * sizeof(float) + 192 * sizeof(short);
+  im2col7_flow_kernel<<<B * nt * H, 256, smem, STREAM>>>(cond, x, BFW(a), B, tc, tp, t0, nt, H, W);
   EXTDM_CHECK_LAUNCH();
   return EXTDM_OK;
 }
@@ -773,10 +798,19 @@ extern "C" int extdm_bilinear_resize_cl(const void* x, void* y, long long F, int
 }
 
 extern "C" int extdm_time_mlp(const long long* time, const float* w1, const float* b1, const float* w2,
-                              const float* b2, const float* wss, const float* bss, float* out, int B, int dim,
-                              int n_ss, void* stream) {
-  dim3 grid(B, 8);
-  time_mlp_kernel<<<grid, 256, 9 * dim * sizeof(float), STREAM>>>(time, w1, b1, w2, b2, wss, bss, out, dim, n_ss);
+                              const float* b2, const float* wss, const float* bss, float* out, float* scratch, int B,
+                              int dim, int n_ss, void* stream) {
+  const int td = 4 * dim;
+  if (td > 256 || B * td * 4 > 200 * 1024) return bad_arg("time_mlp: 4*dim <= 256 and B*4*dim floats must fit in shared memory");
+  time_mlp_kernel<<<B, 256, 5 * dim * sizeof(float), STREAM>>>(time, w1, b1, w2, b2, scratch, dim);
+  EXTDM_CHECK_LAUNCH();
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(time_ss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    configured = true;
+  }
+  const int grid = grid_for(static_cast<long long>(n_ss) * 32, 256, 148 * 2);
+  time_ss_kernel<<<grid, 256, static_cast<size_t>(B) * td * sizeof(float), STREAM>>>(scratch, wss, bss, out, B, td, n_ss);
   EXTDM_CHECK_LAUNCH();
   return EXTDM_OK;
 }

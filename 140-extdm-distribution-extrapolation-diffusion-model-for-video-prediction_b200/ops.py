@@ -299,8 +299,9 @@ def bilinear_resize_cl(rec, x, y):
 
 
 def time_mlp(rec, time, w1, b1, w2, b2, wss, bss, out, dim):
-    rec.emit("extdm_time_mlp", (_p(time), _p(w1), _p(b1), _p(w2), _p(b2), _p(wss), _p(bss), _p(out), time.shape[0],
-                                dim, wss.shape[0]), keep=(time, w1, b1, w2, b2, wss, bss, out))
+    scratch = torch.empty(time.shape[0], 4 * dim, dtype=torch.float32, device=out.device)
+    rec.emit("extdm_time_mlp", (_p(time), _p(w1), _p(b1), _p(w2), _p(b2), _p(wss), _p(bss), _p(out), _p(scratch),
+                                time.shape[0], dim, wss.shape[0]), keep=(time, w1, b1, w2, b2, wss, bss, out, scratch))
 
 
 def head_project(rec, hf, ho, wf, bf, wo, bo, out, t0):

@@ -138,9 +138,11 @@ int extdm_bilinear_resize_cl(const void* x, void* y, long long F, int h, int w, 
 
 /* Sinusoidal embedding + time_mlp + every ResnetBlock's SiLU->Linear in one launch
  * (...cross_multi.py:110-122, 812-817, 184-199).  time: (B,) int64.  w1 (4d, d), w2 (4d, 4d) fp32;
- * wss: (n_ss, 4d) fp32 = all blocks' mlp.1.weight stacked, bss (n_ss).  out: (B, n_ss) fp32. */
+ * wss: (n_ss, 4d) fp32 = all blocks' mlp.1.weight stacked, bss (n_ss).  out: (B, n_ss) fp32.
+ * scratch: (B, 4d) fp32 workspace (the SiLU(time embedding) rows shared by the two stages). */
 int extdm_time_mlp(const long long* time, const float* w1, const float* b1, const float* w2, const float* b2,
-                   const float* wss, const float* bss, float* out, int B, int dim, int n_ss, void* stream);
+                   const float* wss, const float* bss, float* out, float* scratch, int B, int dim, int n_ss,
+                   void* stream);
 
 /* Final 1x1 projections of the two heads (final_conv[1], occlusion_map[1]; ...cross_multi.py:875-892) on
  * frames [t0, T): out (B, 3, T-t0, H, W) fp32 NCTHW; hf / ho: (B, T, HW, C) bf16 head features. */
