@@ -65,6 +65,10 @@ struct StwParams {
   const float* rsin;           // [NTOK][DH/2]
   const float* ln_w;           // temporal mode: nn.LayerNorm weight / bias applied after the channel LayerNorm
   const float* ln_b;
+  // optional fused producer (16-warp kernel): the layer input is x = silu(h*a[b,c] + d[b,c]) + res, i.e. the last
+  // GroupNorm + SiLU + residual of the preceding ResnetBlock applied on load (h = p.x, the block2 conv output)
+  const __nv_bfloat16* pre_res;
+  const float* pre_ad;         // (B, 2, C): a then d
   int B, T, H, W, sd, sh, sw, Dp, n_windows;
   float eps;
 };
@@ -624,9 +628,21 @@ __global__ void __launch_bounds__(512, 1) stw_fused16_kernel(const __grid_consta
     cp_async_commit();
   };
 
+  // fused-producer mode: this thread's 16-byte slice of the residual branch, fetched one window ahead
+  const bool pre = p.pre_res != nullptr;
+  auto load_res = [&](const Win& w) -> uint4 {
+    const int s = src_pixel(w, tid / TPT);
+    if (!pre || s < 0 || CPT != 8) return make_uint4(0u, 0u, 0u, 0u);
+    return *reinterpret_cast<const uint4*>(p.pre_res + static_cast<long long>(s) * C + (tid % TPT) * CPT);
+  };
+
   int widx = blockIdx.x;
   int buf = 0;
-  if (widx < p.n_windows) prefetch_window(decode(widx), 0);
+  uint4 res_next = make_uint4(0u, 0u, 0u, 0u);
+  if (widx < p.n_windows) {
+    prefetch_window(decode(widx), 0);
+    res_next = load_res(decode(widx));
+  }
   const float qscale = rsqrtf(static_cast<float>(DH)) * kLog2e;
   constexpr float kMask = -100.0f * kLog2e;
 
@@ -635,8 +651,12 @@ __global__ void __launch_bounds__(512, 1) stw_fused16_kernel(const __grid_consta
     const int nxt = widx + gridDim.x;
     cp_async_wait<0>();
     __syncthreads();                                       // S1
-    if (nxt < p.n_windows) prefetch_window(decode(nxt), buf ^ 1);
-    const __nv_bfloat16* raw = s_raw + buf * NTOK * XP;
+    const uint4 res_cur = res_next;
+    if (nxt < p.n_windows) {
+      prefetch_window(decode(nxt), buf ^ 1);
+      res_next = load_res(decode(nxt));
+    }
+    __nv_bfloat16* raw = s_raw + buf * NTOK * XP;
     const bool has_mask = shifted && ((p.sd && win.id == nWd - 1) || (p.sh && win.ih == nWh - 1) ||
                                       (p.sw && win.iw == nWw - 1));
     if (has_mask && warp < NTOK / 32) {
@@ -657,6 +677,25 @@ __global__ void __launch_bounds__(512, 1) stw_fused16_kernel(const __grid_consta
         const uint4 t = *reinterpret_cast<const uint4*>(raw + n * XP + part * CPT);
         const float2 a = unpack_bf16(t.x), b = unpack_bf16(t.y), c = unpack_bf16(t.z), d = unpack_bf16(t.w);
         v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+        if (pre) {
+          // x = silu(GroupNorm(h)) + res, rounded to bf16 exactly as the stand-alone groupnorm_apply stores it; the
+          // tile keeps x (the layer's residual); T-padding tokens stay zero
+          const bool live = src_pixel(win, n) >= 0;
+          const float* ad = p.pre_ad + static_cast<long long>(win.b) * 2 * C + part * CPT;
+          const uint32_t rw[4] = {res_cur.x, res_cur.y, res_cur.z, res_cur.w};
+          uint32_t xb[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 rr = unpack_bf16(rw[j]);
+            const float x0 = live ? silu_fast(v[2 * j] * __ldg(ad + 2 * j) + __ldg(ad + C + 2 * j)) + rr.x : 0.f;
+            const float x1 = live ? silu_fast(v[2 * j + 1] * __ldg(ad + 2 * j + 1) + __ldg(ad + C + 2 * j + 1)) + rr.y : 0.f;
+            xb[j] = pack_bf16(x0, x1);
+            const float2 back = unpack_bf16(xb[j]);
+            v[2 * j] = back.x;
+            v[2 * j + 1] = back.y;
+          }
+          *reinterpret_cast<uint4*>(raw + n * XP + part * CPT) = make_uint4(xb[0], xb[1], xb[2], xb[3]);
+        }
       } else {
         const uint2 t = *reinterpret_cast<const uint2*>(raw + n * XP + part * CPT);
         const float2 a = unpack_bf16(t.x), b = unpack_bf16(t.y);
@@ -925,10 +964,11 @@ extern "C" int extdm_stw_fused_supported(int C, int heads, int dh, int wd, int w
   return 0;
 }
 
-extern "C" int extdm_stw_fused(const void* x, void* y, const float* gamma, const void* wqkv, const void* wproj,
-                               const float* proj_bias, const float* bias_table, const float* rope_cos,
-                               const float* rope_sin, int B, int T, int H, int W, int C, int heads, int dh, int wd,
-                               int wh, int ww, int sd, int sh, int sw, float eps, void* stream) {
+static int stw_fused_impl(const void* x, void* y, const float* gamma, const void* wqkv, const void* wproj,
+                          const float* proj_bias, const float* bias_table, const float* rope_cos,
+                          const float* rope_sin, const void* pre_res, const float* pre_ad, int B, int T, int H, int W,
+                          int C, int heads, int dh, int wd, int wh, int ww, int sd, int sh, int sw, float eps,
+                          void* stream) {
   if (!extdm_stw_fused_supported(C, heads, dh, wd, wh, ww) || H % wh || W % ww || sd < 0 || sd >= wd || sh < 0 ||
       sh >= wh || sw < 0 || sw >= ww) {
     extdm_set_error("stw_fused: unsupported (C, heads, dh, window, shift) combination", __FILE__, __LINE__);
@@ -945,6 +985,8 @@ extern "C" int extdm_stw_fused(const void* x, void* y, const float* gamma, const
   p.rcos = rope_cos;
   p.rsin = rope_sin;
   p.ln_w = p.ln_b = nullptr;
+  p.pre_res = reinterpret_cast<const __nv_bfloat16*>(pre_res);
+  p.pre_ad = pre_ad;
   p.B = B; p.T = T; p.H = H; p.W = W;
   p.sd = sd; p.sh = sh; p.sw = sw;
   p.Dp = (T + wd - 1) / wd * wd;
@@ -959,6 +1001,14 @@ extern "C" int extdm_stw_fused(const void* x, void* y, const float* gamma, const
   //                 (LN -> MMA -> TMEM drain -> attention -> MMA -> epilogue) is latency bound at one window per
   //                 iteration; two windows per iteration need 258 KB of shared memory
   static const bool use8 = getenv("EXTDM_STW8") != nullptr, use_tc = getenv("EXTDM_STW_TC") != nullptr;
+  if (pre_res) {
+    if (!(ntok == 64 && C == 64) || use8 || use_tc) {
+      extdm_set_error("stw_fused_pre: the fused GroupNorm producer exists for the 16-warp C = 64 kernel only", __FILE__,
+                      __LINE__);
+      return EXTDM_ERR_ARG;
+    }
+    return launch_stw16<64, 16, 64>(p, st);
+  }
   if (ntok == 64 && C == 64) {
     if (use8) return launch_stw<64, 16, 64>(p, st);
     if (use_tc)
@@ -968,6 +1018,32 @@ extern "C" int extdm_stw_fused(const void* x, void* y, const float* gamma, const
   }
   if (ntok == 64 && C == 128) return launch_stw<64, 16, 128>(p, st);
   return launch_stw<32, 32, 64>(p, st);       // (2,4,4) windows: the 16-warp layout would need 233 KB of shared memory
+}
+
+extern "C" int extdm_stw_fused(const void* x, void* y, const float* gamma, const void* wqkv, const void* wproj,
+                               const float* proj_bias, const float* bias_table, const float* rope_cos,
+                               const float* rope_sin, int B, int T, int H, int W, int C, int heads, int dh, int wd,
+                               int wh, int ww, int sd, int sh, int sw, float eps, void* stream) {
+  return stw_fused_impl(x, y, gamma, wqkv, wproj, proj_bias, bias_table, rope_cos, rope_sin, nullptr, nullptr, B, T, H, W,
+                        C, heads, dh, wd, wh, ww, sd, sh, sw, eps, stream);
+}
+
+extern "C" int extdm_stw_fused_pre_supported(int C, int heads, int dh, int wd, int wh, int ww) {
+  static const bool alt = getenv("EXTDM_STW8") != nullptr || getenv("EXTDM_STW_TC") != nullptr;
+  return !alt && heads == 8 && dh == 16 && C == 64 && wd == 4 && wh == 4 && ww == 4;
+}
+
+extern "C" int extdm_stw_fused_pre(const void* h, const void* res, const float* ad, void* y, const float* gamma,
+                                   const void* wqkv, const void* wproj, const float* proj_bias, const float* bias_table,
+                                   const float* rope_cos, const float* rope_sin, int B, int T, int H, int W, int C,
+                                   int heads, int dh, int wd, int wh, int ww, int sd, int sh, int sw, float eps,
+                                   void* stream) {
+  if (!res || !ad) {
+    extdm_set_error("stw_fused_pre: residual and affine table required", __FILE__, __LINE__);
+    return EXTDM_ERR_ARG;
+  }
+  return stw_fused_impl(h, y, gamma, wqkv, wproj, proj_bias, bias_table, rope_cos, rope_sin, res, ad, B, T, H, W, C,
+                        heads, dh, wd, wh, ww, sd, sh, sw, eps, stream);
 }
 
 extern "C" int extdm_temporal_fused_supported(int C, int heads, int dh, int T) {
@@ -994,6 +1070,8 @@ extern "C" int extdm_temporal_fused(const void* x, void* y, const float* gamma, 
   p.rsin = rope_sin;
   p.ln_w = ln_w;
   p.ln_b = ln_b;
+  p.pre_res = nullptr;
+  p.pre_ad = nullptr;
   p.B = B; p.T = T; p.H = HW; p.W = 1;
   p.sd = p.sh = p.sw = 0;
   p.Dp = 32;

@@ -160,6 +160,40 @@ __global__ void __launch_bounds__(256, 4) groupnorm_apply_kernel(
   }
 }
 
+// GroupNorm(8) folded to a per-(sample, channel) affine from the convolution's per-tile partial sums:
+// ad[b][0][c] = rstd*gamma[c], ad[b][1][c] = beta[c] - mean*rstd*gamma[c]  (consumed by kernels that apply the norm on load)
+__global__ void __launch_bounds__(256) groupnorm_affine_kernel(const float* __restrict__ part, int n_part,
+                                                               const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, float* __restrict__ ad,
+                                                               long long P, int C, float eps) {
+  __shared__ float s_part[8][16];
+  __shared__ float s_mean[8], s_rstd[8];
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float a0 = 0.f;
+  for (int i = warp * 2 + (lane >> 4); i < n_part; i += 16)
+    a0 += part[(static_cast<long long>(b) * n_part + i) * 16 + (lane & 15)];
+  a0 += __shfl_xor_sync(0xffffffffu, a0, 16);
+  if (lane < 16) s_part[warp][lane] = a0;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    const int g = threadIdx.x;
+    float sum = 0.f, sq = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { sum += s_part[w][g]; sq += s_part[w][8 + g]; }
+    const float cnt = static_cast<float>(P) * (C / 8);
+    const float mean = sum / cnt;
+    s_mean[g] = mean;
+    s_rstd[g] = rsqrtf(fmaxf(sq / cnt - mean * mean, 0.f) + eps);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / (C / 8);
+    const float a = s_rstd[g] * gamma[c];
+    ad[(static_cast<long long>(b) * 2) * C + c] = a;
+    ad[(static_cast<long long>(b) * 2 + 1) * C + c] = beta[c] - s_mean[g] * a;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ channel LayerNorm
 // One warp per row; lane owns V consecutive channels of each source.
 template <int V>
@@ -593,6 +627,89 @@ __global__ void __launch_bounds__(128) head_project_kernel(const __nv_bfloat16* 
   }
 }
 
+// Output heads with the last GroupNorm of each head's ResnetBlock fused in (final_conv / occlusion_map,
+// ...cross_multi.py:875-892, 963-966): per row y = silu(GN(h2)) + res (rounded to bf16 as the un-fused path stores it),
+// then the 1x1x1 projections.  Only the tp predicted frames are touched; the GroupNorm statistics (per-tile partial
+// sums from the producing convolutions' epilogues) still cover all T frames.  One sample per blockIdx.y.
+__global__ void __launch_bounds__(128) head_project_gn_kernel(
+    const __nv_bfloat16* __restrict__ h2f, const __nv_bfloat16* __restrict__ rf, const float* __restrict__ partf,
+    const float* __restrict__ gamma_f, const float* __restrict__ beta_f, const __nv_bfloat16* __restrict__ h2o,
+    const __nv_bfloat16* __restrict__ ro, const float* __restrict__ parto, const float* __restrict__ gamma_o,
+    const float* __restrict__ beta_o, int n_part, const float* __restrict__ wf, const float* __restrict__ bf,
+    const float* __restrict__ wo, const float* __restrict__ bo, float* __restrict__ out, int T, int t0, int HW, int C,
+    float eps) {
+  extern __shared__ float s_w[];            // wf[2][C], wo[C], a_f[C], d_f[C], a_o[C], d_o[C]
+  float* s_af = s_w + 3 * C;
+  float* s_df = s_af + C;
+  float* s_ao = s_df + C;
+  float* s_do = s_ao + C;
+  __shared__ float s_stat[2][16];           // per head: 8 sums, 8 sums of squares
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) s_w[i] = i < 2 * C ? wf[i] : wo[i - 2 * C];
+  // fold the partial sums: warps 0,1 -> head f, warps 2,3 -> head o; lanes = (part parity, value)
+  {
+    const float* part = warp < 2 ? partf : parto;
+    float a0 = 0.f;
+    for (int i = (warp & 1) * 2 + (lane >> 4); i < n_part; i += 4)
+      a0 += part[(static_cast<long long>(b) * n_part + i) * 16 + (lane & 15)];
+    a0 += __shfl_xor_sync(0xffffffffu, a0, 16);
+    __shared__ float s_tmp[4][16];
+    if (lane < 16) s_tmp[warp][lane] = a0;
+    __syncthreads();
+    if (threadIdx.x < 32) s_stat[threadIdx.x >> 4][threadIdx.x & 15] =
+        s_tmp[(threadIdx.x >> 4) * 2][threadIdx.x & 15] + s_tmp[(threadIdx.x >> 4) * 2 + 1][threadIdx.x & 15];
+  }
+  __syncthreads();
+  const float cnt = static_cast<float>(T) * HW * (C / 8);
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+    const int h = c / C, cc = c % C, g = cc / (C / 8);
+    const float mean = s_stat[h][g] / cnt;
+    const float var = fmaxf(s_stat[h][8 + g] / cnt - mean * mean, 0.f);
+    const float a = rsqrtf(var + eps) * (h ? gamma_o[cc] : gamma_f[cc]);
+    const float d = (h ? beta_o[cc] : beta_f[cc]) - mean * a;
+    if (h) { s_ao[cc] = a; s_do[cc] = d; } else { s_af[cc] = a; s_df[cc] = d; }
+  }
+  __syncthreads();
+  // C/8 threads per row (one 16-byte vector of each of the four tensors per thread), shuffle-reduced dot products
+  const int nt = T - t0;
+  const long long per = static_cast<long long>(nt) * HW;
+  const int tpr = C / 8;                                      // threads per row (8 for C = 64): a power of two <= 32
+  const int sub = threadIdx.x % tpr;
+  const long long rows_per_pass = static_cast<long long>(gridDim.x) * (blockDim.x / tpr);
+  for (long long i = static_cast<long long>(blockIdx.x) * (blockDim.x / tpr) + threadIdx.x / tpr; i < per;
+       i += rows_per_pass) {
+    const int p = i % HW;
+    const int t = i / HW;
+    const long long row = (static_cast<long long>(b) * T + t0 + t) * HW + p;
+    const int c = sub * 8;
+    float f[8], r[8], o[8], q[8];
+    load8(h2f + row * C + c, f);
+    load8(rf + row * C + c, r);
+    load8(h2o + row * C + c, o);
+    load8(ro + row * C + c, q);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float yf = __bfloat162float(__float2bfloat16(silu_fast(f[j] * s_af[c + j] + s_df[c + j]) + r[j]));
+      const float yo = __bfloat162float(__float2bfloat16(silu_fast(o[j] * s_ao[c + j] + s_do[c + j]) + q[j]));
+      a0 += yf * s_w[c + j];
+      a1 += yf * s_w[C + c + j];
+      a2 += yo * s_w[2 * C + c + j];
+    }
+    for (int off = tpr >> 1; off > 0; off >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, off);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, off);
+    }
+    if (sub == 0) {
+      const long long ob = ((static_cast<long long>(b) * 3) * nt + t) * HW + p;
+      out[ob] = a0 + bf[0];
+      out[ob + static_cast<long long>(nt) * HW] = a1 + bf[1];
+      out[ob + 2ll * nt * HW] = a2 + bo[0];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ LFAE helpers
 __global__ void __launch_bounds__(256) bn_relu_cl_kernel(const __nv_bfloat16* __restrict__ x,
                                                          const float* __restrict__ scale,
@@ -680,6 +797,14 @@ extern "C" int extdm_groupnorm_stats(const void* x, float* part, int B, long lon
   if (C % (8 * G) || G > 64 || 256 % (C / 8)) return bad_arg("groupnorm_stats: need C % (8G) == 0, C/8 | 256");
   dim3 grid(kGnChunks, B);
   groupnorm_stats_kernel<<<grid, 256, 0, STREAM>>>(BF(x), part, P, C, G);
+  EXTDM_CHECK_LAUNCH();
+  return EXTDM_OK;
+}
+
+extern "C" int extdm_groupnorm_affine(const float* part, int n_part, const float* gamma, const float* beta, float* ad,
+                                      int B, long long P, int C, int G, float eps, void* stream) {
+  if (G != 8 || C % 8 || n_part < 1) return bad_arg("groupnorm_affine: 8 groups, C % 8 == 0");
+  groupnorm_affine_kernel<<<B, 256, 0, STREAM>>>(part, n_part, gamma, beta, ad, P, C, eps);
   EXTDM_CHECK_LAUNCH();
   return EXTDM_OK;
 }
@@ -821,6 +946,22 @@ extern "C" int extdm_head_project(const void* hf, const void* ho, const float* w
   const long long total = static_cast<long long>(B) * (T - t0) * HW;
   head_project_kernel<<<grid_for(total, 128), 128, 3 * C * sizeof(float), STREAM>>>(BF(hf), BF(ho), wf, bf, wo, bo, out,
                                                                                   B, T, t0, HW, C);
+  EXTDM_CHECK_LAUNCH();
+  return EXTDM_OK;
+}
+
+extern "C" int extdm_head_project_gn(const void* h2f, const void* rf, const float* partf, const float* gamma_f,
+                                     const float* beta_f, const void* h2o, const void* ro, const float* parto,
+                                     const float* gamma_o, const float* beta_o, int n_part, const float* wf,
+                                     const float* bf, const float* wo, const float* bo, float* out, int B, int T, int t0,
+                                     int HW, int C, int G, float eps, void* stream) {
+  if (C % 8 || G != 8 || n_part < 1 || (C / 8) > 32 || ((C / 8) & (C / 8 - 1)) || (static_cast<long long>(T - t0) * HW) % (128 / (C / 8)))
+    return bad_arg("head_project_gn: C/8 a power of two <= 32, 8 groups, rows a multiple of the rows per block");
+  const long long per = static_cast<long long>(T - t0) * HW;
+  dim3 grid(grid_for(per * (C / 8), 128, (148 * 12 + B - 1) / B), B);
+  head_project_gn_kernel<<<grid, 128, 7 * C * sizeof(float), STREAM>>>(BF(h2f), BF(rf), partf, gamma_f, beta_f, BF(h2o),
+                                                                     BF(ro), parto, gamma_o, beta_o, n_part, wf, bf, wo,
+                                                                     bo, out, T, t0, HW, C, eps);
   EXTDM_CHECK_LAUNCH();
   return EXTDM_OK;
 }

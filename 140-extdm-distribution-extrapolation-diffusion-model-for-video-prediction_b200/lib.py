@@ -49,9 +49,13 @@ PROTOTYPES = {
     "extdm_bilinear_resize_cl": [_P, _P, _L, _I, _I, _I, _I, _I, _P],
     "extdm_time_mlp": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "extdm_head_project": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "extdm_head_project_gn": [_P] * 10 + [_I] + [_P] * 5 + [_I] * 6 + [_F, _P],
     "extdm_window_attention": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "extdm_stw_fused_supported": [_I, _I, _I, _I, _I, _I],
     "extdm_stw_fused": [_P, _P, _P, _P, _P, _P, _P, _P, _P] + [_I] * 13 + [_F, _P],
+    "extdm_stw_fused_pre_supported": [_I, _I, _I, _I, _I, _I],
+    "extdm_stw_fused_pre": [_P] * 11 + [_I] * 13 + [_F, _P],
+    "extdm_groupnorm_affine": [_P, _I, _P, _P, _P, _I, _L, _I, _I, _F, _P],
     "extdm_temporal_fused_supported": [_I, _I, _I, _I],
     "extdm_temporal_fused": [_P] * 10 + [_I] * 6 + [_F, _P],
     "extdm_cross_attention": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],

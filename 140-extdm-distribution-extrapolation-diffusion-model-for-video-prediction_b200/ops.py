@@ -310,6 +310,15 @@ def head_project(rec, hf, ho, wf, bf, wo, bo, out, t0):
              keep=(hf, ho, wf, bf, wo, bo, out))
 
 
+def head_project_gn(rec, h2f, rf, partf, gf, bf_, h2o, ro, parto, go, bo_, n_part, wf, bf, wo, bo, out, t0, eps=1e-5):
+    B, T, H, W, Cc = h2f.shape
+    rec.emit("extdm_head_project_gn", (_p(h2f), _p(rf), _p(partf), _p(gf), _p(bf_), _p(h2o), _p(ro), _p(parto), _p(go),
+                                       _p(bo_), n_part, _p(wf), _p(bf), _p(wo), _p(bo), _p(out), B, T, t0, H * W, Cc,
+                                       8, C.c_float(eps)),
+             keep=(h2f, rf, partf, gf, bf_, h2o, ro, parto, go, bo_, wf, bf, wo, bo, out),
+             meta=dict(bytes=8.0 * B * (T - t0) * H * W * Cc))
+
+
 def window_attention(rec, qkv, out, bias_table, rcos, rsin, heads, dh, window, shift):
     B, T, H, W, _ = qkv.shape
     rec.emit("extdm_window_attention", (_p(qkv), _p(out), _p(bias_table), _p(rcos), _p(rsin), B, T, H, W, heads, dh,
@@ -329,6 +338,26 @@ def stw_fused(rec, x, y, gamma, wqkv, wproj, proj_bias, bias_table, rcos, rsin, 
                                  shift[0], shift[1], shift[2], C.c_float(eps)),
              keep=(x, y, gamma, wqkv, wproj, proj_bias, bias_table, rcos, rsin),
              meta=dict(bytes=4.0 * x.numel(), tag=f"C={Cc} {T}x{H}x{W}"))
+
+
+def stw_fused_pre_supported(C_, heads, dh, window):
+    return bool(_lib.load().extdm_stw_fused_pre_supported(C_, heads, dh, window[0], window[1], window[2]))
+
+
+def groupnorm_affine(rec, part, n_part, gamma, beta, ad, P, Cc, eps=1e-5):
+    B = ad.shape[0]
+    rec.emit("extdm_groupnorm_affine", (_p(part), n_part, _p(gamma), _p(beta), _p(ad), B, P, Cc, 8, C.c_float(eps)),
+             keep=(part, gamma, beta, ad))
+
+
+def stw_fused_pre(rec, h, res, ad, y, gamma, wqkv, wproj, proj_bias, bias_table, rcos, rsin, heads, dh, window, shift,
+                  eps=1e-5):
+    B, T, H, W, Cc = h.shape
+    rec.emit("extdm_stw_fused_pre", (_p(h), _p(res), _p(ad), _p(y), _p(gamma), _p(wqkv), _p(wproj), _p(proj_bias),
+                                     _p(bias_table), _p(rcos), _p(rsin), B, T, H, W, Cc, heads, dh, window[0],
+                                     window[1], window[2], shift[0], shift[1], shift[2], C.c_float(eps)),
+             keep=(h, res, ad, y, gamma, wqkv, wproj, proj_bias, bias_table, rcos, rsin),
+             meta=dict(bytes=6.0 * h.numel(), tag=f"C={Cc} {T}x{H}x{W} +gn"))
 
 
 def temporal_fused_supported(C_, heads, dh, T):

@@ -111,6 +111,10 @@ class UnetRunner:
     """Launch lists + static buffers for one (config, batch, resolution)."""
 
     fuse_stw = True          # class-level switch (tests compare the fused and the un-fused STW paths)
+    # ResnetBlock's last GroupNorm applied inside the following attention kernel (extdm_stw_fused_pre).  Parity green but
+    # no faster on B200 (800 vs 716 + 98 us per level-0 pair: the attention kernel is compute bound and the extra
+    # element-wise work lands on its critical path), so it is off by default.
+    fuse_gn_stw = False
 
     def __init__(self, packed, B, H=32, W=32, fea_hw=16):
         cfg = packed.cfg
@@ -156,15 +160,46 @@ class UnetRunner:
         ops.linear_rows(rec, o, pk.w[p + ".fn.fn.fn.attn.to_out.weight"], C, y, res=xz)
         return y
 
-    def _stw(self, rec, x, p, shifted):
-        cfg, pk = self.cfg, self.pk
-        B, T, H, W, C = x.shape
+    def _window_shift(self, T, H, W, shifted):
+        """get_window_size (...cross_multi.py:393-406): a dim no larger than its window is not shifted."""
+        cfg = self.cfg
         window, shift = list(cfg.window), list(cfg.shift if shifted else (0, 0, 0))
         for i, size in enumerate((T, H, W)):
             if size <= window[i]:
                 if size != window[i]:
                     raise NotImplementedError(f"window {cfg.window} larger than the volume {(T, H, W)}")
                 shift[i] = 0
+        return window, shift
+
+    def _res_stw(self, rec, x, pres, pstw, cout, shifted, x2=None):
+        """ResnetBlock followed by its STW attention layer.  Where the 16-warp fused attention kernel applies, the
+        block's last GroupNorm + SiLU + residual are applied by that kernel on load (no stand-alone apply pass)."""
+        cfg, pk = self.cfg, self.pk
+        B, T, H, W, _ = x.shape
+        window, shift = self._window_shift(T, H, W, shifted)
+        if self.fuse_stw and self.fuse_gn_stw and cfg.groups == 8 and \
+                ops.stw_fused_pre_supported(cout, cfg.heads, cfg.dim_head, window):
+            h2, r, gnp, npart = self._resblock(rec, x, pres, cout, x2=x2, defer_norm2="shared")
+            ad = self.buf(B, 2, cout, dtype=torch.float32)
+            ops.groupnorm_affine(rec, gnp, npart, pk.f32[pres + ".block2.norm.weight"],
+                                 pk.f32[pres + ".block2.norm.bias"], ad, T * H * W, cout)
+            y = self.buf(B, T, H, W, cout)
+            ops.stw_fused_pre(rec, h2, r, ad, y, pk.f32[pstw + ".fn.norm.gamma"], pk.w[pstw + ".fn.fn.attn.qkv.weight"],
+                              pk.w[pstw + ".fn.fn.attn.proj.weight"], pk.f32[pstw + ".fn.fn.attn.proj.bias"],
+                              pk.f32[pstw + ".fn.fn.attn.relative_position_bias_table"], pk.rope_w[0], pk.rope_w[1],
+                              cfg.heads, cfg.dim_head, window, shift)
+            self.taps[pstw] = y
+            return y
+        x = self._resblock(rec, x, pres, cout, x2=x2)
+        self.taps[pres] = x
+        x = self._stw(rec, x, pstw, shifted)
+        self.taps[pstw] = x
+        return x
+
+    def _stw(self, rec, x, p, shifted):
+        cfg, pk = self.cfg, self.pk
+        B, T, H, W, C = x.shape
+        window, shift = self._window_shift(T, H, W, shifted)
         if self.fuse_stw and ops.stw_fused_supported(C, cfg.heads, cfg.dim_head, window):
             y = self.buf(B, T, H, W, C)
             ops.stw_fused(rec, x, y, pk.f32[p + ".fn.norm.gamma"], pk.w[p + ".fn.fn.attn.qkv.weight"],
@@ -184,7 +219,9 @@ class UnetRunner:
                         res=x)
         return y
 
-    def _resblock(self, rec, x, p, cout, x2=None, time=True):
+    def _resblock(self, rec, x, p, cout, x2=None, time=True, defer_norm2=False):
+        """defer_norm2: stop after block2's convolution and return (h2, residual, gn partial workspace, n_part) --
+        the caller fuses the last GroupNorm + SiLU + residual into its own kernel."""
         cfg, pk = self.cfg, self.pk
         B, T, H, W, _ = x.shape
         h1 = self.buf(B, T, H, W, cout)
@@ -198,6 +235,11 @@ class UnetRunner:
                            groups=cfg.groups, scale_shift=self.ss if time else None,
                            ss_off=pk.ss_off[p] if time else 0, n_part=npart)
         h2 = self.buf(B, T, H, W, cout)
+        if defer_norm2:
+            if not fused:
+                raise NotImplementedError("deferred GroupNorm needs the fused-statistics convolution")
+            if defer_norm2 != "shared":                   # own workspace: it must survive until the consumer runs
+                gnp = torch.zeros_like(self.gn_ws)
         ops.conv_cl(rec, h1, pk.w[p + ".block2.proj.weight"], cout, 3, h2, bias=pk.f32[p + ".block2.proj.bias"],
                     gn_partials=gnp)
         if (p + ".res_conv.weight") in pk.w:
@@ -205,6 +247,8 @@ class UnetRunner:
             ops.conv_cl(rec, x, pk.w[p + ".res_conv.weight"], cout, 1, r, x2=x2, bias=pk.f32[p + ".res_conv.bias"])
         else:
             r = x
+        if defer_norm2:
+            return h2, r, gnp, npart
         y = self.buf(B, T, H, W, cout)
         ops.groupnorm_silu(rec, h2, self.gn_ws, pk.f32[p + ".block2.norm.weight"], pk.f32[p + ".block2.norm.bias"], y,
                            groups=cfg.groups, res=r, n_part=npart)
@@ -269,14 +313,8 @@ class UnetRunner:
         return y
 
     def _stage(self, rec, x, p, cout, has_adaptor, x2=None):
-        x = self._resblock(rec, x, p + ".0", cout, x2=x2)
-        self.taps[p + ".0"] = x
-        x = self._stw(rec, x, p + ".1", True)
-        self.taps[p + ".1"] = x
-        x = self._resblock(rec, x, p + ".2", cout)
-        self.taps[p + ".2"] = x
-        x = self._stw(rec, x, p + ".3", False)
-        self.taps[p + ".3"] = x
+        x = self._res_stw(rec, x, p + ".0", p + ".1", cout, True, x2=x2)
+        x = self._res_stw(rec, x, p + ".2", p + ".3", cout, False)
         if has_adaptor:
             x = self._adaptor(rec, x, p + ".4")
             self.taps[p + ".4"] = x
@@ -414,6 +452,17 @@ class UnetRunner:
             if i < nres - 1:
                 x = self._upsample(st, x, p + ".5")
                 self.taps[p + ".5"] = x
+        if cfg.groups == 8 and d in (64, 128, 256):
+            # the heads' last GroupNorm + SiLU + residual run inside the projection kernel, on the tp frames only
+            h2f, rf, pf, npart = self._resblock(st, x, "final_conv.0", d, x2=x0, time=False, defer_norm2=True)
+            h2o, ro, po, _ = self._resblock(st, x, "occlusion_map.0", d, x2=x0, time=False, defer_norm2=True)
+            ops.head_project_gn(st, h2f, rf, pf, pk.f32["final_conv.0.block2.norm.weight"],
+                                pk.f32["final_conv.0.block2.norm.bias"], h2o, ro, po,
+                                pk.f32["occlusion_map.0.block2.norm.weight"],
+                                pk.f32["occlusion_map.0.block2.norm.bias"], npart, pk.f32["final_conv.1.weight"],
+                                pk.f32["final_conv.1.bias"], pk.f32["occlusion_map.1.weight"],
+                                pk.f32["occlusion_map.1.bias"], self.out, tm)
+            return
         hf = self._resblock(st, x, "final_conv.0", d, x2=x0, time=False)
         ho = self._resblock(st, x, "occlusion_map.0", d, x2=x0, time=False)
         ops.head_project(st, hf, ho, pk.f32["final_conv.1.weight"], pk.f32["final_conv.1.bias"],

@@ -161,6 +161,15 @@ int extdm_window_attention(const void* qkv, void* out, const float* bias_table, 
                            const float* rope_sin, int B, int T, int H, int W, int heads, int dh, int wd, int wh,
                            int ww, int sd, int sh, int sw, void* stream);
 
+/* extdm_head_project with the last GroupNorm(8)+SiLU+residual of each head's ResnetBlock fused in: hXf / hXo are
+ * the block2 convolution outputs (bf16, (B,T,HW,C)), rf / ro the residual branches, partf / parto the convolutions'
+ * gn_partials ((B, n_part, 16) fp32), gamma / beta the block2 norm parameters.  Writes out as extdm_head_project. */
+int extdm_head_project_gn(const void* h2f, const void* rf, const float* partf, const float* gamma_f,
+                          const float* beta_f, const void* h2o, const void* ro, const float* parto,
+                          const float* gamma_o, const float* beta_o, int n_part, const float* wf, const float* bf,
+                          const float* wo, const float* bo, float* out, int B, int T, int t0, int HW, int C, int G,
+                          float eps, void* stream);
+
 /* Whole Residual(PreNorm(STWAttentionLayer)) in one kernel for the high-resolution levels:
  * y = x + proj(window_attention(chanLN(x) @ Wqkv^T)) (...cross_multi.py:139-159, 409-560).  x, y: (B,T,H,W,C) bf16
  * (y must not alias x); wqkv: (3*heads*dh, C) bf16; wproj: (C, heads*dh) bf16.  Supported: heads 8 and
@@ -170,6 +179,20 @@ int extdm_stw_fused(const void* x, void* y, const float* gamma, const void* wqkv
                     const float* proj_bias, const float* bias_table, const float* rope_cos, const float* rope_sin,
                     int B, int T, int H, int W, int C, int heads, int dh, int wd, int wh, int ww, int sd, int sh,
                     int sw, float eps, void* stream);
+
+/* The same layer with the preceding ResnetBlock's last GroupNorm + SiLU + residual applied on load
+ * (...cross_multi.py:170-178 + :203 feeding :499-560): layer input x = silu(h*a[b,c] + d[b,c]) + res, h = the block2
+ * convolution output, (a, d) = extdm_groupnorm_affine of its gn_partials.  Saves the groupnorm_apply pass (one read of
+ * h, one of res, one write of x) and the layer's own read of x.  C = 64, (4,4,4) windows, 8 heads x 16. */
+int extdm_stw_fused_pre_supported(int C, int heads, int dh, int wd, int wh, int ww);
+int extdm_stw_fused_pre(const void* h, const void* res, const float* ad, void* y, const float* gamma, const void* wqkv,
+                        const void* wproj, const float* proj_bias, const float* bias_table, const float* rope_cos,
+                        const float* rope_sin, int B, int T, int H, int W, int C, int heads, int dh, int wd, int wh,
+                        int ww, int sd, int sh, int sw, float eps, void* stream);
+/* GroupNorm(8) as a per-(sample, channel) affine: ad (B, 2, C) fp32 = (rstd*gamma, beta - mean*rstd*gamma) from
+ * per-tile partial sums (B, n_part, 16).  P = T*H*W elements per channel. */
+int extdm_groupnorm_affine(const float* part, int n_part, const float* gamma, const float* beta, float* ad, int B,
+                           long long P, int C, int G, float eps, void* stream);
 
 /* Whole temporal attention layer Residual(PreNorm(EinopsToAndFrom(AttentionLayer))) in one kernel for C = 64
  * (init_temporal_attn, ...cross_multi.py:253-328, 794-795): y = x + z + to_out(attn(LayerNorm(z))), z = chanLN(x)*gamma;

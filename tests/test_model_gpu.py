@@ -93,6 +93,25 @@ def test_unet_layers_vs_oracle(name):
     assert worst <= 3e-2, worst
 
 
+def test_unet_forward_with_groupnorm_fused_into_attention():
+    """UnetRunner.fuse_gn_stw: the ResnetBlock's last GroupNorm + SiLU + residual applied on load by the following
+    window-attention kernel (extdm_stw_fused_pre) -- same gate as the default path."""
+    from extdm_b200.unet import UnetRunner
+    fx = torch.load(os.path.join(GOLD, "unet_ada_c2p5.pt"))
+    UnetRunner.fuse_gn_stw = True
+    try:
+        u, _ = build_unet(fx)
+        inp = unet_inputs(fx["variant"], fx["tc"], fx["tp"], fx["B"], fx["input_seed"])
+        out = u(inp["x"].cuda(), inp["time"].cuda(), cond_frames=inp["cond_frames"].cuda(),
+                cond_fea=inp["cond_fea"].cuda()).cpu()
+        names = [n for _, _, n in u.runner(fx["B"], 32, 32, 16).step.steps]
+        assert "extdm_stw_fused_pre" in names
+    finally:
+        UnetRunner.fuse_gn_stw = False
+    r = rel_l2(out, fx["out"])
+    assert r <= 2e-2, r
+
+
 def test_ddim_sample_matches_reference():
     from extdm_b200.diffusion import GaussianDiffusion
     fx = torch.load(os.path.join(GOLD, "ddim_ada_c2p5.pt"))
