@@ -40,6 +40,7 @@ struct GemmDev {
   float* gn_part;
   // halo kernel (k x k 'same' convolutions whose 128-row tile is bh full-width rows of one frame)
   int kh, kw, stages, a_ext_bytes;
+  int dbg;   // profiling experiments only (EXTDM_GEMM_DBG): 1 = no epilogue stores, 2 = no MMA issue, 4 = no TMA loads
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -299,12 +300,17 @@ __device__ __forceinline__ void epilogue_simple(const GemmDev& p, uint64_t* acc_
                                                 uint32_t tmem_base, int warp, int lane) {
   constexpr uint32_t kAccCols = BN < 32 ? 32 : BN;
   constexpr int kChunks = BN / 16;
-  constexpr int kThreads = 128 * EPW;
-  float* s_bias = s_gn;                    // [BN]
-  float* s_part = s_gn + 256;              // [2][4 quarters][kChunks][4] : {sum lo8, sum hi8, sq lo8, sq hi8}
+  // The EPW warps of a TMEM lane quarter form two groups: group 0 drains the even tiles of this CTA (accumulator
+  // stage 0), group 1 the odd ones (stage 1), so the per-tile latency chain of one group (barrier wake-up, tcgen05.ld,
+  // stores) overlaps the other group's tile.  Within a group the warps take the 16-column chunks round-robin.
+  constexpr int kGroups = EPW >= 2 ? 2 : 1;
+  constexpr int kWpg = EPW / kGroups;      // warps per (quarter, group)
+  constexpr int kGThreads = 128 * kWpg;    // threads per group
   const int q = warp & 3;                  // TMEM lane quarter
   const int e = (warp - 2) >> 2;           // which of the EPW warps of this quarter
-  const int et = (warp - 2) * 32 + lane;   // epilogue thread index
+  const int grp = e / kWpg, eg = e % kWpg;
+  float* s_bias = s_gn + grp * 256;        // [BN] per group
+  const int gt = (eg * 4 + ((warp - 2) & 3)) * 32 + lane;     // thread index inside the group
   const int m = q * 32 + lane;             // tile row
   int r = m;
   const int i1 = r % p.box[0]; r /= p.box[0];
@@ -314,6 +320,7 @@ __device__ __forceinline__ void epilogue_simple(const GemmDev& p, uint64_t* acc_
   int staged_n0 = -1;
   int local = 0;
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+    if (kGroups == 2 && (local & 1) != grp) continue;
     const int as = local & 1;
     const uint32_t aphase = (local >> 1) & 1;
     const TileCoord tc = decode_tile(p, tile, BN);
@@ -323,17 +330,17 @@ __device__ __forceinline__ void epilogue_simple(const GemmDev& p, uint64_t* acc_
                         g3 < p.start[2] + p.count[2] && g4 < p.start[3] + p.count[3];
     __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + p.out_base + g1 * p.out_stride[0] +
                           g2 * p.out_stride[1] + g3 * p.out_stride[2] + g4 * p.out_stride[3] + n0;
-    if (n0 != staged_n0) {
-      if (staged_n0 >= 0) asm volatile("bar.sync 2, %0;" ::"n"(kThreads) : "memory");
-      for (int j = et; j < BN; j += kThreads) s_bias[j] = (p.bias && n0 + j < p.n) ? __ldg(p.bias + n0 + j) : 0.f;
-      asm volatile("bar.sync 2, %0;" ::"n"(kThreads) : "memory");
+    if (n0 != staged_n0) {                 // uniform over the group's threads; named barrier 2 + grp
+      if (staged_n0 >= 0) asm volatile("bar.sync %0, %1;" ::"r"(2 + grp), "n"(kGThreads) : "memory");
+      for (int j = gt; j < BN; j += kGThreads) s_bias[j] = (p.bias && n0 + j < p.n) ? __ldg(p.bias + n0 + j) : 0.f;
+      asm volatile("bar.sync %0, %1;" ::"r"(2 + grp), "n"(kGThreads) : "memory");
       staged_n0 = n0;
     }
     mbar_wait(&acc_full[as], aphase);
     tc_fence_after();
     const uint32_t taddr = tmem_base + as * kAccCols + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-    for (int ch = e; ch < kChunks; ch += EPW) {
+    for (int ch = eg; ch < kChunks; ch += kWpg) {
       uint32_t raw[16];
       tmem_ld16(taddr + ch * 16, raw);
       tmem_ld_wait();
@@ -353,8 +360,10 @@ __device__ __forceinline__ void epilogue_simple(const GemmDev& p, uint64_t* acc_
         uint32_t pk[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
-        *reinterpret_cast<uint4*>(orow + ch * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(orow + ch * 16 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        if (!(p.dbg & 1)) {
+          *reinterpret_cast<uint4*>(orow + ch * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(orow + ch * 16 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
         if (GN) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -365,7 +374,10 @@ __device__ __forceinline__ void epilogue_simple(const GemmDev& p, uint64_t* acc_
         }
       }
       if (GN) {
-        // 4 values per thread -> warp totals (fixed-order butterfly); lanes 0, 8, 16, 24 publish value (lane >> 3)
+        // 4 values per thread -> warp totals (fixed-order butterfly); lanes 0, 8, 16, 24 hold value (lane >> 3) of
+        // {sum lo8, sum hi8, sq lo8, sq hi8}.  Every warp publishes its own partial record slots straight to global
+        // memory -- record (tile, lane quarter[, chunk parity for BN = 256]) of 16 floats = 8 group sums + 8 group sums
+        // of squares -- so the epilogue warps never synchronise with each other; groupnorm_apply folds the records.
         {
           const bool up = (lane & 16) != 0;
           const float s0 = up ? gst[0] : gst[2], k0 = up ? gst[2] : gst[0];
@@ -381,29 +393,21 @@ __device__ __forceinline__ void epilogue_simple(const GemmDev& p, uint64_t* acc_
         gst[0] += __shfl_xor_sync(0xffffffffu, gst[0], 4);
         gst[0] += __shfl_xor_sync(0xffffffffu, gst[0], 2);
         gst[0] += __shfl_xor_sync(0xffffffffu, gst[0], 1);
-        if ((lane & 7) == 0) s_part[((as * 4 + q) * kChunks + ch) * 4 + (lane >> 3)] = gst[0];
+        constexpr int kCpg = BN / 8;                   // columns per GroupNorm group
+        constexpr int kRec = BN == 256 ? 2 : 1;        // records per (tile, quarter)
+        float* rec = p.gn_part + ((static_cast<long long>(tc.m_tile) * 4 + q) * kRec + (BN == 256 ? (ch & 1) : 0)) * 16;
+        const int stat = lane >> 4;                    // lanes 0 / 8 -> sums, 16 / 24 -> sums of squares
+        if (kCpg == 8) {
+          if ((lane & 7) == 0) rec[stat * 8 + 2 * ch + ((lane >> 3) & 1)] = gst[0];
+        } else {
+          const float tot = gst[0] + __shfl_xor_sync(0xffffffffu, gst[0], 8);       // lo8 + hi8 of this chunk
+          if ((lane & 15) == 0) rec[stat * 8 + (kCpg == 16 ? ch : (ch >> 1))] = tot;
+        }
       }
     }
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&acc_empty[as]);
-    if (GN) {
-      asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
-      if (et < 16) {
-        // value et: stat = et / 8 (0 sum, 1 sum of squares), group g = et % 8 = 8-column units [g*U, (g+1)*U)
-        constexpr int U = BN / 64;           // 8-column units per GroupNorm group (BN/8 columns per group)
-        const int stat = et >> 3, g = et & 7;
-        float tot = 0.f;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int unit = g * U + u;
-          const int ch = unit >> 1, idx = stat * 2 + (unit & 1);
-          tot += (s_part[((as * 4 + 0) * kChunks + ch) * 4 + idx] + s_part[((as * 4 + 1) * kChunks + ch) * 4 + idx]) +
-                 (s_part[((as * 4 + 2) * kChunks + ch) * 4 + idx] + s_part[((as * 4 + 3) * kChunks + ch) * 4 + idx]);
-        }
-        p.gn_part[static_cast<long long>(tc.m_tile) * 16 + et] = tot;
-      }
-    }
   }
 }
 
@@ -453,7 +457,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4 * PlainCfg<BN, SIMPLE>::kEpw);
+      mbar_init(&acc_empty[s], SIMPLE ? 4 * (PlainCfg<BN, SIMPLE>::kEpw / 2) : 4);
     }
     fence_barrier_init();
   }
@@ -490,7 +494,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
           const int o1 = p.tap[tap][0], o2 = p.tap[tap][1], o3 = p.tap[tap][2];
           for (int kc = 0; kc < nk; ++kc) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            if (elect_one()) {
+            if (p.dbg & 4) {
+              if (elect_one()) mbar_arrive(&full_bar[stage]);
+            } else if (elect_one()) {
               uint8_t* sa = smem + stage * kStageBytes;
               uint8_t* sb = sa + kATileBytes;
               mbar_expect_tx(&full_bar[stage], kStageBytes);
@@ -528,10 +534,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
             const uint32_t sa = smem_u32(smem + stage * kStageBytes);
             const uint64_t da = umma_desc_sw128(sa);
             const uint64_t db = umma_desc_sw128(sa + kATileBytes);
+            if (!(p.dbg & 2)) {
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              // advance 16 bf16 = 32 B along K inside the 128B swizzle row: +2 in (addr >> 4) units
-              umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                // advance 16 bf16 = 32 B along K inside the 128B swizzle row: +2 in (addr >> 4) units
+                umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+              }
             }
             umma_commit(&empty_bar[stage]);
           }
@@ -605,7 +613,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], SIMPLE ? 4 * kHaloEpw : 4);
+      mbar_init(&acc_empty[s], SIMPLE ? 4 * (kHaloEpw / 2) : 4);
     }
     mbar_init(resb_bar, 1);
     fence_barrier_init();
@@ -649,7 +657,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
         for (int kx = 0; kx < p.kw; ++kx) {
           for (int kc = 0; kc < nk; ++kc) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            if (elect_one()) {
+            if (p.dbg & 4) {
+              if (elect_one()) mbar_arrive(&full_bar[stage]);
+            } else if (elect_one()) {
               uint8_t* sa = s_stage + stage * stage_bytes;
               mbar_expect_tx(&full_bar[stage], stage_bytes);
               const int x0 = tc.c1 + kx - p.kw / 2, y0 = tc.c2 - p.kh / 2;
@@ -697,7 +707,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
             if (elect_one()) {
               const uint32_t sa = smem_u32(s_stage + stage * stage_bytes);
               uint32_t acc = accumulate;
-              for (int ky = 0; ky < p.kh; ++ky) {
+              for (int ky = 0; ky < ((p.dbg & 2) ? 0 : p.kh); ++ky) {
                 const uint32_t sb = RESB ? smem_u32(s_resb + ((ky * p.kw + kx) * nk + kc) * kBTileBytes)
                                          : sa + p.a_ext_bytes + ky * kBTileBytes;
                 const uint64_t da = umma_desc_sw128(sa + ky * row_shift);
@@ -892,6 +902,8 @@ extern "C" int extdm_conv_gemm(const ExtdmGemm* g, void* stream_) {
   dev.col_shift = g->col_shift;
   dev.act = g->act;
   dev.gn_part = g->gn_partials;
+  static const int dbg_flags = getenv("EXTDM_GEMM_DBG") ? atoi(getenv("EXTDM_GEMM_DBG")) : 0;
+  dev.dbg = dbg_flags;
   if ((g->col_scale == nullptr) != (g->col_shift == nullptr)) {
     extdm_set_error("extdm_conv_gemm: col_scale and col_shift go together", __FILE__, __LINE__);
     return EXTDM_ERR_ARG;
@@ -962,8 +974,8 @@ extern "C" int extdm_conv_gemm(const ExtdmGemm* g, void* stream_) {
   rc = encode_map(&mb, g->w, 2, wd, ws, wb, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
   if (rc) return rc;
 
-  if (g->gn_partials && (g->n != bn || bn < 64 || g->out_fp32 || g->col_group < g->n || g->box[3] != 1)) {
-    extdm_set_error("extdm_conv_gemm: gn_partials needs n in {64,128,256} (= block_n), bf16 output, box[3] == 1",
+  if (g->gn_partials && (g->n != bn || bn < 64 || !simple || g->box[3] != 1)) {
+    extdm_set_error("extdm_conv_gemm: gn_partials needs n in {64,128,256} (= block_n), a bias-only bf16 epilogue, box[3] == 1",
                     __FILE__, __LINE__);
     return EXTDM_ERR_ARG;
   }

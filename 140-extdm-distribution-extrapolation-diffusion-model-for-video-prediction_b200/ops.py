@@ -220,6 +220,12 @@ def conv_tiles_per_sample(T, H, W):
     return -(-W // bw) * -(-H // bh) * -(-T // bt)
 
 
+def gn_parts_per_sample(T, H, W, Cc):
+    """GroupNorm partial records (16 floats each) one sample's convolution epilogue writes: one per (128-row tile,
+    TMEM lane quarter), two for 256 channels (include/extdm_b200.h: ExtdmGemm.gn_partials)."""
+    return conv_tiles_per_sample(T, H, W) * 4 * (2 if Cc == 256 else 1)
+
+
 GN_CHUNKS = 32          # EXTDM_GN_CHUNKS
 
 

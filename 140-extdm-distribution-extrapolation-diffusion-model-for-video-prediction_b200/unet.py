@@ -128,7 +128,7 @@ class UnetRunner:
         self.cond_fea = torch.zeros(B, 256, T, fea_hw, fea_hw, **f32)
         self.time = torch.zeros(B, dtype=torch.long, device=dev)
         self.out = torch.zeros(B, 3, tp, H, W, **f32)
-        self.gn_ws = torch.zeros(B * max(32, ops.conv_tiles_per_sample(T, H, W)) * cfg.groups * 2, **f32)
+        self.gn_ws = torch.zeros(B * max(32, ops.gn_parts_per_sample(T, H, W, 64)) * cfg.groups * 2, **f32)
         self.ss = torch.zeros(B, packed.n_ss, **f32)
         self.prologue = ops.Recorder(record=True)
         self.step = ops.Recorder(record=True)
@@ -227,7 +227,7 @@ class UnetRunner:
         h1 = self.buf(B, T, H, W, cout)
         # GroupNorm statistics come out of the convolution's epilogue (per-tile partial sums), not a second pass
         fused = cfg.groups == 8 and cout in (64, 128, 256)
-        npart = ops.conv_tiles_per_sample(T, H, W) if fused else None
+        npart = ops.gn_parts_per_sample(T, H, W, cout) if fused else None
         gnp = self.gn_ws if fused else None
         ops.conv_cl(rec, x, pk.w[p + ".block1.proj.weight"], cout, 3, h1, x2=x2, bias=pk.f32[p + ".block1.proj.bias"],
                     gn_partials=gnp)

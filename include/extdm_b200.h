@@ -68,10 +68,12 @@ typedef struct ExtdmGemm {
   const float* col_shift;
   int act; /* 0 none, 1 relu, 2 silu, 3 sigmoid */
   int block_n; /* 0 = choose automatically (16/64/128/256) */
-  /* Optional GroupNorm(8) statistics of the stored (bf16) output, fused into the epilogue: per 128-row tile t (tiles
-   * ordered D1 fastest .. D4 slowest, so a sample's tiles are contiguous) 16 floats gn_partials[t*16 + g] = sum and
-   * [t*16 + 8 + g] = sum of squares over the tile's rows and the n/8 channels of group g.  Requires n == block_n in
-   * {64,128,256}, bf16 output, box[3] == 1.  Consumed by extdm_groupnorm_apply (n_part = tiles per sample). */
+  /* Optional GroupNorm(8) statistics of the stored (bf16) output, fused into the epilogue.  Every epilogue warp writes
+   * its own slots of a 16-float record [8 group sums | 8 group sums of squares]; record index =
+   * (tile*4 + q)*R + r with tile = 128-row tile (ordered D1 fastest .. D4 slowest, so a sample's tiles are
+   * contiguous), q = 32-row quarter of the tile, R = 2 and r = 16-column chunk parity for n = 256, R = 1 otherwise.
+   * A group's statistic is the sum over the sample's records.  Requires n == block_n in {64,128,256}, a bias(+act)-only
+   * bf16 epilogue, box[3] == 1.  Consumed by extdm_groupnorm_apply (n_part = records per sample). */
   float* gn_partials;
 } ExtdmGemm;
 

@@ -170,7 +170,7 @@ def test_conv_epilogue_groupnorm_partials(C, T, H, B):
     bias = rnd(C, seed=3)
     g, b = rnd(C, seed=4) * 0.1 + 1, rnd(C, seed=5) * 0.1
     xc = to_cl(x)
-    npart = ops.conv_tiles_per_sample(T, H, H)
+    npart = ops.gn_parts_per_sample(T, H, H, C)
     ws = torch.full((B * npart * 16,), float("nan"), device=DEV)
     h = torch.zeros(B, T, H, H, C, device=DEV, dtype=BF)
     ops.conv_cl(R, xc, ops.pack_conv_weight(w), C, 3, h, bias=bias, gn_partials=ws)
