@@ -187,3 +187,18 @@ if __name__ == "__main__":
         gen_generator()
     if "pipeline" in which:
         gen_pipeline()
+
+
+def gen_metrics():
+    """PSNR / SSIM of the reference's metrics/ package on seeded random videos -> tests/golden/metrics_ref.pt
+    (checked by tests/test_host_cpu.py::test_metrics_match_reference)."""
+    from metrics.calculate_psnr import calculate_psnr
+    from metrics.calculate_ssim import calculate_ssim
+    g = torch.Generator().manual_seed(77)
+    v1 = torch.rand(3, 4, 3, 32, 32, generator=g)
+    v2 = (v1 + 0.05 * torch.randn(3, 4, 3, 32, 32, generator=g)).clamp(0, 1)
+    v2[0, 0] = v1[0, 0]
+    p, s = calculate_psnr(v1, v2), calculate_ssim(v1, v2)
+    plain = lambda d: {k: float(v) for k, v in d.items()}
+    torch.save({"seed": 77, "psnr": plain(p["psnr"]), "psnr_std": plain(p["psnr_std"]), "ssim": plain(s["ssim"]),
+                "ssim_std": plain(s["ssim_std"])}, os.path.join(HERE, "metrics_ref.pt"))

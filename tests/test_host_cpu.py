@@ -130,3 +130,42 @@ def test_two_rank_sharding_gloo(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29581", str(script)],
                        capture_output=True, text=True, env=env, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_metrics_match_reference():
+    """evaluate.psnr_videos / ssim_videos against the reference's metrics/calculate_{psnr,ssim}.py (golden fixture)."""
+    from extdm_b200 import evaluate
+    fx = torch.load(os.path.join(GOLD, "metrics_ref.pt"))
+    g = torch.Generator().manual_seed(fx["seed"])
+    v1 = torch.rand(3, 4, 3, 32, 32, generator=g)
+    v2 = (v1 + 0.05 * torch.randn(3, 4, 3, 32, 32, generator=g)).clamp(0, 1)
+    v2[0, 0] = v1[0, 0]
+    p, s = evaluate.summarize(evaluate.psnr_videos(v1, v2)), evaluate.summarize(evaluate.ssim_videos(v1, v2))
+    for t in range(4):
+        assert abs(p[f"avg[{t}]"] - fx["psnr"][f"avg[{t}]"]) < 1e-6
+        assert abs(p[f"std[{t}]"] - fx["psnr_std"][f"std[{t}]"]) < 1e-6
+        assert abs(s[f"avg[{t}]"] - fx["ssim"][f"avg[{t}]"]) < 1e-9
+        assert abs(s[f"std[{t}]"] - fx["ssim_std"][f"std[{t}]"]) < 1e-9
+
+
+def test_result_wire_format(tmp_path):
+    """origin.pt / result_{k}.pt dumps (scripts/DM/valid.py:281-286) and the tolerant diffusion-checkpoint loader."""
+    from extdm_b200 import evaluate
+    origin, result = torch.rand(2, 3, 6, 3, 8, 8), torch.rand(2, 3, 6, 3, 8, 8)
+    evaluate.save_results(str(tmp_path), origin, result)
+    assert torch.equal(torch.load(tmp_path / "origin.pt"), origin[:, 0])
+    assert torch.equal(torch.load(tmp_path / "result_2.pt"), result[:, 2])
+    from extdm_b200.flow_diffusion import FlowDiffusion
+    fx = torch.load(os.path.join(GOLD, "pipeline_kth_c2p5.pt"))
+    fd = FlowDiffusion(config=fx["cfg"], pretrained_pth="", is_train=False,
+                       Unet3D_architecture="DenoiseNet_STWAtt_w_w_ref_adaptor_cross_multi_traj_ada").eval()
+    sd = {k: v.clone() + 1 for k, v in fd.diffusion.state_dict().items() if v.dtype.is_floating_point}
+    sd.update({k: v for k, v in fd.diffusion.state_dict().items() if not v.dtype.is_floating_point})
+    sd["denoise_fn.init_temporal_attn.fn.fn.fn.attn.rotary_emb.some_new_buffer"] = torch.zeros(3)   # App. E11
+    info = evaluate.load_dm_checkpoint(fd, {"diffusion": sd, "example": 7, "epoch": 1})
+    assert info == {"example": 7, "epoch": 1}
+    k = "denoise_fn.init_conv.bias"
+    assert torch.equal(fd.diffusion.state_dict()[k], sd[k])
+    del sd[k]
+    with pytest.raises(RuntimeError):
+        evaluate.load_dm_checkpoint(fd, {"diffusion": sd})

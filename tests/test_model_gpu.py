@@ -209,3 +209,22 @@ def test_every_dataset_config_samples(name, B):
     assert tuple(out.shape) == (B, 3, tc + tp, hw, hw)
     assert tuple(ret["sample_vid_grid"].shape) == (B, 2, tc + tp, 32, 32)
     assert torch.isfinite(out).all() and out.min() >= 0 and out.max() <= 1
+
+
+def test_evaluation_loop_wire_shapes():
+    """evaluate.sample_videos = the valid.py:156-197 loop (repeat-n + autoregressive rollout): shapes / layout of
+    origin and result, conditioning frames passed through, on-device and host-hop modes agree given the same noise."""
+    from extdm_b200 import configs, evaluate
+    model, cfg = configs.build_model("ucf", device="cuda")            # tc 4, tp 8 -> 12 predicted = 2 rounds
+    vids = torch.rand(2, 3, 16, 64, 64, generator=torch.Generator().manual_seed(3))
+    torch.manual_seed(5)
+    origin, result = evaluate.sample_videos(model, vids, total_pred=12, num_sample_video=2)
+    assert tuple(origin.shape) == (2, 2, 16, 3, 64, 64) and tuple(result.shape) == (2, 2, 16, 3, 64, 64)
+    assert torch.equal(result[:, :, :4], origin[:, :, :4]) and torch.equal(origin[:, 0], origin[:, 1])
+    assert torch.isfinite(result).all() and result.min() >= 0 and result.max() <= 1
+    torch.manual_seed(5)
+    _, result2 = evaluate.sample_videos(model, vids, total_pred=12, num_sample_video=2, on_device=False)
+    assert (result - result2).abs().max().item() <= 1e-6
+    p = evaluate.psnr_videos(origin[:, 0].cuda(), result[:, 0].cuda())
+    s = evaluate.ssim_videos(origin[:, 0].cuda(), result[:, 0].cuda())
+    assert tuple(p.shape) == (2, 16) and (p[:, :4] == 100).all() and (s[:, :4] > 0.999999).all()
