@@ -995,14 +995,15 @@ static int stw_fused_impl(const void* x, void* y, const float* gamma, const void
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int ntok = wd * wh * ww;
   // Three implementations of the C = 64 / 64-token layer, all parity-tested (tests/test_kernels_gpu.py runs each):
-  //   default       all-mma.sync, 16 warps            716 us per level-0 launch on B200 (HMMA-pipe bound)
+  //   default       projections on tcgen05 (stw_tc.cu), two windows per M = 128 tile; level-0 launch on B200: see
+  //                 DESIGN.md section 5 (needs H/4 and W/4 powers of two, else the 16-warp kernel runs)
+  //   EXTDM_STW16   all-mma.sync, 16 warps            716 us per level-0 launch (legacy-HMMA-pipe bound)
   //   EXTDM_STW8    all-mma.sync, 8 warps             716 us
-  //   EXTDM_STW_TC  projections on tcgen05 (stw_tc.cu) 815 us: 1/3 of the HMMA work but the per-window phase chain
-  //                 (LN -> MMA -> TMEM drain -> attention -> MMA -> epilogue) is latency bound at one window per
-  //                 iteration; two windows per iteration need 258 KB of shared memory
-  static const bool use8 = getenv("EXTDM_STW8") != nullptr, use_tc = getenv("EXTDM_STW_TC") != nullptr;
+  static const bool use8 = getenv("EXTDM_STW8") != nullptr, use16 = getenv("EXTDM_STW16") != nullptr;
+  const int nww_ = W / 4, nwh_ = H / 4;
+  const bool use_tc = !use8 && !use16 && !(nww_ & (nww_ - 1)) && !(nwh_ & (nwh_ - 1));
   if (pre_res) {
-    if (!(ntok == 64 && C == 64) || use8 || use_tc) {
+    if (!(ntok == 64 && C == 64)) {
       extdm_set_error("stw_fused_pre: the fused GroupNorm producer exists for the 16-warp C = 64 kernel only", __FILE__,
                       __LINE__);
       return EXTDM_ERR_ARG;
@@ -1029,8 +1030,7 @@ extern "C" int extdm_stw_fused(const void* x, void* y, const float* gamma, const
 }
 
 extern "C" int extdm_stw_fused_pre_supported(int C, int heads, int dh, int wd, int wh, int ww) {
-  static const bool alt = getenv("EXTDM_STW8") != nullptr || getenv("EXTDM_STW_TC") != nullptr;
-  return !alt && heads == 8 && dh == 16 && C == 64 && wd == 4 && wh == 4 && ww == 4;
+  return heads == 8 && dh == 16 && C == 64 && wd == 4 && wh == 4 && ww == 4;
 }
 
 extern "C" int extdm_stw_fused_pre(const void* h, const void* res, const float* ad, void* y, const float* gamma,

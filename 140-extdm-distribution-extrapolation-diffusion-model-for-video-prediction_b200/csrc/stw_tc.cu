@@ -61,22 +61,22 @@ __device__ __forceinline__ int sw128(int r, int j) { return (r >> 3) * 1024 + (r
 __device__ __forceinline__ int swrow256(int r, int j) { return r * 256 + ((j ^ (r & 7)) << 4); }
 
 struct Smem {
-  static constexpr int wqkv = 0;                       // [384][64] SW128             49152
-  static constexpr int wp = wqkv + 49152;              // 2 x [64][64] SW128          16384
-  static constexpr int a = wp + 16384;                 // [64 (+64 ignored)][64] SW128 8192
-  static constexpr int o = a + 8192;                   // 2 x [64 (+64)][64] SW128    16384
-  static constexpr int q = o + 16384;                  // [64][128] XOR-swizzled rows 16384
-  static constexpr int k = q + 16384;
-  static constexpr int v = k + 16384;
-  static constexpr int bias = v + 16384;               // [8][64][64] bf16, XOR-swizzled rows (128 B)  65536
-  static constexpr int raw = bias + 65536;             // 2 x [64][72] bf16           18432
-  static constexpr int rope = raw + 18432;             // cos, sin [64][8] fp32       4096
-  static constexpr int misc = rope + 4096;             // gamma[64], pbias[64] fp32   512
-  static constexpr int emask = misc + 512;             // [2][8] u32                  64
-  static constexpr int bars = emask + 64;              // 2 mbarriers + tmem slot     32
+  static constexpr int wqkv = 0;                       // [384][64] SW128                         49152
+  static constexpr int wp = wqkv + 49152;              // 2 x [64][64] SW128                      16384
+  static constexpr int a = wp + 16384;                 // [128][64] SW128 (LayerNorm output)      16384
+  static constexpr int qo = a + 16384;                 // 2 x [128][64] SW128: Q, then O in place 32768
+  static constexpr int k = qo + 32768;                 // 2 x [128][64] SW128                     32768
+  static constexpr int v = k + 32768;                  //                                         32768
+  static constexpr int raw = v + 32768;                // 2 x [128][72] bf16 raw tokens           36864
+  static constexpr int tbl = raw + 36864;              // [8][344] bf16 bias table * log2(e)       5504
+  static constexpr int rope = tbl + 5504;              // cos, sin [64][8] fp32                    4096
+  static constexpr int misc = rope + 4096;             // gamma[64], pbias[64] fp32                 512
+  static constexpr int emask = misc + 512;             // [2 windows][2 halves][8] u32              128
+  static constexpr int bars = emask + 128;             // 2 mbarriers + tmem slot                    32
   static constexpr int total = bars + 32;
 };
 constexpr int XPR = 72;                                // raw pitch (bf16)
+constexpr int TBLP = 344;                              // bias-table pitch per head (343 entries)
 
 struct TcParams {
   const __nv_bfloat16* x;
@@ -89,21 +89,25 @@ struct TcParams {
   const float* rcos;
   const float* rsin;
   int B, T, H, W, sd, sh, sw, Dp, n_windows;
+  int lw, lh;                  // log2 of the window counts along W and H (powers of two: checked by the launcher)
   float eps;
 };
 
+// byte offset of hidden-dim chunk j (0..15, 8 bf16 each) of token row r in the two-k-block swizzled [128][128] tile
+__device__ __forceinline__ int sw2(int r, int j) { return (j >> 3) * 16384 + sw128(r, j & 7); }
+
+// Two windows (128 tokens) per iteration: rows 0..63 of every M = 128 tile are window 2p, rows 64..127 window 2p+1.
 __global__ void __launch_bounds__(NTH, 1) stw_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw_[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_) + 1023) & ~uintptr_t(1023));
   uint8_t* s_wqkv = sm + Smem::wqkv;
   uint8_t* s_wp = sm + Smem::wp;
   uint8_t* s_a = sm + Smem::a;
-  uint8_t* s_o = sm + Smem::o;
-  uint8_t* s_q = sm + Smem::q;
+  uint8_t* s_qo = sm + Smem::qo;
   uint8_t* s_k = sm + Smem::k;
   uint8_t* s_v = sm + Smem::v;
-  uint8_t* s_bias = sm + Smem::bias;
   __nv_bfloat16* s_raw = reinterpret_cast<__nv_bfloat16*>(sm + Smem::raw);
+  const unsigned short* s_tbl = reinterpret_cast<const unsigned short*>(sm + Smem::tbl);
   float* s_cos = reinterpret_cast<float*>(sm + Smem::rope);
   float* s_sin = s_cos + NTOK * (DH / 2);
   float* s_gamma = reinterpret_cast<float*>(sm + Smem::misc);
@@ -114,7 +118,6 @@ __global__ void __launch_bounds__(NTH, 1) stw_tc_kernel(const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_o + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
-  const int head = warp & 7, half = warp >> 3;
   const bool shifted = (p.sd | p.sh | p.sw) != 0;
   const int nWw = p.W / 4, nWh = p.H / 4, nWd = p.Dp / 4;
   const int lrow = lane & 15, lhi = lane >> 4;
@@ -131,11 +134,10 @@ __global__ void __launch_bounds__(NTH, 1) stw_tc_kernel(const __grid_constant__ 
   }
   for (int i = tid; i < NTOK * (DH / 2); i += NTH) { s_cos[i] = p.rcos[i]; s_sin[i] = p.rsin[i]; }
   for (int i = tid; i < C; i += NTH) { s_gamma[i] = p.gamma[i]; s_pbias[i] = p.proj_bias ? p.proj_bias[i] : 0.f; }
-  for (int i = tid; i < HEADS * NTOK * NTOK; i += NTH) {
-    const int j = i & 63, q = (i >> 6) & 63, h = i >> 12;
-    const int rel = (((q >> 4) - (j >> 4) + 3) * 7 + (((q >> 2) & 3) - ((j >> 2) & 3) + 3)) * 7 + ((q & 3) - (j & 3) + 3);
-    const int off = h * 8192 + q * 128 + (((j >> 3) ^ (q & 7)) << 4) + (j & 7) * 2;
-    *reinterpret_cast<__nv_bfloat16*>(s_bias + off) = __float2bfloat16(p.bias_table[rel * HEADS + h] * kL2e);
+  for (int i = tid; i < HEADS * TBLP; i += NTH) {
+    const int h = i / TBLP, e = i % TBLP;
+    reinterpret_cast<__nv_bfloat16*>(sm + Smem::tbl)[i] =
+        __float2bfloat16(e < 343 ? p.bias_table[e * HEADS + h] * kL2e : 0.f);
   }
   if (tid == 0) {
     mbar_init(bar_qkv, 1);
@@ -153,16 +155,18 @@ __global__ void __launch_bounds__(NTH, 1) stw_tc_kernel(const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
 
-  struct Win { int b, id, ih, iw; };
+  struct Win { int b, id, ih, iw; };                    // b < 0: no such window (odd tail)
   auto decode = [&](int widx) {
     Win w;
-    w.iw = widx % nWw; widx /= nWw;
-    w.ih = widx % nWh; widx /= nWh;
-    w.id = widx % nWd;
+    if (widx >= p.n_windows) { w.b = -1; w.id = w.ih = w.iw = 0; return w; }
+    w.iw = widx & (nWw - 1); widx >>= p.lw;
+    w.ih = widx & (nWh - 1); widx >>= p.lh;
     w.b = widx / nWd;
+    w.id = widx - w.b * nWd;
     return w;
   };
   auto src_pixel = [&](const Win& w, int n) -> int {
+    if (w.b < 0) return -1;
     int od = w.id * 4 + (n >> 4) + p.sd, oh = w.ih * 4 + ((n >> 2) & 3) + p.sh, ow = w.iw * 4 + (n & 3) + p.sw;
     if (od >= p.Dp) od -= p.Dp;
     if (oh >= p.H) oh -= p.H;
@@ -176,71 +180,94 @@ __global__ void __launch_bounds__(NTH, 1) stw_tc_kernel(const __grid_constant__ 
     if (p.sw && w.iw == nWw - 1 && (n & 3) >= 4 - p.sw) c |= 4;
     return c;
   };
-  auto prefetch_window = [&](const Win& w, int buf) {
-    __nv_bfloat16* dst = s_raw + buf * NTOK * XPR;
-    {
-      const int n = tid >> 3, c8 = tid & 7;            // 64 tokens x 8 chunks = 512 threads
-      const int s = src_pixel(w, n);
+  auto win_masked = [&](const Win& w) -> bool {
+    return shifted && w.b >= 0 && ((p.sd && w.id == nWd - 1) || (p.sh && w.ih == nWh - 1) || (p.sw && w.iw == nWw - 1));
+  };
+  auto prefetch_pair = [&](int pair, int buf) {
+    __nv_bfloat16* dst = s_raw + buf * 128 * XPR;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int i = tid + k * NTH;                     // 128 tokens x 8 chunks: k = 0 -> window 2p, k = 1 -> 2p+1
+      const int n = i >> 3, c8 = i & 7;
+      const Win w = decode(2 * pair + k);
+      const int s = src_pixel(w, n & 63);
       t_cp_async16(dst + n * XPR + c8 * 8, p.x + (s >= 0 ? static_cast<long long>(s) * C + c8 * 8 : 0), s >= 0 ? 16 : 0);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
-  int widx = blockIdx.x;
+  const int n_pairs = (p.n_windows + 1) / 2;
+  int pair = blockIdx.x;
   int buf = 0;
   uint32_t it = 0;
-  if (widx < p.n_windows) prefetch_window(decode(widx), 0);
+  if (pair < n_pairs) prefetch_pair(pair, 0);
   const float qscale = 0.25f * kL2e;                    // dh^-1/2 * log2(e)
   constexpr float kMask = -100.0f * kL2e;
   constexpr uint32_t idesc256 = umma_idesc_bf16(128, 256), idesc128 = umma_idesc_bf16(128, 128),
                      idesc64 = umma_idesc_bf16(128, 64);
+  // attention role of this warp: one (window, head)
+  const int awin = warp >> 3, head = warp & 7;
+  const int hchunk = (head & 3) * 2, hkb = head >> 2;   // this head's 16 hidden dims = chunks hchunk, hchunk+1 of k-block hkb
+  // relative-position table offsets (lin(i) - lin(j) + 171): per-thread parts, the rest are compile-time immediates
+  const int ltg = (tg >> 1) * 7 + (tg & 1) * 2;
+  const int pt0 = (g >> 2) * 7 + (g & 3) - ltg + 171, pt1 = pt0 + 14;
+  const unsigned short* tb = s_tbl + head * TBLP;
 
-  for (; widx < p.n_windows; widx += gridDim.x, ++it) {
-    const Win win = decode(widx);
-    const int nxt = widx + gridDim.x;
+  for (; pair < n_pairs; pair += gridDim.x, ++it) {
+    const Win w0 = decode(2 * pair), w1 = decode(2 * pair + 1);
+    const int nxt = pair + gridDim.x;
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();                                    // S1: raw[buf] landed; previous window fully retired
-    if (nxt < p.n_windows) prefetch_window(decode(nxt), buf ^ 1);
-    const __nv_bfloat16* raw = s_raw + buf * NTOK * XPR;
-    const bool has_mask = shifted && ((p.sd && win.id == nWd - 1) || (p.sh && win.ih == nWh - 1) ||
-                                      (p.sw && win.iw == nWw - 1));
-    if (has_mask && warp < 2) {
-      const int code = region_code(win, warp * 32 + lane);
-      uint32_t mine = 0;
+    __syncthreads();                                    // S1: raw[buf] landed; previous pair fully retired
+    if (nxt < n_pairs) prefetch_pair(nxt, buf ^ 1);
+    const __nv_bfloat16* raw = s_raw + buf * 128 * XPR;
+    if (warp < 4) {                                     // region-membership words of window warp>>1, token half warp&1
+      const Win& w = (warp >> 1) ? w1 : w0;
+      if (win_masked(w)) {
+        const int code = region_code(w, (warp & 1) * 32 + lane);
+        uint32_t mine = 0;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint32_t bal = __ballot_sync(0xffffffffu, code == c);
-        if (lane == c) mine = bal;
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t bal = __ballot_sync(0xffffffffu, code == c);
+          if (lane == c) mine = bal;
+        }
+        if (lane < 8) s_E[warp * 8 + lane] = mine;
       }
-      if (lane < 8) s_E[warp * 8 + lane] = mine;
     }
-    // ---- channel LayerNorm: 8 threads per token, one 16-byte chunk each -> swizzled A tile
+    // ---- channel LayerNorm: 4 threads per token, two 16-byte chunks each -> swizzled A tile
     {
-      const int n = tid >> 3, part = tid & 7;
-      const uint4 t = *reinterpret_cast<const uint4*>(raw + n * XPR + part * 8);
-      const float2 a = unpack_bf16(t.x), b = unpack_bf16(t.y), c = unpack_bf16(t.z), d = unpack_bf16(t.w);
-      float v[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+      const int n = tid >> 2, part = tid & 3;
+      const Win& w = (n >> 6) ? w1 : w0;
+      float v[16];
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const uint4 t = *reinterpret_cast<const uint4*>(raw + n * XPR + part * 16 + h2 * 8);
+        const float2 a = unpack_bf16(t.x), b = unpack_bf16(t.y), c = unpack_bf16(t.z), d = unpack_bf16(t.w);
+        v[h2 * 8] = a.x; v[h2 * 8 + 1] = a.y; v[h2 * 8 + 2] = b.x; v[h2 * 8 + 3] = b.y;
+        v[h2 * 8 + 4] = c.x; v[h2 * 8 + 5] = c.y; v[h2 * 8 + 6] = d.x; v[h2 * 8 + 7] = d.y;
+      }
       float sum = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) sum += v[j];
+      for (int j = 0; j < 16; ++j) sum += v[j];
       sum += __shfl_xor_sync(0xffffffffu, sum, 1);
       sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-      sum += __shfl_xor_sync(0xffffffffu, sum, 4);
       const float mean = sum * (1.0f / C);
       float sq = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { const float dd = v[j] - mean; sq += dd * dd; }
+      for (int j = 0; j < 16; ++j) { const float dd = v[j] - mean; sq += dd * dd; }
       sq += __shfl_xor_sync(0xffffffffu, sq, 1);
       sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-      sq += __shfl_xor_sync(0xffffffffu, sq, 4);
-      const float rstd = src_pixel(win, n) >= 0 ? rsqrtf(sq * (1.0f / C) + p.eps) : 0.f;
-      uint32_t pk[4];
+      const float rstd = src_pixel(w, n & 63) >= 0 ? rsqrtf(sq * (1.0f / C) + p.eps) : 0.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int cc = part * 8 + 2 * j;
-        pk[j] = pack_bf16((v[2 * j] - mean) * rstd * s_gamma[cc], (v[2 * j + 1] - mean) * rstd * s_gamma[cc + 1]);
+      for (int h2 = 0; h2 < 2; ++h2) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int cc = part * 16 + h2 * 8 + 2 * j;
+          pk[j] = pack_bf16((v[h2 * 8 + 2 * j] - mean) * rstd * s_gamma[cc],
+                            (v[h2 * 8 + 2 * j + 1] - mean) * rstd * s_gamma[cc + 1]);
+        }
+        *reinterpret_cast<uint4*>(s_a + sw128(n, part * 2 + h2)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
-      *reinterpret_cast<uint4*>(s_a + sw128(n, part)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
     fence_proxy_async();                                // A tile -> visible to the tensor-core (async) proxy
     __syncthreads();                                    // S2
@@ -264,12 +291,13 @@ __global__ void __launch_bounds__(NTH, 1) stw_tc_kernel(const __grid_constant__ 
     mbar_wait(bar_qkv, it & 1);
     tc_fence_after();
 
-    // ---- drain: warps of TMEM lane quarters 0 / 1 (tokens 0..63), thread = token, 96 columns per warp
-    if ((warp & 3) < 2) {
-      const int tok = (warp & 3) * 32 + lane;
+    // ---- drain: every warp, TMEM lane quarter warp & 3 (32 tokens), 96 columns: thread = token
+    {
+      const int q = warp & 3;
+      const int tok = q * 32 + lane;                    // 0..127 (window tok >> 6, position tok & 63)
       const int e = warp >> 2;                          // 0..3 -> columns [96e, 96e + 96)
-      const uint32_t taddr = tmem_u + (static_cast<uint32_t>((warp & 3) * 32) << 16) + e * 96;
-      const bool live = src_pixel(win, tok) >= 0;       // T-padding tokens stay exactly zero (q = k = v = 0)
+      const uint32_t taddr = tmem_u + (static_cast<uint32_t>(q * 32) << 16) + e * 96;
+      const int pos = tok & 63;
 #pragma unroll 1
       for (int c = 0; c < 6; ++c) {
         uint32_t rr[16];
@@ -279,12 +307,12 @@ __global__ void __launch_bounds__(NTH, 1) stw_tc_kernel(const __grid_constant__ 
         const int region = col >> 7, hd = (col & 127) >> 4;
         float f[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = live ? __uint_as_float(rr[j]) : 0.f;
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(rr[j]);
         if (region < 2) {
           const float sc = region == 0 ? qscale : 1.0f;
 #pragma unroll
           for (int pr = 0; pr < 8; ++pr) {
-            const float cs = s_cos[tok * 8 + pr], sn = s_sin[tok * 8 + pr];
+            const float cs = s_cos[pos * 8 + pr], sn = s_sin[pos * 8 + pr];
             const float x0 = f[2 * pr] * sc, x1 = f[2 * pr + 1] * sc;
             f[2 * pr] = x0 * cs - x1 * sn;
             f[2 * pr + 1] = x1 * cs + x0 * sn;
@@ -293,102 +321,108 @@ __global__ void __launch_bounds__(NTH, 1) stw_tc_kernel(const __grid_constant__ 
         uint32_t pk[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
-        uint8_t* dst = region == 0 ? s_q : (region == 1 ? s_k : s_v);
-        *reinterpret_cast<uint4*>(dst + swrow256(tok, hd * 2)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(dst + swrow256(tok, hd * 2 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        uint8_t* dst = region == 0 ? s_qo : (region == 1 ? s_k : s_v);
+        *reinterpret_cast<uint4*>(dst + sw2(tok, hd * 2)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(dst + sw2(tok, hd * 2 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       }
     }
     tc_fence_before();
     __syncthreads();                                    // S3: Q / K / V tiles complete
 
-    // ---- attention core (mma.sync): warp = (head, half of the query m-tiles)
-    uint32_t kfrag[8][2];
-#pragma unroll
-    for (int np = 0; np < 4; ++np) {
-      uint32_t kf[4];
-      const int r = np * 16 + (lane & 7) + ((lane >> 4) & 1) * 8;
-      t_ldsm_x4(kf, s_k + swrow256(r, head * 2 + ((lane >> 3) & 1)));
-      kfrag[2 * np][0] = kf[0]; kfrag[2 * np][1] = kf[1];
-      kfrag[2 * np + 1][0] = kf[2]; kfrag[2 * np + 1][1] = kf[3];
-    }
-#pragma unroll
-    for (int mi = 0; mi < 2; ++mi) {
-      const int mt = half * 2 + mi;
-      const int r0 = mt * 16 + g, r1 = r0 + 8;
-      uint32_t qa[4];
-      t_ldsm_x4(qa, s_q + swrow256(mt * 16 + lrow, head * 2 + lhi));
-      float s[8][4];
+    // ---- attention core (mma.sync): warp = (window awin, head); all four query m-tiles; O overwrites Q in place
+    {
+      const Win& aw = awin ? w1 : w0;
+      const bool has_mask = win_masked(aw);
+      const int rb = awin * 64;                         // first row of this window in the tiles
+      uint32_t kfrag[8][2];
 #pragma unroll
       for (int np = 0; np < 4; ++np) {
-        uint32_t bb[4];
-        const int r = mt * 16 + lrow;
-        t_ldsm_x4(bb, s_bias + head * 8192 + r * 128 + (((np * 2 + lhi) ^ (r & 7)) << 4));
-        s[2 * np][0] = t_bf_lo(bb[0]); s[2 * np][1] = t_bf_hi(bb[0]);
-        s[2 * np][2] = t_bf_lo(bb[1]); s[2 * np][3] = t_bf_hi(bb[1]);
-        s[2 * np + 1][0] = t_bf_lo(bb[2]); s[2 * np + 1][1] = t_bf_hi(bb[2]);
-        s[2 * np + 1][2] = t_bf_lo(bb[3]); s[2 * np + 1][3] = t_bf_hi(bb[3]);
+        uint32_t kf[4];
+        const int r = rb + np * 16 + (lane & 7) + ((lane >> 4) & 1) * 8;
+        t_ldsm_x4(kf, s_k + hkb * 16384 + sw128(r, hchunk + ((lane >> 3) & 1)));
+        kfrag[2 * np][0] = kf[0]; kfrag[2 * np][1] = kf[1];
+        kfrag[2 * np + 1][0] = kf[2]; kfrag[2 * np + 1][1] = kf[3];
       }
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) t_mma16816(s[nt], qa, kfrag[nt][0], kfrag[nt][1]);
-      if (has_mask) {
-        const int c0 = region_code(win, r0), c1 = region_code(win, r1);
-        const uint32_t e0[2] = {~s_E[c0], ~s_E[8 + c0]}, e1[2] = {~s_E[c1], ~s_E[8 + c1]};
+      for (int mt = 0; mt < 4; ++mt) {
+        const int r0 = mt * 16 + g, r1 = r0 + 8;        // window-local query rows
+        uint32_t qa[4];
+        t_ldsm_x4(qa, s_qo + hkb * 16384 + sw128(rb + mt * 16 + lrow, hchunk + lhi));
+        // scores start from the relative-position bias: tbl[lin(i) - lin(j) + 171], adjacent keys = adjacent entries
+        float s[8][4];
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
-          const int bit = (nt * 8) % 32 + tg * 2;
-          const uint32_t m0 = e0[nt / 4] >> bit, m1 = e1[nt / 4] >> bit;
-          if (m0 & 1) s[nt][0] += kMask;
-          if (m0 & 2) s[nt][1] += kMask;
-          if (m1 & 1) s[nt][2] += kMask;
-          if (m1 & 2) s[nt][3] += kMask;
+          const int kk = mt * 49 - (nt >> 1) * 49 - (nt & 1) * 14;      // compile-time part of the table index
+          s[nt][0] = __uint_as_float(static_cast<uint32_t>(tb[pt0 + kk]) << 16);
+          s[nt][1] = __uint_as_float(static_cast<uint32_t>(tb[pt0 + kk - 1]) << 16);
+          s[nt][2] = __uint_as_float(static_cast<uint32_t>(tb[pt1 + kk]) << 16);
+          s[nt][3] = __uint_as_float(static_cast<uint32_t>(tb[pt1 + kk - 1]) << 16);
         }
-      }
-      float m0 = -3.0e38f, m1 = -3.0e38f;
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
-        m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
-      }
-      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
-      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
-      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-      float l0 = 0.f, l1 = 0.f;
+        for (int nt = 0; nt < 8; ++nt) t_mma16816(s[nt], qa, kfrag[nt][0], kfrag[nt][1]);
+        if (has_mask) {
+          const int c0 = region_code(aw, r0), c1 = region_code(aw, r1);
+          const uint32_t* E = s_E + awin * 16;
+          const uint32_t e0[2] = {~E[c0], ~E[8 + c0]}, e1[2] = {~E[c1], ~E[8 + c1]};
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        s[nt][0] = t_exp2(s[nt][0] - m0);
-        s[nt][1] = t_exp2(s[nt][1] - m0);
-        s[nt][2] = t_exp2(s[nt][2] - m1);
-        s[nt][3] = t_exp2(s[nt][3] - m1);
-        l0 += s[nt][0] + s[nt][1];
-        l1 += s[nt][2] + s[nt][3];
-      }
-      l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-      l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-      l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-      l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-      const float inv0 = __frcp_rn(l0), inv1 = __frcp_rn(l1);
-      float o[2][4];
+          for (int nt = 0; nt < 8; ++nt) {
+            const int bit = (nt * 8) % 32 + tg * 2;
+            const uint32_t m0 = e0[nt / 4] >> bit, m1 = e1[nt / 4] >> bit;
+            if (m0 & 1) s[nt][0] += kMask;
+            if (m0 & 2) s[nt][1] += kMask;
+            if (m1 & 1) s[nt][2] += kMask;
+            if (m1 & 2) s[nt][3] += kMask;
+          }
+        }
+        float m0 = -3.0e38f, m1 = -3.0e38f;
 #pragma unroll
-      for (int dt = 0; dt < 2; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+        for (int nt = 0; nt < 8; ++nt) {
+          m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
+          m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
+        }
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+        float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-      for (int ps = 0; ps < 4; ++ps) {
-        uint32_t a[4];
-        a[0] = pack_bf16(s[2 * ps][0], s[2 * ps][1]);
-        a[1] = pack_bf16(s[2 * ps][2], s[2 * ps][3]);
-        a[2] = pack_bf16(s[2 * ps + 1][0], s[2 * ps + 1][1]);
-        a[3] = pack_bf16(s[2 * ps + 1][2], s[2 * ps + 1][3]);
-        uint32_t vb[4];
-        t_ldsm_x4_trans(vb, s_v + swrow256(ps * 16 + lrow, head * 2 + lhi));
-        t_mma16816(o[0], a, vb[0], vb[1]);
-        t_mma16816(o[1], a, vb[2], vb[3]);
-      }
-      // head output -> swizzled K-major A tile of the output projection: hidden column head*16 + dt*8 + tg*2
+        for (int nt = 0; nt < 8; ++nt) {
+          s[nt][0] = t_exp2(s[nt][0] - m0);
+          s[nt][1] = t_exp2(s[nt][1] - m0);
+          s[nt][2] = t_exp2(s[nt][2] - m1);
+          s[nt][3] = t_exp2(s[nt][3] - m1);
+          l0 += s[nt][0] + s[nt][1];
+          l1 += s[nt][2] + s[nt][3];
+        }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        const float inv0 = __frcp_rn(l0), inv1 = __frcp_rn(l1);
+        float o[2][4];
 #pragma unroll
-      for (int dt = 0; dt < 2; ++dt) {
-        const int chunk = (head * 2 + dt) & 7, kb = head >> 2;
-        *reinterpret_cast<uint32_t*>(s_o + kb * 8192 + sw128(r0, chunk) + tg * 4) = pack_bf16(o[dt][0] * inv0, o[dt][1] * inv0);
-        *reinterpret_cast<uint32_t*>(s_o + kb * 8192 + sw128(r1, chunk) + tg * 4) = pack_bf16(o[dt][2] * inv1, o[dt][3] * inv1);
+        for (int dt = 0; dt < 2; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+#pragma unroll
+        for (int ps = 0; ps < 4; ++ps) {
+          uint32_t a[4];
+          a[0] = pack_bf16(s[2 * ps][0], s[2 * ps][1]);
+          a[1] = pack_bf16(s[2 * ps][2], s[2 * ps][3]);
+          a[2] = pack_bf16(s[2 * ps + 1][0], s[2 * ps + 1][1]);
+          a[3] = pack_bf16(s[2 * ps + 1][2], s[2 * ps + 1][3]);
+          uint32_t vb[4];
+          t_ldsm_x4_trans(vb, s_v + hkb * 16384 + sw128(rb + ps * 16 + lrow, hchunk + lhi));
+          t_mma16816(o[0], a, vb[0], vb[1]);
+          t_mma16816(o[1], a, vb[2], vb[3]);
+        }
+        // head output over this head's Q slots (this warp has consumed them): the A tile of the output projection
+        __syncwarp();
+#pragma unroll
+        for (int dt = 0; dt < 2; ++dt) {
+          *reinterpret_cast<uint32_t*>(s_qo + hkb * 16384 + sw128(rb + r0, hchunk + dt) + tg * 4) =
+              pack_bf16(o[dt][0] * inv0, o[dt][1] * inv0);
+          *reinterpret_cast<uint32_t*>(s_qo + hkb * 16384 + sw128(rb + r1, hchunk + dt) + tg * 4) =
+              pack_bf16(o[dt][2] * inv1, o[dt][3] * inv1);
+        }
       }
     }
     fence_proxy_async();
@@ -400,7 +434,7 @@ __global__ void __launch_bounds__(NTH, 1) stw_tc_kernel(const __grid_constant__ 
       if (elect_one()) {
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
-          const uint64_t da = umma_desc_sw128(smem_u32(s_o) + kb * 8192);
+          const uint64_t da = umma_desc_sw128(smem_u32(s_qo) + kb * 16384);
           const uint64_t db = umma_desc_sw128(smem_u32(s_wp) + kb * 8192);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(tmem_u + 384, da + 2 * k, db + 2 * k, idesc64, (kb | k) ? 1u : 0u);
@@ -411,13 +445,14 @@ __global__ void __launch_bounds__(NTH, 1) stw_tc_kernel(const __grid_constant__ 
     }
     mbar_wait(bar_o, it & 1);
     tc_fence_after();
-    if ((warp & 3) < 2) {
-      const int tok = (warp & 3) * 32 + lane;
+    {
+      const int q = warp & 3;
+      const int tok = q * 32 + lane;
       const int e = warp >> 2;                          // 16-column chunk of the 64 output channels
       uint32_t rr[16];
-      tmem_ld16(tmem_u + (static_cast<uint32_t>((warp & 3) * 32) << 16) + 384 + e * 16, rr);
+      tmem_ld16(tmem_u + (static_cast<uint32_t>(q * 32) << 16) + 384 + e * 16, rr);
       tmem_ld_wait();
-      const int d = src_pixel(win, tok);
+      const int d = src_pixel((tok >> 6) ? w1 : w0, tok & 63);
       if (d >= 0) {
         const uint4 r0v = *reinterpret_cast<const uint4*>(raw + tok * XPR + e * 16);
         const uint4 r1v = *reinterpret_cast<const uint4*>(raw + tok * XPR + e * 16 + 8);
@@ -470,6 +505,14 @@ int extdm_stw_tc_launch(const void* x, void* y, const float* gamma, const void* 
   p.Dp = (T + 3) / 4 * 4;
   p.n_windows = B * (p.Dp / 4) * (H / 4) * (W / 4);
   p.eps = eps;
+  const int nww = W / 4, nwh = H / 4;
+  if ((nww & (nww - 1)) || (nwh & (nwh - 1)) || W % 4 || H % 4) {
+    extdm_set_error("stw_tc: H/4 and W/4 must be powers of two", __FILE__, __LINE__);
+    return EXTDM_ERR_ARG;
+  }
+  p.lw = 0; p.lh = 0;
+  while ((1 << p.lw) < nww) ++p.lw;
+  while ((1 << p.lh) < nwh) ++p.lh;
   constexpr int smem = Smem::total + 1024;
   static bool configured = false;
   static int sms = 0;
@@ -484,7 +527,8 @@ int extdm_stw_tc_launch(const void* x, void* y, const float* gamma, const void* 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const int grid = p.n_windows < sms ? p.n_windows : sms;
+  const int n_pairs = (p.n_windows + 1) / 2;
+  const int grid = n_pairs < sms ? n_pairs : sms;
   stw_tc_kernel<<<grid, NTH, smem, static_cast<cudaStream_t>(stream)>>>(p);
   EXTDM_CHECK_LAUNCH();
   return EXTDM_OK;

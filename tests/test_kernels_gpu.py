@@ -483,11 +483,11 @@ def test_lfae_helpers():
 @pytest.mark.parametrize("window,dh,C,T,H,shifted", [((4, 4, 4), 16, 64, 7, 16, True), ((4, 4, 4), 16, 64, 7, 16, False),
                                                      ((4, 4, 4), 16, 128, 6, 8, True), ((2, 4, 4), 32, 64, 5, 8, True),
                                                      ((4, 4, 4), 16, 64, 30, 32, True)])
-@pytest.mark.parametrize("impl", ["default", "EXTDM_STW8", "EXTDM_STW_TC"])
+@pytest.mark.parametrize("impl", ["default", "EXTDM_STW8", "EXTDM_STW16"])
 def test_stw_fused_layer(window, dh, C, T, H, shifted, impl):
     """Whole Residual(PreNorm(STWAttentionLayer)) in one kernel vs the oracle's stw_attention (CPU fp32), for each of
-    the three implementations of the C = 64 / 64-token layer (16-warp mma.sync, 8-warp mma.sync, tcgen05
-    projections).  The library reads the switch once per process, so the non-default ones run in a child process."""
+    the three implementations of the C = 64 / 64-token layer (tcgen05 projections = default, 8-warp mma.sync,
+    16-warp mma.sync).  The library reads the switch once per process, so the non-default ones run in a child process."""
     if impl != "default":
         if not (window == (4, 4, 4) and C == 64):
             pytest.skip("alternative implementations exist for C = 64 / (4,4,4) only")
