@@ -40,7 +40,10 @@ struct GemmDev {
   float* gn_part;
   // halo kernel (k x k 'same' convolutions whose 128-row tile is bh full-width rows of one frame)
   int kh, kw, stages, a_ext_bytes;
-  int dbg;   // profiling experiments only (EXTDM_GEMM_DBG): 1 = no epilogue stores, 2 = no MMA issue, 4 = no TMA loads
+  int prefetch;   // L2 prefetch of the tile two ahead (helps the multi-block shapes, measured per shape)
+  int dbg;   // profiling experiments only (EXTDM_GEMM_DBG): 1 = no epilogue stores, 2 = no MMA issue, 4 = no TMA loads,
+             // 8 = no tcgen05.ld, 16 = no GroupNorm partial reduction, 32 = plain arrives instead of tcgen05.commit,
+             // 64 = invert the L2-prefetch decision
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -295,7 +298,7 @@ __device__ __forceinline__ void epilogue_loop(const GemmDev& p, uint64_t* acc_fu
 // 16-column chunks round-robin (ncu: with a single epilogue warp per scheduler the ~900 dependent instructions per
 // tile issue at one per ~5 cycles and the epilogue, not the tensor pipe or L2, bounds the kernel).
 // bias (+ activation) -> bf16 rows; optional GroupNorm(8) partial sums of the stored values.
-template <int BN, bool GN, int EPW>
+template <int BN, bool GN, int EPW, int NACC = 2>
 __device__ __forceinline__ void epilogue_simple(const GemmDev& p, uint64_t* acc_full, uint64_t* acc_empty, float* s_gn,
                                                 uint32_t tmem_base, int warp, int lane) {
   constexpr uint32_t kAccCols = BN < 32 ? 32 : BN;
@@ -303,7 +306,7 @@ __device__ __forceinline__ void epilogue_simple(const GemmDev& p, uint64_t* acc_
   // The EPW warps of a TMEM lane quarter form two groups: group 0 drains the even tiles of this CTA (accumulator
   // stage 0), group 1 the odd ones (stage 1), so the per-tile latency chain of one group (barrier wake-up, tcgen05.ld,
   // stores) overlaps the other group's tile.  Within a group the warps take the 16-column chunks round-robin.
-  constexpr int kGroups = EPW >= 2 ? 2 : 1;
+  constexpr int kGroups = EPW >= NACC ? NACC : (EPW >= 2 ? 2 : 1);   // NACC accumulator stages -> NACC tile groups
   constexpr int kWpg = EPW / kGroups;      // warps per (quarter, group)
   constexpr int kGThreads = 128 * kWpg;    // threads per group
   const int q = warp & 3;                  // TMEM lane quarter
@@ -320,9 +323,9 @@ __device__ __forceinline__ void epilogue_simple(const GemmDev& p, uint64_t* acc_
   int staged_n0 = -1;
   int local = 0;
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
-    if (kGroups == 2 && (local & 1) != grp) continue;
-    const int as = local & 1;
-    const uint32_t aphase = (local >> 1) & 1;
+    if (kGroups > 1 && (local % kGroups) != grp) continue;
+    const int as = local % NACC;
+    const uint32_t aphase = (local / NACC) & 1;
     const TileCoord tc = decode_tile(p, tile, BN);
     const int n0 = tc.n0;
     const int g1 = tc.c1 + i1, g2 = tc.c2 + i2, g3 = tc.c3 + i3, g4 = tc.c4 + i4;
@@ -342,8 +345,13 @@ __device__ __forceinline__ void epilogue_simple(const GemmDev& p, uint64_t* acc_
 #pragma unroll 1
     for (int ch = eg; ch < kChunks; ch += kWpg) {
       uint32_t raw[16];
-      tmem_ld16(taddr + ch * 16, raw);
-      tmem_ld_wait();
+      if (p.dbg & 8) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) raw[j] = 0u;
+      } else {
+        tmem_ld16(taddr + ch * 16, raw);
+        tmem_ld_wait();
+      }
       float gst[4] = {0.f, 0.f, 0.f, 0.f};
       if (row_ok && n0 + ch * 16 < p.n) {
         float v[16];
@@ -373,7 +381,7 @@ __device__ __forceinline__ void epilogue_simple(const GemmDev& p, uint64_t* acc_
           }
         }
       }
-      if (GN) {
+      if (GN && !(p.dbg & 16)) {
         // 4 values per thread -> warp totals (fixed-order butterfly); lanes 0, 8, 16, 24 hold value (lane >> 3) of
         // {sum lo8, sum hi8, sq lo8, sq hi8}.  Every warp publishes its own partial record slots straight to global
         // memory -- record (tile, lane quarter[, chunk parity for BN = 256]) of 16 floats = 8 group sums + 8 group sums
@@ -477,8 +485,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile, BN);
-        // L2 prefetch of the (un-shifted) A tile this CTA will need two tiles from now
-        if (tc.n0 == 0 && tile + 2 * gridDim.x < p.total_tiles) {
+        // optional L2 prefetch of the (un-shifted) A tile this CTA will need two tiles from now (GemmDev.prefetch)
+        if (p.prefetch && tc.n0 == 0 && tile + 2 * gridDim.x < p.total_tiles) {
           const TileCoord tf = decode_tile(p, tile + 2 * gridDim.x, BN);
           const int o3 = p.tap[p.ntaps / 2][2];
           if (elect_one()) {
@@ -581,7 +589,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                  const __grid_constant__ CUtensorMap map_b, const __grid_constant__ GemmDev p) {
   constexpr int kBTileBytes = BN * kBlockK * 2;
   constexpr uint32_t kAccCols = BN < 32 ? 32 : BN;
-  constexpr uint32_t kTmemCols = 2 * kAccCols;
+  // accumulator stages: the accumulator hand-off (commit -> epilogue wake-up -> drain -> arrive -> MMA wake-up) is a
+  // ~2.5 us latency chain per tile; four stages with one epilogue group each keep four tiles in flight
+  constexpr int kAcc = SIMPLE ? (BN <= 64 ? 4 : (BN <= 128 ? 4 : 2)) : 2;
+  constexpr uint32_t kTmemCols = kAcc * kAccCols;
+  static_assert(kTmemCols <= 512, "TMEM budget");
   constexpr int kMaxStages = 8;
 
   extern __shared__ uint8_t smem_raw[];
@@ -595,8 +607,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_stage + p.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* acc_full = empty_bar + kMaxStages;
-  uint64_t* acc_empty = acc_full + 2;
-  uint64_t* resb_bar = acc_empty + 2;
+  uint64_t* acc_empty = acc_full + 4;
+  uint64_t* resb_bar = acc_empty + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resb_bar + 2);      // keeps s_gn / s_bias 16-byte aligned
   float* s_gn = reinterpret_cast<float*>(tmem_slot + 4);
 
@@ -611,9 +623,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kAcc; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], SIMPLE ? 4 * (kHaloEpw / 2) : 4);
+      mbar_init(&acc_empty[s], SIMPLE ? 4 * (kHaloEpw / kAcc) : 4);
     }
     mbar_init(resb_bar, 1);
     fence_barrier_init();
@@ -641,9 +653,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile, BN);
-        // L2 prefetch of the rows this CTA will need two tiles from now (centre kernel column covers all but one
-        // pixel column of the other two boxes)
-        if (tile + 2 * gridDim.x < p.total_tiles) {
+        // optional L2 prefetch of the rows this CTA will need two tiles from now (GemmDev.prefetch)
+        if (p.prefetch && tile + 2 * gridDim.x < p.total_tiles) {
           const TileCoord tf = decode_tile(p, tile + 2 * gridDim.x, BN);
           if (elect_one()) {
             for (int kc = 0; kc < nk; ++kc) {
@@ -694,8 +705,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
       uint32_t phase = 0;
       int local = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
-        const int as = local & 1;
-        const uint32_t aphase = (local >> 1) & 1;
+        const int as = local % kAcc;
+        const uint32_t aphase = (local / kAcc) & 1;
         mbar_wait(&acc_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_u + as * kAccCols;
@@ -718,19 +729,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                   acc = 1;
                 }
               }
-              umma_commit(&empty_bar[stage]);
+              if (p.dbg & 32) mbar_arrive(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
             }
             accumulate = 1;
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
-        if (elect_one()) umma_commit(&acc_full[as]);
+        if (elect_one()) { if (p.dbg & 32) mbar_arrive(&acc_full[as]); else umma_commit(&acc_full[as]); }
       }
     }
     __syncwarp();
   } else {
     if constexpr (SIMPLE)
-      epilogue_simple<BN, GN, kHaloEpw>(p, acc_full, acc_empty, s_gn, tmem_base, warp, lane);
+      epilogue_simple<BN, GN, kHaloEpw, kAcc>(p, acc_full, acc_empty, s_gn, tmem_base, warp, lane);
     else
       epilogue_loop<BN, GN, false>(p, acc_full, acc_empty, s_gn, tmem_base, warp, lane);
   }
@@ -904,6 +915,9 @@ extern "C" int extdm_conv_gemm(const ExtdmGemm* g, void* stream_) {
   dev.gn_part = g->gn_partials;
   static const int dbg_flags = getenv("EXTDM_GEMM_DBG") ? atoi(getenv("EXTDM_GEMM_DBG")) : 0;
   dev.dbg = dbg_flags;
+  // measured on B200 (profiles/kernel_table_r1.md): the prefetch pays when a tile streams two or more 64-channel blocks
+  // (7x7 init_conv 9.9 -> 9.0 ms per round, two-source 3x3 5.8 -> 5.0 ms), not for single-block shapes
+  dev.prefetch = ((dev.nk0 + dev.nk1 >= 2) ? 1 : 0) ^ ((dbg_flags & 64) ? 1 : 0);
   if ((g->col_scale == nullptr) != (g->col_shift == nullptr)) {
     extdm_set_error("extdm_conv_gemm: col_scale and col_shift go together", __FILE__, __LINE__);
     return EXTDM_ERR_ARG;
@@ -925,11 +939,11 @@ extern "C" int extdm_conv_gemm(const ExtdmGemm* g, void* stream_) {
   const bool simple = !g->res && !g->col_scale && !g->out_fp32 && g->col_group >= g->n && g->n % 16 == 0;
   static const bool halo_off = getenv("EXTDM_NO_HALO") != nullptr;
   static const bool halo7_off = getenv("EXTDM_NO_HALO7") != nullptr;
-  // measured on B200: with a single 64-channel block per tap the plain kernel at two CTAs per
-  // SM is ~8% faster (113 vs 122 us on the level-0 3x3), with two or more blocks the halo kernel wins
+  // measured on B200: the halo kernel wins on every 3x3 / 7x7 shape it supports
+  // (level-0 3x3: 96 vs 115 us; two sources: 160 vs 171 us; 7x7: 0.92 vs 1.12 ms)
   static const bool halo_all = getenv("EXTDM_HALO_ALL") != nullptr;
   bool halo = kk && (simple || kk == 7) && !halo_off && !(kk == 7 && halo7_off) &&
-              (halo_all || dev.nk0 + dev.nk1 >= 2) && g->box[2] == 1 && g->box[3] == 1 && g->box[0] % 8 == 0 &&
+              (halo_all || kk == 3 || dev.nk0 + dev.nk1 >= 2) && g->box[2] == 1 && g->box[3] == 1 && g->box[0] % 8 == 0 &&
               (bn == 64 || bn == 128);
   int ebox[4] = {g->box[0], g->box[1] + kk - 1, 1, 1};
   bool resb = false;
@@ -946,6 +960,7 @@ extern "C" int extdm_conv_gemm(const ExtdmGemm* g, void* stream_) {
     } else {
       stages = kSmemBudget / (a_ext + kk * btile);
     }
+    const long long per_kx = a_ext + (resb ? 0 : kk * btile);
     if (stages > 8) stages = 8;
     if (stages < 2) {
       halo = false;
@@ -953,8 +968,8 @@ extern "C" int extdm_conv_gemm(const ExtdmGemm* g, void* stream_) {
       dev.kh = dev.kw = kk;
       dev.stages = stages;
       dev.a_ext_bytes = a_ext;
-      halo_smem = static_cast<int>((resb ? resb_bytes : 0) + static_cast<long long>(stages) * (a_ext + (resb ? 0 : kk * btile))) +
-                  (2 * 8 + 6) * 8 + 16 + 4096 + 1024;
+      halo_smem = static_cast<int>((resb ? resb_bytes : 0) + static_cast<long long>(stages) * per_kx) +
+                  (2 * 8 + 10) * 8 + 16 + 4096 + 1024;
     }
   }
 
