@@ -69,7 +69,9 @@ class FlowDiffusion(nn.Module):
             # the reference silently constructs NotImplementedError() and then dies with a NameError
             # (VideoFlowDiffusion_multi_w_ref.py:71-80); fail with a message instead
             raise NotImplementedError(f"unknown Unet3D architecture {Unet3D_architecture!r}")
-        base = UNET_ARCHITECTURES[Unet3D_architecture] == "base"
+        # base and ada_u22 feed the 3-channel flow volume to init_conv directly (VideoFlowDiffusion_multi1248.py:72,
+        # VideoFlowDiffusion_multi_w_ref_u22.py:199-201); the others go through init_noise_conv (3 -> 256) first
+        base = UNET_ARCHITECTURES[Unet3D_architecture] in ("base", "u22")
         self.unet = Unet3D(dim=64, channels=3 + 256 if base else 256 + 256, out_grid_dim=2, out_conf_dim=1,
                            dim_mults=dim_mults, use_bert_text_cond=False, learn_null_cond=learn_null_cond,
                            use_final_activation=False, use_deconv=use_deconv, padding_mode=padding_mode,
@@ -175,6 +177,18 @@ class FlowDiffusionMulti1248(FlowDiffusion):
     WRAPPER = "multi1248"
 
 
+class FlowDiffusionU22(FlowDiffusion):
+    """VideoFlowDiffusion_multi_w_ref_u22.py:142-236,415-510: the w_ref pipeline around the ada_u22 UNet.  The
+    reference spreads LFAE and DM over `device_ids` (model parallel, one video batch at a time); here the whole
+    round runs on one GPU and videos shard across ranks (sharding.py), so `device_ids` is accepted and ignored."""
+
+    def __init__(self, config="", pretrained_pth="", is_train=True, ddim_sampling_eta=1.0, timesteps=1000,
+                 dim_mults=(1, 2, 4, 4), learn_null_cond=False, use_deconv=True, padding_mode="zeros", withFea=True,
+                 Unet3D_architecture="DenoiseNet_STWAtt_w_w_ref_adaptor_cross_multi_traj_ada_u22", device_ids=None):
+        super().__init__(config, pretrained_pth, is_train, ddim_sampling_eta, timesteps, dim_mults, learn_null_cond,
+                         use_deconv, padding_mode, withFea, Unet3D_architecture)
+
+
 class FlowDiffusionMulti(FlowDiffusion):
     WRAPPER = "multi"
 
@@ -183,12 +197,12 @@ WRAPPERS = {
     "VideoFlowDiffusion_multi_w_ref": FlowDiffusion,
     "VideoFlowDiffusion_multi1248": FlowDiffusionMulti1248,
     "VideoFlowDiffusion_multi": FlowDiffusionMulti,
+    "VideoFlowDiffusion_multi_w_ref_u22": FlowDiffusionU22,
 }
 
 
 def flow_diffusion_class(dm_arch):
     """`--DM_arch` string (scripts/DM/valid.py:83-92) -> class."""
     if dm_arch not in WRAPPERS:
-        raise NotImplementedError(f"DM architecture {dm_arch!r}: VideoFlowDiffusion_multi_w_ref_u22 is inconsistent "
-                                  "in the reference (SURVEY.md App. E1) and is not provided")
+        raise NotImplementedError(f"unknown DM architecture {dm_arch!r}")
     return WRAPPERS[dm_arch]

@@ -12,6 +12,7 @@ UNET_ARCHITECTURES = {
     "DenoiseNet_STWAtt_w_w_ref_adaptor_cross_multi_traj_u12": "u12",
     "DenoiseNet_STWAtt_w_w_ref_adaptor_cross_multi_traj_u22": "u12",   # byte-identical file in the reference
     "DenoiseNet_STWAtt_w_wo_ref_adaptor_cross_multi": "base",
+    "DenoiseNet_STWAtt_w_w_ref_adaptor_cross_multi_traj_ada_u22": "u22",
 }
 
 SCHEDULE_KEYS = (
@@ -31,18 +32,24 @@ class UnetConfig:
     """Hyper-parameters of one Unet3D variant."""
 
     def __init__(self, variant, tc, tp, dim=64, dim_mults=(1, 2, 4, 4), channels=None, heads=8, groups=8):
-        if variant not in ("ada", "u12", "base"):
+        if variant not in ("ada", "u12", "base", "u22"):
             raise ValueError(f"unknown Unet3D variant {variant!r}")
         self.variant, self.tc, self.tp = variant, int(tc), int(tp)
         self.tm = self.tc - 1 if variant == "base" else self.tc
         self.T = self.tm + self.tp
         self.dim, self.dim_mults = int(dim), tuple(dim_mults)
         self.heads, self.groups = heads, groups
-        self.window = (4, 4, 4) if variant == "ada" else (2, 4, 4)
+        # ..._traj_ada.py:872-877 (4,4,4)/16; ..._traj_ada_u22.py:1016-1021 (4,4,4)/32; the others (2,4,4)/32
+        self.window = (4, 4, 4) if variant in ("ada", "u22") else (2, 4, 4)
         self.dim_head = 16 if variant == "ada" else 32
         self.hidden = self.heads * self.dim_head
         self.shift = tuple(w // 2 for w in self.window)
-        self.channels = channels if channels is not None else (3 + 256 if variant == "base" else 512)
+        # base and ada_u22 feed the 3-channel flow volume to init_conv directly (no init_noise_conv in their forward)
+        self.channels = channels if channels is not None else (3 + 256 if variant in ("base", "u22") else 512)
+        # ada_u22: a MotionAdaptor and a temporal attention at every level, 3x3x3 extrapolators, blocks re-ordered
+        self.per_level_temporal = variant == "u22"
+        self.extrap_kt = 3 if variant == "u22" else 1
+        self.resample_slot = 6 if variant == "u22" else 5   # index of Downsample / Upsample in a stage's ModuleList
         self.levels = [self.dim * m for m in self.dim_mults]
         self.L, self.n_extra = adaptor_layers(self.tm, self.tp)
 
@@ -93,7 +100,7 @@ def unet_manifest(cfg):
         m[f"{p}.adaptors.predictor.fn.fn.bias"] = (C,)
         m[f"{p}.adaptors.predictor.fn.norm.gamma"] = (1, C, 1, 1, 1)
         for i in range(cfg.L):
-            m[f"{p}.adaptors.extrapolators.{i}.fn.weight"] = (C, C, 1, 3, 3)
+            m[f"{p}.adaptors.extrapolators.{i}.fn.weight"] = (C, C, cfg.extrap_kt, 3, 3)
         m[f"{p}.Tmodulator.weight"] = (C * cfg.tp, C * cfg.n_extra, 1, 1)
         m[f"{p}.Tmodulator.bias"] = (C * cfg.tp,)
         m[f"{p}.fuser.fn.weight"] = (C, 2 * C, 1, 1, 1)
@@ -104,12 +111,17 @@ def unet_manifest(cfg):
     m["init_conv.weight"] = (d, cfg.channels, 1, 7, 7)
     m["init_conv.bias"] = (d,)
     temporal("init_temporal_attn", d)
-    if cfg.variant != "base":
+    if cfg.variant != "base":                             # constructed (and checkpointed) but unused by ada_u22
         m["init_noise_conv.weight"] = (256, 3, 1, 7, 7)
         m["init_noise_conv.bias"] = (256,)
-    if cfg.variant == "ada":
+    if cfg.variant in ("ada", "u22"):
         temporal("cond_temporal_attn", 256)
         adaptor("cond_adaptor", 256)
+    if cfg.variant == "u22":
+        # used by forward(path=1) only; the sampler calls path=0 (..._traj_ada_u22.py:1048,1123-1124,1181-1210)
+        m["rel_pos_bias_thw.relative_attention_bias.weight"] = (32, heads)
+        m["alpha"] = (heads,)
+        m["beta"] = (heads,)
     if cfg.variant == "u12":
         adaptor("init_adaptor", 256)                      # constructed but unused by the reference forward
         for n in ("q", "k", "v", "o"):
@@ -125,17 +137,21 @@ def unet_manifest(cfg):
     dims = [d] + cfg.levels
     in_out = list(zip(dims[:-1], dims[1:]))
     nres = len(in_out)
+    u22 = cfg.variant == "u22"
+    rs = cfg.resample_slot
     for i, (ci, co) in enumerate(in_out):
         p = f"downs.{i}"
         res(f"{p}.0", ci, co)
         stw(f"{p}.1", co)
         res(f"{p}.2", co, co)
         stw(f"{p}.3", co)
-        if i > 1:
+        if i > 1 or u22:
             adaptor(f"{p}.4", co)
+        if u22:
+            temporal(f"{p}.5", co)
         if i < nres - 1:
-            m[f"{p}.5.weight"] = (co, co, 1, 4, 4)
-            m[f"{p}.5.bias"] = (co,)
+            m[f"{p}.{rs}.weight"] = (co, co, 1, 4, 4)
+            m[f"{p}.{rs}.bias"] = (co,)
     mid = dims[-1]
     res("mid_block1", mid, mid)
     stw("mid_attn1", mid)
@@ -150,9 +166,11 @@ def unet_manifest(cfg):
         stw(f"{p}.3", ci)
         if i > 1:
             adaptor(f"{p}.4", ci)
+        if u22:
+            temporal(f"{p}.5", ci)
         if i < nres - 1:
-            m[f"{p}.5.weight"] = (ci, ci, 1, 4, 4)
-            m[f"{p}.5.bias"] = (ci,)
+            m[f"{p}.{rs}.weight"] = (ci, ci, 1, 4, 4)
+            m[f"{p}.{rs}.bias"] = (ci,)
     for head, oc in (("final_conv", 2), ("occlusion_map", 1)):
         res(f"{head}.0", 2 * d, d, time=False)
         m[f"{head}.1.weight"] = (oc, d, 1, 1, 1)

@@ -84,6 +84,12 @@ def pack_conv_weight(w):
     return w.permute(0, 2, 3, 1).reshape(co, kh * kw * ci).to(BF16).contiguous()
 
 
+def pack_conv3d_weight(w):
+    """(Cout, Cin, kt, kh, kw) fp32 -> (Cout, kt*kh*kw*Cin) bf16, K index = ((kt*kh + ky)*kw + kx)*Cin + ci."""
+    co, ci, kt, kh, kw = w.shape
+    return w.permute(0, 2, 3, 4, 1).reshape(co, kt * kh * kw * ci).to(BF16).contiguous()
+
+
 def pack_linear_weight(w):
     return w.reshape(w.shape[0], -1).to(BF16).contiguous()
 
@@ -118,6 +124,10 @@ def pack_upsample_weight(w):
 
 def conv_taps(k):
     return [(kx - k // 2, ky - k // 2, 0) for ky in range(k) for kx in range(k)]
+
+
+def conv3d_taps(k):
+    return [(kx - k // 2, ky - k // 2, kt - k // 2) for kt in range(k) for ky in range(k) for kx in range(k)]
 
 
 def std_box(H, W):

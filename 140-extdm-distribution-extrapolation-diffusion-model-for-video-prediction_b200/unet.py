@@ -62,10 +62,12 @@ class PackedUnet:
                 self.f32[k] = t.reshape(t.shape[0], -1).contiguous()
             elif k.endswith((".bias", ".gamma", "norm.weight")):
                 self.f32[k] = t.reshape(-1).contiguous()
-            elif k.startswith("downs.") and k.endswith(".5.weight"):
+            elif k.startswith("downs.") and k.endswith(f".{cfg.resample_slot}.weight"):
                 self.w[k] = ops.pack_downsample_weight(t)
-            elif k.startswith("ups.") and k.endswith(".5.weight"):
+            elif k.startswith("ups.") and k.endswith(f".{cfg.resample_slot}.weight"):
                 self.w[k] = ops.pack_upsample_weight(t)
+            elif t.dim() == 5 and t.shape[2] == 3:
+                self.w[k] = ops.pack_conv3d_weight(t)
             elif t.dim() == 5:
                 self.w[k] = ops.pack_conv_weight(t)
             else:
@@ -77,7 +79,7 @@ class PackedUnet:
             out[:, :147] = w3[:, :, 0].permute(0, 2, 3, 1).reshape(n, 147).to(BF16)
             return out
         ic = self.f32["init_conv.weight"]
-        if cfg.variant == "base":
+        if cfg.variant in ("base", "u22"):
             self.w["init_flow"] = pack7(ic[:, :3])
             self.w["init_fea"] = ops.pack_conv_weight(ic[:, 3:])
         elif cfg.variant == "u12":
@@ -272,8 +274,11 @@ class UnetRunner:
             nh = self.buf(B, n_i, H, W, C)
             ms = self.buf(2, B, C, dtype=torch.float32)
             ops.adaptor_normalize(rec, E, n_i, nh, ms, ws)
+            # ada_u22's extrapolators are 3x3x3 (zero padding along T as well): 27 taps, the frame offsets are
+            # coordinate offsets of the same TMA loads and out-of-range frames read as zeros
             ops.conv_cl(rec, nh, pk.w[p + f".adaptors.extrapolators.{i}.fn.weight"], C, 3, E, out_t_offset=n_i,
-                        res=nh, col_scale=ms[1], col_shift=ms[0])
+                        res=nh, col_scale=ms[1], col_shift=ms[0],
+                        taps=ops.conv3d_taps(3) if cfg.extrap_kt == 3 else None)
         m1 = self.buf(B, tp, H, W, C)
         if hw >= 128:
             box, cnt = (128, 1, 1, 1), (hw, 1, 1, B)
@@ -312,7 +317,26 @@ class UnetRunner:
             ops.conv_cl(rec, x, wm, C, 0, y, bias=pk.f32[p + ".bias"], taps=taps, out_scale=2, out_phase=(py, px))
         return y
 
+    def _stage_u22(self, rec, x, p, cout, has_adaptor, x2=None):
+        """..._traj_ada_u22.py:1268-1279: block1, block2, STW (shifted), STW, adaptor, temporal attention."""
+        x = self._resblock(rec, x, p + ".0", cout, x2=x2)
+        self.taps[p + ".0"] = x
+        x = self._resblock(rec, x, p + ".2", cout)
+        self.taps[p + ".2"] = x
+        x = self._stw(rec, x, p + ".1", True)
+        self.taps[p + ".1"] = x
+        x = self._stw(rec, x, p + ".3", False)
+        self.taps[p + ".3"] = x
+        if has_adaptor:
+            x = self._adaptor(rec, x, p + ".4")
+            self.taps[p + ".4"] = x
+        x = self._temporal(rec, x, p + ".5")
+        self.taps[p + ".5"] = x
+        return x
+
     def _stage(self, rec, x, p, cout, has_adaptor, x2=None):
+        if self.cfg.variant == "u22":
+            return self._stage_u22(rec, x, p, cout, has_adaptor, x2=x2)
         x = self._res_stw(rec, x, p + ".0", p + ".1", cout, True, x2=x2)
         x = self._res_stw(rec, x, p + ".2", p + ".3", cout, False)
         if has_adaptor:
@@ -334,7 +358,7 @@ class UnetRunner:
         ops.ncthw_to_cl(pro, self.cond_fea, cf)
         if cfg.variant == "u12":
             return self._build_u12_front(cf)
-        if cfg.variant == "ada":
+        if cfg.variant in ("ada", "u22"):
             cf = self._adaptor(pro, cf, "cond_adaptor")
             cf = self._temporal(pro, cf, "cond_temporal_attn")
         if fh != H:
@@ -349,7 +373,7 @@ class UnetRunner:
         x0 = self.buf(B, T, H, W, d)
         a_c = self.buf(B * tm * hw, 192)
         a_p = self.buf(B * tp * hw, 192)
-        if cfg.variant == "base":
+        if cfg.variant in ("base", "u22"):
             # init_conv on [flow(3) | cond_fea(256)] channels = im2col GEMM on the flow part + hoisted h0
             ops.im2col7_flow(pro, self.cond_frames, self.x, a_c, 0, tm)
             self._im2col_gemm(pro, a_c, pk.w["init_flow"], d, x0, 0, tm, res=h0)
@@ -430,19 +454,25 @@ class UnetRunner:
         levels = cfg.levels
         nres = len(levels)
         skips = []
+        u22, rs = cfg.variant == "u22", cfg.resample_slot
         for i, co in enumerate(levels):
             p = f"downs.{i}"
-            x = self._stage(st, x, p, co, i > 1)
+            x = self._stage(st, x, p, co, i > 1 or u22)
             skips.append(x)
             if i < nres - 1:
-                x = self._downsample(st, x, p + ".5")
-                self.taps[p + ".5"] = x
+                x = self._downsample(st, x, f"{p}.{rs}")
+                self.taps[f"{p}.{rs}"] = x
         mid = levels[-1]
         x = self._resblock(st, x, "mid_block1", mid)
         x = self._stw(st, x, "mid_attn1", True)
-        x = self._resblock(st, x, "mid_block2", mid)
-        x = self._stw(st, x, "mid_attn2", False)
-        x = self._adaptor(st, x, "mid_adaptor")
+        if u22:                                            # ..._traj_ada_u22.py:1283-1287
+            x = self._stw(st, x, "mid_attn2", False)
+            x = self._adaptor(st, x, "mid_adaptor")
+            x = self._resblock(st, x, "mid_block2", mid)
+        else:
+            x = self._resblock(st, x, "mid_block2", mid)
+            x = self._stw(st, x, "mid_attn2", False)
+            x = self._adaptor(st, x, "mid_adaptor")
         self.taps["mid"] = x
         dims = [d] + levels
         in_out = list(zip(dims[:-1], dims[1:]))
@@ -450,8 +480,8 @@ class UnetRunner:
             p = f"ups.{i}"
             x = self._stage(st, x, p, ci, i > 1, x2=skips.pop())
             if i < nres - 1:
-                x = self._upsample(st, x, p + ".5")
-                self.taps[p + ".5"] = x
+                x = self._upsample(st, x, f"{p}.{rs}")
+                self.taps[f"{p}.{rs}"] = x
         if cfg.groups == 8 and d in (64, 128, 256):
             # the heads' last GroupNorm + SiLU + residual run inside the projection kernel, on the tp frames only
             h2f, rf, pf, npart = self._resblock(st, x, "final_conv.0", d, x2=x0, time=False, defer_norm2=True)

@@ -44,9 +44,12 @@ class SD:
 
 # ----------------------------------------------------------------------------- UNet config
 def unet_config(variant, tc, tp, dim=64, dim_mults=(1, 2, 4, 4)):
-    """variant: 'ada' (KTH/UCF/City), 'u12' (BAIR), 'base' (SMMNIST).  App. A of SURVEY.md."""
+    """variant: 'ada' (KTH/UCF/City), 'u12' (BAIR), 'base' (SMMNIST), 'u22' (ada_u22, the shipped Cityscapes
+    pairing).  App. A of SURVEY.md."""
     if variant == "ada":
         window, dim_head = (4, 4, 4), 16          # ..._traj_ada.py:872-877
+    elif variant == "u22":
+        window, dim_head = (4, 4, 4), 32          # ..._traj_ada_u22.py:1016-1021
     elif variant in ("u12", "base"):
         window, dim_head = (2, 4, 4), 32          # ..._traj_u12.py:871-876, ...cross_multi.py:762-767
     else:
@@ -239,7 +242,8 @@ def motion_adaptor(x, sd, tm, tp):
         std = (flat.var(dim=2) + 1e-5).sqrt()[:, :, None, None, None]       # unbiased
         mean = flat.mean(dim=2)[:, :, None, None, None]
         nh = (cur - mean) / std
-        nh = nh + F.conv3d(nh, ad[f"extrapolators.{i}.fn.weight"], None, padding=(0, 1, 1))
+        wx = ad[f"extrapolators.{i}.fn.weight"]   # (1,3,3) kernels; ada_u22 uses 3x3x3, padding 1 (..._ada_u22.py:793)
+        nh = nh + F.conv3d(nh, wx, None, padding=(wx.shape[2] // 2, 1, 1))
         cur = torch.cat([cur, nh * std + mean], dim=2)
     ext = cur[:, :, tm:]                                                     # (2^L-1)*tm frames
     n, _, Te, h, w = ext.shape
@@ -304,7 +308,7 @@ def _resize_frames(cf, out_hw):
 
 
 def unet_forward(sd, cfg, x, time, cond_frames, cond_fea, taps=None):
-    """Unet3D.forward for the three working variants.  `sd` is an SD view at the UNet root
+    """Unet3D.forward for the working variants ('u22' = ..._traj_ada_u22.py:1172-1310 with path=0).  `sd` is an SD view at the UNet root
     (prefix 'denoise_fn.' inside a diffusion state_dict).  `taps`: optional dict that receives
     intermediate tensors for layer-by-layer parity tests."""
     v, tc, tp, tm = cfg["variant"], cfg["tc"], cfg["tp"], cfg["tm"]
@@ -318,7 +322,12 @@ def unet_forward(sd, cfg, x, time, cond_frames, cond_fea, taps=None):
 
     x = torch.cat([cond_frames[:, :, :tm], x], dim=2)
     pos_bias = t5_bucket_bias(sd["time_rel_pos_bias.relative_attention_bias.weight"], tm + tp)
-    if v != "base":
+    if v == "u22":
+        # no init_noise_conv in this forward: [flow(3) | adapted cond_fea(256)] -> init_conv
+        cf = unet_cond_features(sd, cfg, cond_fea, pos_bias, x.shape[-2:])
+        tap("cond_up", cf)
+        x = torch.cat([x, cf], dim=1)
+    elif v != "base":
         x = F.conv3d(x, sd["init_noise_conv.weight"], sd["init_noise_conv.bias"], padding=(0, 3, 3))
         tap("init_noise_conv", x)
         if v == "ada":
@@ -340,8 +349,29 @@ def unet_forward(sd, cfg, x, time, cond_frames, cond_fea, taps=None):
 
     n_lvl = len(cfg["dim_mults"])
     skips = []
+    rs = "6" if v == "u22" else "5"                 # Downsample / Upsample slot inside a stage's ModuleList
+
+    def stage_u22(x, s, name):
+        # ..._traj_ada_u22.py:1268-1279 / :1290-1301: both ResnetBlocks first, then both STW layers, the adaptor
+        # (every down level, up levels > 1) and a per-level temporal attention
+        x = resnet_block(x, s.sub("0"), groups, t)
+        tap(name + ".0", x)
+        x = resnet_block(x, s.sub("2"), groups, t)
+        tap(name + ".2", x)
+        x = stw_attention(x, s.sub("1"), window, shift, heads, dh)
+        tap(name + ".1", x)
+        x = stw_attention(x, s.sub("3"), window, (0, 0, 0), heads, dh)
+        tap(name + ".3", x)
+        if s.has("4.Tmodulator.weight"):
+            x = motion_adaptor(x, s.sub("4"), tm, tp)
+            tap(name + ".4", x)
+        x = temporal_attention(x, s.sub("5"), pos_bias, heads, dh)
+        tap(name + ".5", x)
+        return x
 
     def stage(x, s, name):
+        if v == "u22":
+            return stage_u22(x, s, name)
         x = resnet_block(x, s.sub("0"), groups, t)
         tap(name + ".0", x)
         x = stw_attention(x, s.sub("1"), window, shift, heads, dh)
@@ -359,24 +389,29 @@ def unet_forward(sd, cfg, x, time, cond_frames, cond_fea, taps=None):
         s = sd.sub(f"downs.{i}")
         x = stage(x, s, f"downs.{i}")
         skips.append(x)
-        if s.has("5.weight"):
-            x = F.conv3d(x, s["5.weight"], s["5.bias"], stride=(1, 2, 2), padding=(0, 1, 1))
-            tap(f"downs.{i}.5", x)
+        if s.has(rs + ".weight"):
+            x = F.conv3d(x, s[rs + ".weight"], s[rs + ".bias"], stride=(1, 2, 2), padding=(0, 1, 1))
+            tap(f"downs.{i}.{rs}", x)
 
     x = resnet_block(x, sd.sub("mid_block1"), groups, t)
     x = stw_attention(x, sd.sub("mid_attn1"), window, shift, heads, dh)
-    x = resnet_block(x, sd.sub("mid_block2"), groups, t)
-    x = stw_attention(x, sd.sub("mid_attn2"), window, (0, 0, 0), heads, dh)
-    x = motion_adaptor(x, sd.sub("mid_adaptor"), tm, tp)
+    if v == "u22":                                  # ..._traj_ada_u22.py:1283-1287: attn1, attn2, adaptor, block2
+        x = stw_attention(x, sd.sub("mid_attn2"), window, (0, 0, 0), heads, dh)
+        x = motion_adaptor(x, sd.sub("mid_adaptor"), tm, tp)
+        x = resnet_block(x, sd.sub("mid_block2"), groups, t)
+    else:
+        x = resnet_block(x, sd.sub("mid_block2"), groups, t)
+        x = stw_attention(x, sd.sub("mid_attn2"), window, (0, 0, 0), heads, dh)
+        x = motion_adaptor(x, sd.sub("mid_adaptor"), tm, tp)
     tap("mid", x)
 
     for i in range(n_lvl):
         s = sd.sub(f"ups.{i}")
         x = torch.cat((x, skips.pop()), dim=1)
         x = stage(x, s, f"ups.{i}")
-        if s.has("5.weight"):
-            x = F.conv_transpose3d(x, s["5.weight"], s["5.bias"], stride=(1, 2, 2), padding=(0, 1, 1))
-            tap(f"ups.{i}.5", x)
+        if s.has(rs + ".weight"):
+            x = F.conv_transpose3d(x, s[rs + ".weight"], s[rs + ".bias"], stride=(1, 2, 2), padding=(0, 1, 1))
+            tap(f"ups.{i}.{rs}", x)
 
     x = torch.cat((x, r), dim=1)
 

@@ -27,6 +27,7 @@ UNET_MODULES = {
     "ada": "DenoiseNet_STWAtt_w_w_ref_adaptor_cross_multi_traj_ada",
     "u12": "DenoiseNet_STWAtt_w_w_ref_adaptor_cross_multi_traj_u12",
     "base": "DenoiseNet_STWAtt_w_wo_ref_adaptor_cross_multi",
+    "u22": "DenoiseNet_STWAtt_w_w_ref_adaptor_cross_multi_traj_ada_u22",
 }
 
 UNET_CASES = {
@@ -34,6 +35,7 @@ UNET_CASES = {
     "unet_ada_c2p5": ("ada", 2, 5, (1, 2, 4, 4), 1),
     "unet_u12_c2p3": ("u12", 2, 3, (1, 2, 4, 4), 1),
     "unet_base_c3p2": ("base", 3, 2, (1, 2, 4, 8), 1),
+    "unet_u22_c2p5": ("u22", 2, 5, (1, 2, 4, 4), 1),
 }
 
 
@@ -54,7 +56,9 @@ def unet_inputs(variant, tc, tp, B, seed):
 
 def build_ref_unet(variant, tc, tp, dim_mults):
     mod = importlib.import_module("model.BaseDM_adaptor." + UNET_MODULES[variant])
-    channels = 3 + 256 if variant == "base" else 512
+    # ada_u22 feeds the 3-channel flow volume straight into init_conv (its forward never calls init_noise_conv,
+    # ..._traj_ada_u22.py:1176-1242), so it takes 3 + 256 input channels like the base variant
+    channels = 3 + 256 if variant in ("base", "u22") else 512
     return mod.Unet3D(dim=64, channels=channels, out_grid_dim=2, out_conf_dim=1, dim_mults=dim_mults,
                       use_bert_text_cond=False, learn_null_cond=False, use_final_activation=False,
                       use_deconv=True, padding_mode="zeros", cond_num=tc, pred_num=tp).eval()
@@ -180,6 +184,9 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["unet", "ddim", "generator", "pipeline"]
     if "unet" in which:
         for n in UNET_CASES:
+            gen_unet(n)
+    for n in which:
+        if n in UNET_CASES:
             gen_unet(n)
     if "ddim" in which:
         gen_ddim()

@@ -45,7 +45,7 @@ def psnr(a, b):
 
 def build_unet(fx):
     from extdm_b200.unet import Unet3D
-    channels = 3 + 256 if fx["variant"] == "base" else 512
+    channels = 3 + 256 if fx["variant"] in ("base", "u22") else 512
     u = Unet3D(dim=64, channels=channels, dim_mults=fx["dim_mults"], cond_num=fx["tc"], pred_num=fx["tp"],
                architecture=fx["variant"]).cuda()
     sd = synth_state_dict(fx["manifest"], fx["weight_seed"])
@@ -54,7 +54,7 @@ def build_unet(fx):
     return u, sd
 
 
-@pytest.mark.parametrize("name", ["unet_ada_c2p5", "unet_base_c3p2", "unet_u12_c2p3"])
+@pytest.mark.parametrize("name", ["unet_ada_c2p5", "unet_base_c3p2", "unet_u12_c2p3", "unet_u22_c2p5"])
 def test_unet_forward_matches_reference(name):
     fx = torch.load(os.path.join(GOLD, name + ".pt"))
     u, _ = build_unet(fx)
@@ -66,7 +66,7 @@ def test_unet_forward_matches_reference(name):
     assert r <= 2e-2, r
 
 
-@pytest.mark.parametrize("name", ["unet_ada_c2p5", "unet_u12_c2p3", "unet_base_c3p2"])
+@pytest.mark.parametrize("name", ["unet_ada_c2p5", "unet_u12_c2p3", "unet_base_c3p2", "unet_u22_c2p5"])
 def test_unet_layers_vs_oracle(name):
     """Layer-by-layer: every tapped activation of the CUDA runner against the oracle's (rel-L2 <= 3e-2)."""
     from oracle import extdm_oracle as O
@@ -195,7 +195,8 @@ def test_pipeline_matches_reference(request):
     assert psnr(ret["real_out_vid"].cpu(), fx["out"]["real_out_vid"]) >= 35.0
 
 
-@pytest.mark.parametrize("name,B", [("smmnist", 1), ("bair", 2), ("ucf", 2), ("cityscapes", 1), ("kth", 1)])
+@pytest.mark.parametrize("name,B", [("smmnist", 1), ("bair", 2), ("ucf", 2), ("cityscapes", 1), ("kth", 1),
+                                    ("cityscapes_u22", 1)])
 def test_every_dataset_config_samples(name, B):
     """Every configuration BASELINE.json names builds and runs one sample_one_video round on the CUDA path:
     output shapes as the reference's, finite values, frames in [0, 1]."""
