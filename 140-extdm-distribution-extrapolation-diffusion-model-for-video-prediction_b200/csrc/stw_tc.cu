@@ -15,6 +15,7 @@
 // Only rows 0..63 of the M = 128 tiles are real (one window per iteration); the other accumulator lanes are ignored.
 // The 64 x 64 x 16 per-head score / PV products (block-diagonal, below any tcgen05 tile) stay on mma.sync with
 // ldmatrix operands, bias-initialised accumulators and the ballot shift mask, two warps per head.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -67,16 +68,26 @@ struct Smem {
   static constexpr int qo = a + 16384;                 // 2 x [128][64] SW128: Q, then O in place 32768
   static constexpr int k = qo + 32768;                 // 2 x [128][64] SW128                     32768
   static constexpr int v = k + 32768;                  //                                         32768
-  static constexpr int raw = v + 32768;                // 2 x [128][72] bf16 raw tokens           36864
-  static constexpr int tbl = raw + 36864;              // [8][344] bf16 bias table * log2(e)       5504
-  static constexpr int rope = tbl + 5504;              // cos, sin [64][8] fp32                    4096
+  static constexpr int raw = v + 32768;                // 2 x [128][64] bf16 raw tokens, chunk-swizzled 32768
+  static constexpr int tbl = raw + 32768;              // [8][344] words: bias pairs (e-1, e) * log2(e) 11008
+  static constexpr int rope = tbl + 11008;             // cos, sin [64][8] fp32                    4096
   static constexpr int misc = rope + 4096;             // gamma[64], pbias[64] fp32                 512
   static constexpr int emask = misc + 512;             // [2 windows][2 halves][8] u32              128
   static constexpr int bars = emask + 128;             // 2 mbarriers + tmem slot                    32
   static constexpr int total = bars + 32;
 };
-constexpr int XPR = 72;                                // raw pitch (bf16)
-constexpr int TBLP = 344;                              // bias-table pitch per head (343 entries)
+constexpr int XPR = 64;                                // raw pitch (bf16); 16-byte chunk j of token n sits at chunk j ^ (n & 7)
+constexpr int TBLP = 344;                              // bias-table pitch per head (343 entries), one 32-bit word each:
+                                                       // low half = entry e - 1, high half = entry e (adjacent keys)
+__device__ __forceinline__ int raw_off(int n, int chunk) { return n * XPR + ((chunk ^ (n & 7)) << 3); }
+__device__ __forceinline__ uint32_t t_lds32(uint32_t addr) {
+  uint32_t v;
+  asm("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+// EXTDM_STW_PROF=1: per-phase cycle counts of CTA 0 (thread 0's view, barrier waits included), printed by the launcher
+__device__ unsigned long long g_stw_prof[8];
 
 struct TcParams {
   const __nv_bfloat16* x;
@@ -91,6 +102,7 @@ struct TcParams {
   int B, T, H, W, sd, sh, sw, Dp, n_windows;
   int lw, lh;                  // log2 of the window counts along W and H (powers of two: checked by the launcher)
   float eps;
+  int prof;
 };
 
 // byte offset of hidden-dim chunk j (0..15, 8 bf16 each) of token row r in the two-k-block swizzled [128][128] tile
@@ -107,7 +119,6 @@ __global__ void __launch_bounds__(NTH, 1) stw_tc_kernel(const __grid_constant__ 
   uint8_t* s_k = sm + Smem::k;
   uint8_t* s_v = sm + Smem::v;
   __nv_bfloat16* s_raw = reinterpret_cast<__nv_bfloat16*>(sm + Smem::raw);
-  const unsigned short* s_tbl = reinterpret_cast<const unsigned short*>(sm + Smem::tbl);
   float* s_cos = reinterpret_cast<float*>(sm + Smem::rope);
   float* s_sin = s_cos + NTOK * (DH / 2);
   float* s_gamma = reinterpret_cast<float*>(sm + Smem::misc);
@@ -136,8 +147,9 @@ __global__ void __launch_bounds__(NTH, 1) stw_tc_kernel(const __grid_constant__ 
   for (int i = tid; i < C; i += NTH) { s_gamma[i] = p.gamma[i]; s_pbias[i] = p.proj_bias ? p.proj_bias[i] : 0.f; }
   for (int i = tid; i < HEADS * TBLP; i += NTH) {
     const int h = i / TBLP, e = i % TBLP;
-    reinterpret_cast<__nv_bfloat16*>(sm + Smem::tbl)[i] =
-        __float2bfloat16(e < 343 ? p.bias_table[e * HEADS + h] * kL2e : 0.f);
+    const float hi = e < 343 ? p.bias_table[e * HEADS + h] * kL2e : 0.f;
+    const float lo = e >= 1 ? p.bias_table[(e - 1) * HEADS + h] * kL2e : 0.f;
+    reinterpret_cast<uint32_t*>(sm + Smem::tbl)[i] = pack_bf16(lo, hi);
   }
   if (tid == 0) {
     mbar_init(bar_qkv, 1);
@@ -191,16 +203,12 @@ __global__ void __launch_bounds__(NTH, 1) stw_tc_kernel(const __grid_constant__ 
       const int n = i >> 3, c8 = i & 7;
       const Win w = decode(2 * pair + k);
       const int s = src_pixel(w, n & 63);
-      t_cp_async16(dst + n * XPR + c8 * 8, p.x + (s >= 0 ? static_cast<long long>(s) * C + c8 * 8 : 0), s >= 0 ? 16 : 0);
+      t_cp_async16(dst + raw_off(n, c8), p.x + (s >= 0 ? static_cast<long long>(s) * C + c8 * 8 : 0), s >= 0 ? 16 : 0);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
   const int n_pairs = (p.n_windows + 1) / 2;
-  int pair = blockIdx.x;
-  int buf = 0;
-  uint32_t it = 0;
-  if (pair < n_pairs) prefetch_pair(pair, 0);
   const float qscale = 0.25f * kL2e;                    // dh^-1/2 * log2(e)
   constexpr float kMask = -100.0f * kL2e;
   constexpr uint32_t idesc256 = umma_idesc_bf16(128, 256), idesc128 = umma_idesc_bf16(128, 128),
@@ -211,68 +219,51 @@ __global__ void __launch_bounds__(NTH, 1) stw_tc_kernel(const __grid_constant__ 
   // relative-position table offsets (lin(i) - lin(j) + 171): per-thread parts, the rest are compile-time immediates
   const int ltg = (tg >> 1) * 7 + (tg & 1) * 2;
   const int pt0 = (g >> 2) * 7 + (g & 3) - ltg + 171, pt1 = pt0 + 14;
-  const unsigned short* tb = s_tbl + head * TBLP;
+  const uint32_t tb0 = smem_u32(sm + Smem::tbl) + static_cast<uint32_t>(head * TBLP + pt0) * 4u;
+  const uint32_t tb1 = tb0 + static_cast<uint32_t>(pt1 - pt0) * 4u;
+  // drain / epilogue role: TMEM lane quarter warp & 3 (thread = token), column group warp >> 2
+  const int dq = warp & 3, de = warp >> 2;
+  const int dtok = dq * 32 + lane;                      // 0..127 (window dtok >> 6, position dtok & 63)
+  const uint32_t tlane = tmem_u + (static_cast<uint32_t>(dq * 32) << 16);
 
-  for (; pair < n_pairs; pair += gridDim.x, ++it) {
-    const Win w0 = decode(2 * pair), w1 = decode(2 * pair + 1);
-    const int nxt = pair + gridDim.x;
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();                                    // S1: raw[buf] landed; previous pair fully retired
-    if (nxt < n_pairs) prefetch_pair(nxt, buf ^ 1);
-    const __nv_bfloat16* raw = s_raw + buf * 128 * XPR;
-    if (warp < 4) {                                     // region-membership words of window warp>>1, token half warp&1
-      const Win& w = (warp >> 1) ? w1 : w0;
-      if (win_masked(w)) {
-        const int code = region_code(w, (warp & 1) * 32 + lane);
-        uint32_t mine = 0;
+  // channel LayerNorm of one pair: 4 threads per token, two 16-byte chunks each -> swizzled A tile
+  auto layernorm_pair = [&](int pr, const __nv_bfloat16* raw) {
+    const int n = tid >> 2, part = tid & 3;
+    const Win w = decode(2 * pr + (n >> 6));
+    float v[16];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint32_t bal = __ballot_sync(0xffffffffu, code == c);
-          if (lane == c) mine = bal;
-        }
-        if (lane < 8) s_E[warp * 8 + lane] = mine;
-      }
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const uint4 t = *reinterpret_cast<const uint4*>(raw + raw_off(n, part * 2 + h2));
+      const float2 a = unpack_bf16(t.x), b = unpack_bf16(t.y), c = unpack_bf16(t.z), d = unpack_bf16(t.w);
+      v[h2 * 8] = a.x; v[h2 * 8 + 1] = a.y; v[h2 * 8 + 2] = b.x; v[h2 * 8 + 3] = b.y;
+      v[h2 * 8 + 4] = c.x; v[h2 * 8 + 5] = c.y; v[h2 * 8 + 6] = d.x; v[h2 * 8 + 7] = d.y;
     }
-    // ---- channel LayerNorm: 4 threads per token, two 16-byte chunks each -> swizzled A tile
-    {
-      const int n = tid >> 2, part = tid & 3;
-      const Win& w = (n >> 6) ? w1 : w0;
-      float v[16];
+    float sum = 0.f;
 #pragma unroll
-      for (int h2 = 0; h2 < 2; ++h2) {
-        const uint4 t = *reinterpret_cast<const uint4*>(raw + n * XPR + part * 16 + h2 * 8);
-        const float2 a = unpack_bf16(t.x), b = unpack_bf16(t.y), c = unpack_bf16(t.z), d = unpack_bf16(t.w);
-        v[h2 * 8] = a.x; v[h2 * 8 + 1] = a.y; v[h2 * 8 + 2] = b.x; v[h2 * 8 + 3] = b.y;
-        v[h2 * 8 + 4] = c.x; v[h2 * 8 + 5] = c.y; v[h2 * 8 + 6] = d.x; v[h2 * 8 + 7] = d.y;
+    for (int j = 0; j < 16; ++j) sum += v[j];
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    const float mean = sum * (1.0f / C);
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { const float dd = v[j] - mean; sq += dd * dd; }
+    sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+    sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+    const float rstd = src_pixel(w, n & 63) >= 0 ? rsqrtf(sq * (1.0f / C) + p.eps) : 0.f;
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int cc = part * 16 + h2 * 8 + 2 * j;
+        pk[j] = pack_bf16((v[h2 * 8 + 2 * j] - mean) * rstd * s_gamma[cc],
+                          (v[h2 * 8 + 2 * j + 1] - mean) * rstd * s_gamma[cc + 1]);
       }
-      float sum = 0.f;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) sum += v[j];
-      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-      const float mean = sum * (1.0f / C);
-      float sq = 0.f;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) { const float dd = v[j] - mean; sq += dd * dd; }
-      sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-      sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-      const float rstd = src_pixel(w, n & 63) >= 0 ? rsqrtf(sq * (1.0f / C) + p.eps) : 0.f;
-#pragma unroll
-      for (int h2 = 0; h2 < 2; ++h2) {
-        uint32_t pk[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int cc = part * 16 + h2 * 8 + 2 * j;
-          pk[j] = pack_bf16((v[h2 * 8 + 2 * j] - mean) * rstd * s_gamma[cc],
-                            (v[h2 * 8 + 2 * j + 1] - mean) * rstd * s_gamma[cc + 1]);
-        }
-        *reinterpret_cast<uint4*>(s_a + sw128(n, part * 2 + h2)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      }
+      *reinterpret_cast<uint4*>(s_a + sw128(n, part * 2 + h2)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
-    fence_proxy_async();                                // A tile -> visible to the tensor-core (async) proxy
-    __syncthreads();                                    // S2
-
-    // ---- QKV projection on tcgen05: D[:, 0:256] (Q | K) and D[:, 256:384] (V)
+  };
+  // QKV projection of the pair whose normalised tokens sit in s_a: D[:, 0:256] (Q | K) and D[:, 256:384] (V)
+  auto issue_qkv = [&]() {
     if (warp == 0) {
       tc_fence_after();
       if (elect_one()) {
@@ -288,46 +279,122 @@ __global__ void __launch_bounds__(NTH, 1) stw_tc_kernel(const __grid_constant__ 
       }
       __syncwarp();
     }
-    mbar_wait(bar_qkv, it & 1);
-    tc_fence_after();
-
-    // ---- drain: every warp, TMEM lane quarter warp & 3 (32 tokens), 96 columns: thread = token
-    {
-      const int q = warp & 3;
-      const int tok = q * 32 + lane;                    // 0..127 (window tok >> 6, position tok & 63)
-      const int e = warp >> 2;                          // 0..3 -> columns [96e, 96e + 96)
-      const uint32_t taddr = tmem_u + (static_cast<uint32_t>(q * 32) << 16) + e * 96;
-      const int pos = tok & 63;
-#pragma unroll 1
-      for (int c = 0; c < 6; ++c) {
-        uint32_t rr[16];
-        tmem_ld16(taddr + c * 16, rr);
-        tmem_ld_wait();
-        const int col = e * 96 + c * 16;                // 16 columns = one head of Q, K or V
-        const int region = col >> 7, hd = (col & 127) >> 4;
-        float f[16];
+  };
+  // one 16-column accumulator chunk (one head of Q, K or V) -> rotary / q-scale -> bf16 operand tile
+  auto emit_chunk = [&](const uint32_t (&rr)[16], int region, int hd) {
+    const int pos = dtok & 63;
+    float f[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(rr[j]);
-        if (region < 2) {
-          const float sc = region == 0 ? qscale : 1.0f;
+    for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(rr[j]);
+    if (region < 2) {
+      const float sc = region == 0 ? qscale : 1.0f;
 #pragma unroll
-          for (int pr = 0; pr < 8; ++pr) {
-            const float cs = s_cos[pos * 8 + pr], sn = s_sin[pos * 8 + pr];
-            const float x0 = f[2 * pr] * sc, x1 = f[2 * pr + 1] * sc;
-            f[2 * pr] = x0 * cs - x1 * sn;
-            f[2 * pr + 1] = x1 * cs + x0 * sn;
-          }
-        }
-        uint32_t pk[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
-        uint8_t* dst = region == 0 ? s_qo : (region == 1 ? s_k : s_v);
-        *reinterpret_cast<uint4*>(dst + sw2(tok, hd * 2)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(dst + sw2(tok, hd * 2 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      for (int pr = 0; pr < 8; ++pr) {
+        const float cs = s_cos[pos * 8 + pr], sn = s_sin[pos * 8 + pr];
+        const float x0 = f[2 * pr] * sc, x1 = f[2 * pr + 1] * sc;
+        f[2 * pr] = x0 * cs - x1 * sn;
+        f[2 * pr + 1] = x1 * cs + x0 * sn;
       }
     }
+    uint32_t pk[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
+    uint8_t* dst = region == 0 ? s_qo : (region == 1 ? s_k : s_v);
+    *reinterpret_cast<uint4*>(dst + sw2(dtok, hd * 2)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    *reinterpret_cast<uint4*>(dst + sw2(dtok, hd * 2 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  };
+  auto drain_region = [&](int region) {                 // this warp's two heads (2 de, 2 de + 1) of Q, K or V
+    uint32_t ra[16], rb[16];
+    tmem_ld16(tlane + region * 128 + de * 32, ra);
+    tmem_ld16(tlane + region * 128 + de * 32 + 16, rb);
+    tmem_ld_wait();
+    emit_chunk(ra, region, 2 * de);
+    emit_chunk(rb, region, 2 * de + 1);
+  };
+  // output-projection epilogue of a finished pair: TMEM columns 384.. + bias + residual -> global
+  auto epilogue = [&](int d) {
+    uint32_t rr[16];
+    tmem_ld16(tlane + 384 + de * 16, rr);
+    tmem_ld_wait();
+    if (d >= 0) {
+      const uint4* xp = reinterpret_cast<const uint4*>(p.x + static_cast<long long>(d) * C + de * 16);
+      const uint4 r0v = xp[0], r1v = xp[1];
+      const uint32_t rw[8] = {r0v.x, r0v.y, r0v.z, r0v.w, r1v.x, r1v.y, r1v.z, r1v.w};
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 rv = unpack_bf16(rw[j]);
+        pk[j] = pack_bf16(__uint_as_float(rr[2 * j]) + s_pbias[de * 16 + 2 * j] + rv.x,
+                          __uint_as_float(rr[2 * j + 1]) + s_pbias[de * 16 + 2 * j + 1] + rv.y);
+      }
+      __nv_bfloat16* yp = p.y + static_cast<long long>(d) * C + de * 16;
+      *reinterpret_cast<uint4*>(yp) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(yp + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    }
+  };
+
+  // Software pipeline over this CTA's pairs (it = 0, 1, ...):
+  //   phase A(it): drain K, V of pair it | LayerNorm of pair it+1 | wait out-proj(it-1) | drain Q | epilogue(it-1)
+  //   barrier S3 ; issue QKV MMA(it+1) ; prefetch raw tokens of pair it+2
+  //   phase B(it): attention(it) ; barrier S4 ; issue out-proj MMA(it)
+  // so both tcgen05 products and the global loads run under the attention of a neighbouring pair.
+  int pair = blockIdx.x;
+  uint32_t it = 0;
+  int d_prev = -1;
+  if (pair < n_pairs) {
+    prefetch_pair(pair, 0);
+    if (pair + static_cast<int>(gridDim.x) < n_pairs) prefetch_pair(pair + gridDim.x, 1);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    layernorm_pair(pair, s_raw);
+    fence_proxy_async();
     tc_fence_before();
-    __syncthreads();                                    // S3: Q / K / V tiles complete
+    __syncthreads();
+    issue_qkv();
+  }
+  for (; pair < n_pairs; pair += gridDim.x, ++it) {
+    const Win w0 = decode(2 * pair), w1 = decode(2 * pair + 1);
+    const int nxt = pair + gridDim.x;
+    long long tk[8];
+    const bool prof = p.prof && blockIdx.x == 0 && tid == 0;
+    if (prof) tk[0] = clock64();
+    if (warp < 4) {                                     // region-membership words of window warp>>1, token half warp&1
+      const Win& w = (warp >> 1) ? w1 : w0;
+      if (win_masked(w)) {
+        const int code = region_code(w, (warp & 1) * 32 + lane);
+        uint32_t mine = 0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t bal = __ballot_sync(0xffffffffu, code == c);
+          if (lane == c) mine = bal;
+        }
+        if (lane < 8) s_E[warp * 8 + lane] = mine;
+      }
+    }
+    const int d_cur = src_pixel((dtok >> 6) ? w1 : w0, dtok & 63);
+    mbar_wait(bar_qkv, it & 1);
+    tc_fence_after();
+    if (prof) tk[1] = clock64();
+    drain_region(1);
+    drain_region(2);
+    if (nxt < n_pairs) layernorm_pair(nxt, s_raw + ((it + 1) & 1) * 128 * XPR);
+    if (prof) tk[2] = clock64();
+    if (it > 0) {
+      mbar_wait(bar_o, (it - 1) & 1);                   // out-proj(it-1) done: its A operand (the Q / O slots) is free
+      tc_fence_after();
+    }
+    if (prof) tk[3] = clock64();
+    drain_region(0);
+    if (it > 0) epilogue(d_prev);
+    d_prev = d_cur;
+    fence_proxy_async();                                // next pair's A tile -> visible to the tensor-core proxy
+    tc_fence_before();
+    __syncthreads();                                    // S3: Q / K / V tiles complete, TMEM drained, s_a written
+    if (prof) tk[4] = clock64();
+    if (nxt < n_pairs) {
+      issue_qkv();
+      if (nxt + static_cast<int>(gridDim.x) < n_pairs) prefetch_pair(nxt + gridDim.x, it & 1);
+    }
 
     // ---- attention core (mma.sync): warp = (window awin, head); all four query m-tiles; O overwrites Q in place
     {
@@ -353,10 +420,11 @@ __global__ void __launch_bounds__(NTH, 1) stw_tc_kernel(const __grid_constant__ 
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
           const int kk = mt * 49 - (nt >> 1) * 49 - (nt & 1) * 14;      // compile-time part of the table index
-          s[nt][0] = __uint_as_float(static_cast<uint32_t>(tb[pt0 + kk]) << 16);
-          s[nt][1] = __uint_as_float(static_cast<uint32_t>(tb[pt0 + kk - 1]) << 16);
-          s[nt][2] = __uint_as_float(static_cast<uint32_t>(tb[pt1 + kk]) << 16);
-          s[nt][3] = __uint_as_float(static_cast<uint32_t>(tb[pt1 + kk - 1]) << 16);
+          const uint32_t w0b = t_lds32(tb0 + kk * 4), w1b = t_lds32(tb1 + kk * 4);
+          s[nt][0] = t_bf_hi(w0b);                      // key column 2*tg     -> entry e
+          s[nt][1] = t_bf_lo(w0b);                      // key column 2*tg + 1 -> entry e - 1
+          s[nt][2] = t_bf_hi(w1b);
+          s[nt][3] = t_bf_lo(w1b);
         }
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) t_mma16816(s[nt], qa, kfrag[nt][0], kfrag[nt][1]);
@@ -425,10 +493,13 @@ __global__ void __launch_bounds__(NTH, 1) stw_tc_kernel(const __grid_constant__ 
         }
       }
     }
+    if (prof) tk[5] = clock64();
+    asm volatile("cp.async.wait_group 0;" ::: "memory");  // raw tokens of the pair after next: visible after S4
     fence_proxy_async();
     __syncthreads();                                    // S4: O tile complete
+    if (prof) tk[6] = clock64();
 
-    // ---- output projection on tcgen05: D_o[128 x 64] at TMEM column 384
+    // ---- output projection on tcgen05: D_o[128 x 64] at TMEM column 384; consumed in the next iteration's phase A
     if (warp == 0) {
       tc_fence_after();
       if (elect_one()) {
@@ -443,34 +514,16 @@ __global__ void __launch_bounds__(NTH, 1) stw_tc_kernel(const __grid_constant__ 
       }
       __syncwarp();
     }
-    mbar_wait(bar_o, it & 1);
-    tc_fence_after();
-    {
-      const int q = warp & 3;
-      const int tok = q * 32 + lane;
-      const int e = warp >> 2;                          // 16-column chunk of the 64 output channels
-      uint32_t rr[16];
-      tmem_ld16(tmem_u + (static_cast<uint32_t>(q * 32) << 16) + 384 + e * 16, rr);
-      tmem_ld_wait();
-      const int d = src_pixel((tok >> 6) ? w1 : w0, tok & 63);
-      if (d >= 0) {
-        const uint4 r0v = *reinterpret_cast<const uint4*>(raw + tok * XPR + e * 16);
-        const uint4 r1v = *reinterpret_cast<const uint4*>(raw + tok * XPR + e * 16 + 8);
-        const uint32_t rw[8] = {r0v.x, r0v.y, r0v.z, r0v.w, r1v.x, r1v.y, r1v.z, r1v.w};
-        uint32_t pk[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float2 rv = unpack_bf16(rw[j]);
-          pk[j] = pack_bf16(__uint_as_float(rr[2 * j]) + s_pbias[e * 16 + 2 * j] + rv.x,
-                            __uint_as_float(rr[2 * j + 1]) + s_pbias[e * 16 + 2 * j + 1] + rv.y);
-        }
-        __nv_bfloat16* yp = p.y + static_cast<long long>(d) * C + e * 16;
-        *reinterpret_cast<uint4*>(yp) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(yp + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      }
+    if (prof) {
+      tk[7] = clock64();
+      for (int i = 0; i < 7; ++i) g_stw_prof[i] += static_cast<unsigned long long>(tk[i + 1] - tk[i]);
+      g_stw_prof[7] += 1;
     }
-    tc_fence_before();
-    buf ^= 1;
+  }
+  if (it > 0) {                                         // epilogue of this CTA's last pair
+    mbar_wait(bar_o, (it - 1) & 1);
+    tc_fence_after();
+    epilogue(d_prev);
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   tc_fence_before();
@@ -529,7 +582,22 @@ int extdm_stw_tc_launch(const void* x, void* y, const float* gamma, const void* 
   }
   const int n_pairs = (p.n_windows + 1) / 2;
   const int grid = n_pairs < sms ? n_pairs : sms;
+  static const bool prof = getenv("EXTDM_STW_PROF") != nullptr;
+  p.prof = prof ? 1 : 0;
+  if (prof) {
+    unsigned long long z[8] = {};
+    cudaMemcpyToSymbol(g_stw_prof, z, sizeof(z));
+  }
   stw_tc_kernel<<<grid, NTH, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  if (prof) {
+    unsigned long long h[8];
+    cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+    cudaMemcpyFromSymbol(h, g_stw_prof, sizeof(h));
+    const double n = h[7] ? static_cast<double>(h[7]) : 1.0;
+    fprintf(stderr, "[stw_tc prof] B=%d T=%d H=%d W=%d shift=%d pairs/CTA=%.0f cycles/pair: qkv_wait %.0f drainKV+ln %.0f proj_wait %.0f "
+            "drainQ+epi %.0f S3 %.0f attn %.0f S4 %.0f issue %.0f\n", B, T, H, W, sd | sh | sw, n, h[0] / n, h[1] / n,
+            h[2] / n, h[3] / n, h[4] / n, h[5] / n, h[6] / n, 0.0);
+  }
   EXTDM_CHECK_LAUNCH();
   return EXTDM_OK;
 }
