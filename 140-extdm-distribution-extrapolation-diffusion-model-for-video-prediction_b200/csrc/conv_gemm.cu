@@ -40,6 +40,7 @@ struct GemmDev {
   float* gn_part;
   // halo kernel (k x k 'same' convolutions whose 128-row tile is bh full-width rows of one frame)
   int kh, kw, stages, a_ext_bytes;
+  int tf32;       // operands are fp32, product runs as kind::tf32 (ExtdmGemm.tf32)
   int prefetch;   // L2 prefetch of the tile two ahead (helps the multi-block shapes, measured per shape)
   int dbg;   // profiling experiments only (EXTDM_GEMM_DBG): 1 = no epilogue stores, 2 = no MMA issue, 4 = no TMA loads,
              // 8 = no tcgen05.ld, 16 = no GroupNorm partial reduction, 32 = plain arrives instead of tcgen05.commit,
@@ -524,7 +525,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
   } else if (warp == 1) {
     // =========================== MMA issuer (warp-uniform control flow, one elected lane issues)
     {
-      constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN < 16 ? 16 : BN);
+      const uint32_t idesc = p.tf32 ? umma_idesc_tf32(kTileM, BN < 16 ? 16 : BN) : umma_idesc_bf16(kTileM, BN < 16 ? 16 : BN);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -546,7 +547,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
 #pragma unroll
               for (int k = 0; k < kBlockK / 16; ++k) {
                 // advance 16 bf16 = 32 B along K inside the 128B swizzle row: +2 in (addr >> 4) units
-                umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                if (p.tf32) umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                else umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
               }
             }
             umma_commit(&empty_bar[stage]);
@@ -694,7 +696,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
   } else if (warp == 1) {
     // =========================== MMA issuer (warp-uniform control flow, one elected lane issues)
     {
-      constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN < 16 ? 16 : BN);
+      const uint32_t idesc = p.tf32 ? umma_idesc_tf32(kTileM, BN < 16 ? 16 : BN) : umma_idesc_bf16(kTileM, BN < 16 ? 16 : BN);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const int row_shift = p.box[0] * 128;            // bytes between the A views of consecutive kernel rows
       if (RESB) {
@@ -725,7 +727,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                 const uint64_t db = umma_desc_sw128(sb);
 #pragma unroll
                 for (int k = 0; k < kBlockK / 16; ++k) {
-                  umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, acc);
+                  if (p.tf32) umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, acc);
+                  else umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, acc);
                   acc = 1;
                 }
               }
@@ -913,6 +916,7 @@ extern "C" int extdm_conv_gemm(const ExtdmGemm* g, void* stream_) {
   dev.col_shift = g->col_shift;
   dev.act = g->act;
   dev.gn_part = g->gn_partials;
+  dev.tf32 = g->tf32;
   static const int dbg_flags = getenv("EXTDM_GEMM_DBG") ? atoi(getenv("EXTDM_GEMM_DBG")) : 0;
   dev.dbg = dbg_flags;
   // measured on B200 (profiles/kernel_table_r1.md): the prefetch pays when a tile streams two or more 64-channel blocks

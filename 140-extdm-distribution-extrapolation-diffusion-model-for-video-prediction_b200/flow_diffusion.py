@@ -125,7 +125,10 @@ class FlowDiffusion(nn.Module):
         n_rep = (1 + tp) if self.WRAPPER == "w_ref" else tp
         fea = torch.cat([enc_frames[:, :tc - 1], ref_fea[:, None].expand(B, n_rep, *ref_fea.shape[1:])], dim=1)
         fea = fea.transpose(1, 2).contiguous()                                       # (B, 256, T', h, w)
-        if self.WRAPPER != "w_ref":
+        if self.WRAPPER != "w_ref" and not fea.is_cuda:
+            # VideoFlowDiffusion_multi1248.py:243-245 resizes cond_fea to the flow resolution before the UNet.  On the
+            # CUDA path the UNet prologue does that resize itself (extdm_bilinear_resize_cl, align_corners=False like
+            # F.interpolate), so the features stay at H/4 here; this branch serves the CPU parity fixtures only.
             n, c, t, h, w = fea.shape
             hw = ret["real_vid_grid"].shape[-2:]
             fea = F.interpolate(fea.transpose(1, 2).reshape(n * t, c, h, w), size=hw, mode="bilinear")

@@ -27,6 +27,7 @@ class ExtdmGemm(C.Structure):
         ("col_scale", C.c_void_p), ("col_shift", C.c_void_p),
         ("act", C.c_int), ("block_n", C.c_int),
         ("gn_partials", C.c_void_p),
+        ("tf32", C.c_int),
     ]
 
 

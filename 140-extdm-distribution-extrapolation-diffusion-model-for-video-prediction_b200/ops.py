@@ -142,7 +142,7 @@ def std_box(H, W):
 def gemm(rec, *, a0, c0, dims, strides0, box, start, count, taps, w, n, out, out_stride, out_base=0,
          a1=None, c1=0, strides1=None, out_fp32=False, col_group=None, col_group_stride=0, bias=None,
          res=None, res_fp32=False, res_base=0, res_stride=None, col_scale=None, col_shift=None, act=0,
-         block_n=0, gn_partials=None, a1_offset=0):
+         block_n=0, gn_partials=None, a1_offset=0, tf32=False):
     """Generic launch of extdm_conv_gemm.  dims/strides: extents and element strides of D1..D4 of the A
     tensor(s); box/start/count: tile geometry; taps: list of (o1,o2,o3)."""
     g = _lib.ExtdmGemm()
@@ -173,8 +173,11 @@ def gemm(rec, *, a0, c0, dims, strides0, box, start, count, taps, w, n, out, out
     g.col_shift = 0 if col_shift is None else col_shift.data_ptr()
     g.act, g.block_n = act, block_n
     g.gn_partials = 0 if gn_partials is None else gn_partials.data_ptr()
+    g.tf32 = int(tf32)
     rows = count[0] * count[1] * count[2] * count[3]
     ktot = len(taps) * (c0 + (c1 if a1 is not None else 0))
+    if tf32:
+        ktot //= 2                                       # channel counts are in 2-byte units: K in fp32 elements
     meta = dict(flops=2.0 * rows * n * ktot, rows=rows, n=n, k=ktot, taps=len(taps),
                 bytes=2.0 * rows * (c0 + (c1 if a1 is not None else 0)) + 2.0 * n * ktot
                 + rows * n * (4.0 if out_fp32 else 2.0))
@@ -197,7 +200,7 @@ def linear_rows(rec, x, w, n, out, *, bias=None, res=None, res_fp32=False, act=0
 
 def conv_cl(rec, x, w, n, k, out, *, x2=None, bias=None, res=None, res_fp32=False, act=0, out_fp32=False,
             t_range=None, col_scale=None, col_shift=None, out_t_offset=0, res_t_offset=0, taps=None,
-            out_scale=1, out_phase=(0, 0), block_n=0, gn_partials=None, x2_t_offset=0):
+            out_scale=1, out_phase=(0, 0), block_n=0, gn_partials=None, x2_t_offset=0, tf32=False):
     """k x k 'same' convolution over channels-last x (B, T, H, W, C) [channel-concatenated with x2].
     out: (B, To, Ho, Wo, n') with n' >= n.  t_range=(t0, t1) restricts the frames computed; the output
     frame index is t + out_t_offset.  out_scale/out_phase write a strided output (ConvTranspose phases)."""
@@ -221,7 +224,34 @@ def conv_cl(rec, x, w, n, k, out, *, x2=None, bias=None, res=None, res_fp32=Fals
          box=(bw, bh, bt, 1), start=(0, 0, t0, 0), count=(W, H, t1 - t0, B),
          taps=taps if taps is not None else conv_taps(k), w=w, n=n, out=out, out_stride=ostr, out_base=obase,
          out_fp32=out_fp32, bias=bias, res=res, res_fp32=res_fp32, res_base=rbase, res_stride=rstr,
-         col_scale=col_scale, col_shift=col_shift, act=act, block_n=block_n, gn_partials=gn_partials)
+         col_scale=col_scale, col_shift=col_shift, act=act, block_n=block_n, gn_partials=gn_partials, tf32=tf32)
+
+
+def pack_conv_weight_f32(w, cin_pad=None, splits=None):
+    """(Cout, Cin, kh, kw) fp32 -> (Cout, kh*kw*Cin') fp32 for the tf32 GEMM mode, K index = tap*Cin' + c.
+    splits = [(c_begin, c_end, c_padded), ...] re-lays the input channels as several zero-padded groups
+    (channel-concatenated sources whose widths are not multiples of 32)."""
+    co, ci, kh, kw = w.shape
+    if splits is None:
+        splits = [(0, ci, cin_pad or ci)]
+    parts = []
+    for b, e, cp in splits:
+        blk = torch.zeros(co, kh, kw, cp, device=w.device, dtype=torch.float32)
+        blk[..., : e - b] = w[:, b:e].permute(0, 2, 3, 1)
+        parts.append(blk)
+    return torch.cat(parts, dim=3).reshape(co, -1).contiguous()
+
+
+def conv_cl_tf32(rec, x, w, n, k, out, *, x2=None, bias=None, act=0, taps=None):
+    """k x k 'same' convolution of fp32 channels-last x (F, H, W, C) [| x2] in tf32 (fp32 accumulate), fp32 output
+    (F, H, W, n') -- the LFAE conditioning convolutions (the reference's cuDNN path runs them in TF32 as well).
+    w: pack_conv_weight_f32 layout; channel counts are multiples of 32."""
+    for t in (x, x2, w, out):
+        if t is not None and t.dtype != torch.float32:
+            raise ValueError("conv_cl_tf32: fp32 tensors expected")
+    v = lambda t: None if t is None else t.view(BF16).view(t.shape[0], 1, t.shape[1], t.shape[2], 2 * t.shape[3])
+    conv_cl(rec, v(x), w.view(BF16), n, k, out.view(out.shape[0], 1, *out.shape[1:]), x2=v(x2), bias=bias, act=act,
+            out_fp32=True, taps=taps, tf32=True)
 
 
 def conv_tiles_per_sample(T, H, W):

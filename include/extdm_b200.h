@@ -75,6 +75,12 @@ typedef struct ExtdmGemm {
    * A group's statistic is the sum over the sample's records.  Requires n == block_n in {64,128,256}, a bias(+act)-only
    * bf16 epilogue, box[3] == 1.  Consumed by extdm_groupnorm_apply (n_part = records per sample). */
   float* gn_partials;
+  /* 1: the A tensors and W hold fp32 and the product runs as tcgen05 kind::tf32 (fp32 accumulate) -- the precision the
+   * reference's GPU convolutions run at (cudnn.allow_tf32 defaults to True, never changed by scripts/DM/valid.py).  All
+   * channel counts, element strides and W's row pitch are then given in 2-byte units, i.e. twice the fp32 element
+   * counts (an fp32 tensor of C channels is described exactly like a bf16 tensor of 2C channels; C % 32 == 0).
+   * Used by the LFAE conditioning stage (region / background / flow predictors). */
+  int tf32;
 } ExtdmGemm;
 
 int extdm_conv_gemm(const ExtdmGemm* g, void* stream);

@@ -585,3 +585,27 @@ def test_temporal_fused_layer(T, H):
     with torch.no_grad():
         ref = O.temporal_attention(xc.float().permute(0, 4, 1, 2, 3).cpu(), O.SD(sd), pos_bias, heads, dh)
     close(from_cl(y).cpu(), ref, rel=2e-2, atol=5e-3, what="temporal fused")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("F_,H,W,c0,c1,n,k", [(4, 16, 16, 32, 0, 64, 3), (3, 8, 8, 64, 64, 32, 3), (2, 32, 32, 32, 32, 10, 7),
+                                              (130, 1, 1, 64, 0, 128, 3), (5, 2, 2, 128, 0, 256, 3)])
+def test_conv_tf32_matches_torch(F_, H, W, c0, c1, n, k):
+    """tcgen05 kind::tf32 mode of the implicit GEMM (fp32 operands / output) against F.conv2d in full fp32:
+    TF32 keeps 10 mantissa bits, so the products agree to ~1e-3 of the output scale."""
+    g = torch.Generator().manual_seed(F_ * 7 + n)
+    x = torch.randn(F_, c0 + c1, H, W, generator=g)
+    w = torch.randn(n, c0 + c1, k, k, generator=g) / (k * (c0 + c1) ** 0.5)
+    b = torch.randn(n, generator=g)
+    ref = torch.relu(F.conv2d(x, w, b, padding=k // 2))
+    xcl = x.permute(0, 2, 3, 1).contiguous().cuda()
+    x0 = xcl[..., :c0].contiguous()
+    x1 = xcl[..., c0:].contiguous() if c1 else None
+    wp = ops.pack_conv_weight_f32(w.cuda())
+    npad = (n + 3) // 4 * 4
+    out = torch.zeros(F_, H, W, npad, device="cuda")
+    ops.conv_cl_tf32(ops.IMMEDIATE, x0, wp, n, k, out, x2=x1, bias=b.cuda(), act=1)
+    torch.cuda.synchronize()
+    got = out[..., :n].permute(0, 3, 1, 2).cpu()
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    assert err <= 2e-3, err

@@ -1,5 +1,5 @@
-"""Per-shape kernel time table of one KTH round (CUDA events per launch, eager replay).  GPU box only.
-   python tools/kernel_table.py [batch]  -> markdown on stdout"""
+"""Per-shape kernel time table of one round (CUDA events per launch, eager replay).  GPU box only.
+   python tools/kernel_table.py [batch] [config name, default kth]  -> markdown on stdout"""
 import os
 import sys
 
@@ -10,16 +10,19 @@ import extdm_b200  # noqa: E402
 from extdm_b200 import configs  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
-model, cfg = configs.build_model("kth", device="cuda")
+NAME = sys.argv[2] if len(sys.argv) > 2 else "kth"
+model, cfg = configs.build_model(NAME, device="cuda")
 tc, tp = model.cond_frame_num, model.pred_frame_num
-clip = torch.rand(B, 3, tc, 64, 64, device="cuda")
+HW = cfg["dataset_params"]["frame_shape"]
+clip = torch.rand(B, 3, tc, HW, HW, device="cuda")
 for _ in range(2):
     model.sample_one_video(1.0, clip)
 torch.cuda.synchronize()
-runner = model.unet.runner(B, 32, 32, 16)
-dec = model.generator.decoder(B, tc + tp, 64, 64, 32, 32, True)
+runner = next(iter(model.unet._runners.values()))
+dec = next(r for k, r in model.generator._runners.items() if k[0] != "enc")
+steps = cfg["diffusion_params"]["model_params"]["sampling_timesteps"]
 rows = {}
-for label, rec, mult in (("prologue", runner.prologue, 1), ("step", runner.step, 10), ("decode", dec.rec, 1)):
+for label, rec, mult in (("prologue", runner.prologue, 1), ("step", runner.step, steps), ("decode", dec.rec, 1)):
     rec.run()
     torch.cuda.synchronize()
     best = None
