@@ -190,6 +190,13 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
 }
+// fp32 -> nearest tf32 (10 explicit mantissa bits), kept in an fp32 container: tcgen05 kind::tf32 ignores the low 13
+// mantissa bits of its operands, so operands are rounded where they are produced instead of being truncated there
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 // x*sigmoid(x) = 0.5*x*(1 + tanh(x/2)) with the single-MUFU tanh.approx (|rel err| ~ 2^-11: below bf16 resolution)
 __device__ __forceinline__ float silu_fast(float x) {

@@ -213,6 +213,10 @@ __device__ __forceinline__ void epilogue_loop(const GemmDev& p, uint64_t* acc_fu
               for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
             }
             if (!SIMPLE && p.out_fp32) {
+              if (p.tf32 == 2) {                        // the consumer is another tf32 product: round, do not truncate
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = round_tf32(v[j]);
+              }
               float* op = reinterpret_cast<float*>(p.out) + orow + coff;
               if (full) {
 #pragma unroll
@@ -433,7 +437,7 @@ struct PlainCfg {
   static constexpr int kThreads = 64 + 128 * kEpw;
 };
 
-template <int BN, int STAGES, bool GN, bool SIMPLE>
+template <int BN, int STAGES, bool GN, bool SIMPLE, bool TF32 = false>
 __global__ void __launch_bounds__(PlainCfg<BN, SIMPLE>::kThreads, BN == 256 ? 1 : 2)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                  const __grid_constant__ CUtensorMap map_b, const __grid_constant__ GemmDev p) {
@@ -525,7 +529,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
   } else if (warp == 1) {
     // =========================== MMA issuer (warp-uniform control flow, one elected lane issues)
     {
-      const uint32_t idesc = p.tf32 ? umma_idesc_tf32(kTileM, BN < 16 ? 16 : BN) : umma_idesc_bf16(kTileM, BN < 16 ? 16 : BN);
+      constexpr uint32_t idesc = TF32 ? umma_idesc_tf32(kTileM, BN < 16 ? 16 : BN) : umma_idesc_bf16(kTileM, BN < 16 ? 16 : BN);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -547,7 +551,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
 #pragma unroll
               for (int k = 0; k < kBlockK / 16; ++k) {
                 // advance 16 bf16 = 32 B along K inside the 128B swizzle row: +2 in (addr >> 4) units
-                if (p.tf32) umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                if (TF32) umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
                 else umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
               }
             }
@@ -696,7 +700,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
   } else if (warp == 1) {
     // =========================== MMA issuer (warp-uniform control flow, one elected lane issues)
     {
-      const uint32_t idesc = p.tf32 ? umma_idesc_tf32(kTileM, BN < 16 ? 16 : BN) : umma_idesc_bf16(kTileM, BN < 16 ? 16 : BN);
+      constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN < 16 ? 16 : BN);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const int row_shift = p.box[0] * 128;            // bytes between the A views of consecutive kernel rows
       if (RESB) {
@@ -727,8 +731,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                 const uint64_t db = umma_desc_sw128(sb);
 #pragma unroll
                 for (int k = 0; k < kBlockK / 16; ++k) {
-                  if (p.tf32) umma_tf32(tmem_d, da + 2 * k, db + 2 * k, idesc, acc);
-                  else umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, acc);
+                  umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, acc);
                   acc = 1;
                 }
               }
@@ -842,14 +845,14 @@ static int launch_halo(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUt
   return EXTDM_OK;
 }
 
-template <int BN, int STAGES, bool GN, bool SIMPLE>
+template <int BN, int STAGES, bool GN, bool SIMPLE, bool TF32 = false>
 static int launch(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb, GemmDev& dev, int m_tiles,
                   cudaStream_t stream) {
   constexpr int kStageBytes = kATileBytes + BN * kBlockK * 2;
   constexpr int smem_bytes = STAGES * kStageBytes + (2 * STAGES + 4) * 8 + 16 + 4096 + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, GN, SIMPLE>,
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, GN, SIMPLE, TF32>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) {
       extdm_set_error(cudaGetErrorString(e), __FILE__, __LINE__);
@@ -861,7 +864,7 @@ static int launch(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensor
   dev.total_tiles = m_tiles * dev.n_tiles_n;
   const int resident = sm_count() * (BN == 256 ? 1 : 2);
   const int grid = dev.total_tiles < resident ? dev.total_tiles : resident;
-  conv_gemm_kernel<BN, STAGES, GN, SIMPLE><<<grid, PlainCfg<BN, SIMPLE>::kThreads, smem_bytes, stream>>>(ma0, ma1, mb,
+  conv_gemm_kernel<BN, STAGES, GN, SIMPLE, TF32><<<grid, PlainCfg<BN, SIMPLE>::kThreads, smem_bytes, stream>>>(ma0, ma1, mb,
                                                                                                      dev);
   EXTDM_CHECK_LAUNCH();
   return EXTDM_OK;
@@ -948,7 +951,7 @@ extern "C" int extdm_conv_gemm(const ExtdmGemm* g, void* stream_) {
   static const bool halo_all = getenv("EXTDM_HALO_ALL") != nullptr;
   bool halo = kk && (simple || kk == 7) && !halo_off && !(kk == 7 && halo7_off) &&
               (halo_all || kk == 3 || dev.nk0 + dev.nk1 >= 2) && g->box[2] == 1 && g->box[3] == 1 && g->box[0] % 8 == 0 &&
-              (bn == 64 || bn == 128);
+              (bn == 64 || bn == 128) && !g->tf32;
   int ebox[4] = {g->box[0], g->box[1] + kk - 1, 1, 1};
   bool resb = false;
   int halo_smem = 0;
@@ -1021,6 +1024,18 @@ extern "C" int extdm_conv_gemm(const ExtdmGemm* g, void* stream_) {
       case 64: PLAIN(64, 4, true);
       case 128: PLAIN(128, 3, true);
       default: PLAIN(256, 4, true);
+    }
+  }
+  if (g->tf32) {                                        // fp32 operands (tf32 product), fp32 output: general epilogue
+    if (g->gn_partials || !g->out_fp32 || g->res || g->col_scale) {
+      extdm_set_error("extdm_conv_gemm: tf32 mode supports a bias / activation fp32 epilogue only", __FILE__, __LINE__);
+      return EXTDM_ERR_ARG;
+    }
+    switch (bn) {
+      case 16: return launch<16, 5, false, false, true>(ma0, ma1, mb, dev, m_tiles, stream);
+      case 64: return launch<64, 4, false, false, true>(ma0, ma1, mb, dev, m_tiles, stream);
+      case 128: return launch<128, 3, false, false, true>(ma0, ma1, mb, dev, m_tiles, stream);
+      default: return launch<256, 4, false, false, true>(ma0, ma1, mb, dev, m_tiles, stream);
     }
   }
   switch (bn) {

@@ -11,7 +11,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .diffusion import GaussianDiffusion
-from .lfae import BGMotionPredictor, Generator, RegionPredictor
+from .lfae import BGMotionPredictor, CondRunner, Generator, RegionPredictor
 from .unet import Unet3D
 
 _DEFAULT_UNET = {
@@ -23,6 +23,7 @@ _DEFAULT_UNET = {
 
 class FlowDiffusion(nn.Module):
     WRAPPER = "w_ref"            # "w_ref" | "multi1248" | "multi"
+    native_conditioning = True   # class-level switch: False runs the conditioning stage as torch modules (tests A/B)
 
     def __init__(self, config="", pretrained_pth="", is_train=True, ddim_sampling_eta=1.0, timesteps=1000,
                  dim_mults=None, learn_null_cond=False, use_deconv=True, padding_mode="zeros", withFea=True,
@@ -82,6 +83,9 @@ class FlowDiffusion(nn.Module):
             loss_type=diffusion_params["loss_type"], use_dynamic_thres=True,
             null_cond_prob=diffusion_params["null_cond_prob"], ddim_sampling_eta=ddim_sampling_eta).to(dev)
         self.cond_frame_num, self.pred_frame_num, self.frame_num = tc, tp, tc + tp
+        self._cond_runners = {}
+        for m in (self.generator, self.region_predictor, self.bg_predictor):
+            m.register_load_state_dict_post_hook(lambda mod, k: self._cond_runners.clear())
         self.is_train = is_train
         if is_train:
             raise NotImplementedError("training (FlowDiffusion.forward / p_losses) is outside the sampling hot path")
@@ -97,6 +101,47 @@ class FlowDiffusion(nn.Module):
         tp = self.pred_frame_num
         ref = real_vid[:, :, tc - 1]
         frames = real_vid.permute(0, 2, 1, 3, 4).reshape(B * tc, 3, H, W).contiguous(memory_format=torch.channels_last)
+        pfp = self.generator.pixelwise_flow_predictor
+        if real_vid.is_cuda and self.native_conditioning and not with_decode and \
+                CondRunner.supported(self.region_predictor, self.bg_predictor, pfp):
+            # (A) on the CUDA kernels: tf32 tcgen05 convolutions + fp32 element-wise kernels (lfae.CondRunner)
+            key = (real_vid.device, B, tc, H, W)
+            if key not in self._cond_runners:
+                self._cond_runners[key] = CondRunner(self.region_predictor, self.bg_predictor, pfp, real_vid.device,
+                                                     B, tc, H, W)
+            grid, conf = self._cond_runners[key].run(real_vid.float())
+            ret = {"real_vid_grid": grid.clone()}
+            if self.estimate_occlusion_map:
+                ret["real_vid_conf"] = conf.clone()
+            elif self.WRAPPER != "w_ref":
+                raise KeyError("occlusion_map")
+        else:
+            ret = self._condition_torch(real_vid, ref, frames, with_decode)
+        # bottleneck features: encoder of frames 0..tc-2, then the reference frame's repeated
+        enc_frames = self.generator.forward_bottle(frames).reshape(B, tc, 256, H // 4, W // 4)
+        ref_fea = enc_frames[:, tc - 1]
+        n_rep = (1 + tp) if self.WRAPPER == "w_ref" else tp
+        fea = torch.cat([enc_frames[:, :tc - 1], ref_fea[:, None].expand(B, n_rep, *ref_fea.shape[1:])], dim=1)
+        fea = fea.transpose(1, 2).contiguous()                                       # (B, 256, T', h, w)
+        if self.WRAPPER != "w_ref" and not fea.is_cuda:
+            # VideoFlowDiffusion_multi1248.py:243-245 resizes cond_fea to the flow resolution before the UNet.  On the
+            # CUDA path the UNet prologue does that resize itself (extdm_bilinear_resize_cl, align_corners=False like
+            # F.interpolate), so the features stay at H/4 here; this branch serves the CPU parity fixtures only.
+            n, c, t, h, w = fea.shape
+            hw = ret["real_vid_grid"].shape[-2:]
+            fea = F.interpolate(fea.transpose(1, 2).reshape(n * t, c, h, w), size=hw, mode="bilinear")
+            fea = fea.reshape(n, t, c, *hw).transpose(1, 2).contiguous()
+        grid = ret["real_vid_grid"]
+        if self.estimate_occlusion_map:
+            x_cond = torch.cat((grid, ret["real_vid_conf"] * 2 - 1), dim=1)
+        else:
+            x_cond = torch.cat((grid, torch.zeros_like(grid)[:, 0:1]), dim=1)
+        return ret, x_cond, fea, ref
+
+    def _condition_torch(self, real_vid, ref, frames, with_decode):
+        """The same stage as ordinary torch modules (cuDNN on a GPU): CPU parity fixtures, unsupported predictor
+        hyper-parameters, and the A/B partner of the native path in the tests."""
+        B, _, tc, H, W = real_vid.shape
         ref_rep = ref.repeat_interleave(tc, dim=0)
         src_params = self.region_predictor(ref)
         src_rep = {k: v.repeat_interleave(tc, dim=0) for k, v in src_params.items()}
@@ -119,26 +164,7 @@ class FlowDiffusion(nn.Module):
             full = self.generator(ref_rep, source_region_params=src_rep, driving_region_params=drv_params, bg_params=bg)
             ret["real_out_vid"] = per_frame(full["prediction"]).contiguous()
             ret["real_warped_vid"] = per_frame(full["deformed"]).contiguous()
-        # bottleneck features: encoder of frames 0..tc-2, then the reference frame's repeated
-        enc_frames = self.generator.forward_bottle(frames).reshape(B, tc, 256, H // 4, W // 4)
-        ref_fea = enc_frames[:, tc - 1]
-        n_rep = (1 + tp) if self.WRAPPER == "w_ref" else tp
-        fea = torch.cat([enc_frames[:, :tc - 1], ref_fea[:, None].expand(B, n_rep, *ref_fea.shape[1:])], dim=1)
-        fea = fea.transpose(1, 2).contiguous()                                       # (B, 256, T', h, w)
-        if self.WRAPPER != "w_ref" and not fea.is_cuda:
-            # VideoFlowDiffusion_multi1248.py:243-245 resizes cond_fea to the flow resolution before the UNet.  On the
-            # CUDA path the UNet prologue does that resize itself (extdm_bilinear_resize_cl, align_corners=False like
-            # F.interpolate), so the features stay at H/4 here; this branch serves the CPU parity fixtures only.
-            n, c, t, h, w = fea.shape
-            hw = ret["real_vid_grid"].shape[-2:]
-            fea = F.interpolate(fea.transpose(1, 2).reshape(n * t, c, h, w), size=hw, mode="bilinear")
-            fea = fea.reshape(n, t, c, *hw).transpose(1, 2).contiguous()
-        grid = ret["real_vid_grid"]
-        if self.estimate_occlusion_map:
-            x_cond = torch.cat((grid, ret["real_vid_conf"] * 2 - 1), dim=1)
-        else:
-            x_cond = torch.cat((grid, torch.zeros_like(grid)[:, 0:1]), dim=1)
-        return ret, x_cond, fea, ref
+        return ret
 
     # ------------------------------------------------------------------ full round
     @torch.no_grad()

@@ -558,3 +558,134 @@ class DecodeRunner:
 
     def run(self):
         self.rec.run()
+
+
+# =============================================================================================== CUDA conditioning
+_BG_TYPES = {"shift": 1, "affine": 2, "perspective": 3}
+
+
+def _pad32(c):
+    return (c + 31) // 32 * 32
+
+
+class CondRunner:
+    """The conditioning stage of FlowDiffusion.sample_one_video (VideoFlowDiffusion_multi_w_ref.py:231-262) for F = B*tc
+    frames on the CUDA kernels: RegionPredictor -> BGMotionPredictor -> PixelwiseFlowPredictor.
+
+    Convolutions run on the tcgen05 implicit GEMM in its tf32 mode (fp32 tensors, fp32 accumulate: the precision of the
+    reference's cuDNN path), everything else on the fp32 kernels of csrc/lfae_cond.cu.  The one library call left is
+    the batched 2x2 torch.svd of the region covariances: its sign convention is the reference's own
+    (region_predictor.py:130-136), a closed form would have to guess it.
+
+    The reference evaluates the region predictor twice on each video's last conditioning frame (once as `ref_img`,
+    once as driving frame tc-1, same weights, same input); here the source parameters are read from frame tc-1."""
+
+    @staticmethod
+    def supported(rp, bgp, pfp):
+        return (rp.pca_based and rp.jacobian is None and rp.scale_factor == pfp.scale_factor
+                and rp.scale_factor in (1, 0.5, 0.25) and pfp.use_deformed_source
+                and rp.regions.kernel_size == (7, 7) and rp.regions.padding[0] <= 3)
+
+    def __init__(self, rp, bgp, pfp, dev, B, tc, H, W):
+        self.recA, self.recB = ops.Recorder(record=True), ops.Recorder(record=True)
+        f32 = dict(device=dev, dtype=torch.float32)
+        buf = lambda *s: torch.empty(*s, **f32)
+        Fn = B * tc
+        self.frames = torch.zeros(Fn, 3, H, W, **f32)          # frame f = video f // tc, time f % tc
+        self.ref = torch.zeros(B, 3, H, W, **f32)
+        K = pfp.num_regions
+        st = int(round(1 / rp.scale_factor))
+        h, w = H // st, W // st
+        kern = rp.down.weight[0, 0].to(**f32).contiguous() if rp.scale_factor != 1 else None
+        # ---- region predictor
+        xd = buf(Fn, h, w, 32)
+        ops.image_to_cl(self.recA, self.frames, 1, xd, kern=kern, stride=st)
+        feat, xin = self._hourglass(self.recA, rp.predictor, xd, 3, buf)
+        be = feat.shape[-1]
+        wr = ops.pack_conv_weight_f32(rp.regions.weight.detach().to(**f32), splits=[(0, be, be), (be, be + 3, 32)])
+        logits = buf(Fn, h, w, 16 * ((K + 15) // 16))
+        ops.conv_cl_tf32(self.recA, feat, wr, K, 7, logits, x2=xin, bias=rp.regions.bias.detach().to(**f32).contiguous(),
+                         round_out=False)
+        self.shift, self.covar = torch.zeros(Fn, K, 2, **f32), torch.zeros(Fn, K, 2, 2, **f32)
+        self.affine = torch.zeros(Fn, K, 2, 2, **f32)
+        ops.region_moments(self.recA, logits, K, 3 - rp.regions.padding[0], float(rp.temperature), self.shift, self.covar)
+        # ---- background predictor (full resolution, [reference | frame] channels)
+        rec = self.recB
+        self.bg = None
+        if bgp.bg_type != "zero":
+            xb = buf(Fn, H, W, 32)
+            ops.image_to_cl(rec, self.ref, tc, xb, b=self.frames, b_div=1)
+            cur, ci, hh, ww = xb, 6, H, W
+            for blk in bgp.encoder.down_blocks:
+                cur = self._down(rec, blk, cur, ci, hh, ww, buf)
+                ci, hh, ww = cur.shape[-1], hh // 2, ww // 2
+            self.bg = torch.zeros(Fn, 3, 3, **f32)
+            ops.bg_head(rec, cur, bgp.fc.weight.detach().to(**f32).contiguous(),
+                        bgp.fc.bias.detach().to(**f32).contiguous(), _BG_TYPES[bgp.bg_type], self.bg)
+        # ---- pixel-wise flow predictor
+        cin = 4 * (K + 1)
+        cpad = _pad32(cin)
+        inp, self.motion = buf(Fn, h, w, cpad), buf(Fn, K + 1, h, w, 2)
+        ops.sparse_motion(rec, xd, self.shift, self.covar, self.affine, self.bg, tc, pfp.revert_axis_swap,
+                          pfp.use_covar_heatmap, float(pfp.region_var), inp, self.motion)
+        feat, xin = self._hourglass(rec, pfp.hourglass, inp, cin, buf)
+        be = feat.shape[-1]
+        heads = [pfp.mask] + ([pfp.occlusion] if pfp.occlusion is not None else [])
+        wh = torch.cat([m.weight.detach().to(**f32) for m in heads], 0)
+        bh = torch.cat([m.bias.detach().to(**f32) for m in heads], 0).contiguous()
+        whp = ops.pack_conv_weight_f32(wh, splits=[(0, be, be), (be, be + cin, cpad)])
+        head = buf(Fn, h, w, 16 * ((wh.shape[0] + 15) // 16))
+        ops.conv_cl_tf32(rec, feat, whp, wh.shape[0], 7, head, x2=xin, bias=bh, round_out=False)
+        self.grid = torch.zeros(B, 2, tc, h, w, **f32)
+        self.conf = torch.zeros(B, 1, tc, h, w, **f32) if pfp.occlusion is not None else None
+        ops.flow_compose(rec, head, self.motion, K, tc, self.grid, self.conf)
+
+    @staticmethod
+    def _folded(blk, dev):
+        w, b = _fold_bn(blk.conv.weight, blk.conv.bias, blk.norm)
+        return w.to(dev), b.to(dev).contiguous()
+
+    def _down(self, rec, blk, x, cin_real, hh, ww, buf):
+        """DownBlock2d: conv3x3 + BN(eval, folded) + ReLU + AvgPool2 (util.py:118-131)."""
+        w, b = self._folded(blk, x.device)
+        wp = ops.pack_conv_weight_f32(w, splits=[(0, cin_real, x.shape[-1])])
+        y = buf(x.shape[0], hh, ww, w.shape[0])
+        ops.conv_cl_tf32(rec, x, wp, w.shape[0], 3, y, bias=b, act=1)
+        p = buf(x.shape[0], hh // 2, ww // 2, w.shape[0])
+        ops.avgpool2_f32_cl(rec, y, p)
+        return p
+
+    def _hourglass(self, rec, hg, x, cin_real, buf):
+        """Hourglass.forward (util.py:152-221) on x (F, h, w, pad32(cin)).  Returns the two channel groups of its
+        output [last up-block (block_expansion) | x] un-concatenated: the consumer's convolution reads both."""
+        Fn, hh, ww, _ = x.shape
+        feats, cur, ci = [x], x, cin_real
+        for blk in hg.encoder.down_blocks:
+            cur = self._down(rec, blk, cur, ci, hh, ww, buf)
+            feats.append(cur)
+            ci, hh, ww = cur.shape[-1], hh // 2, ww // 2
+        out, skip = feats.pop(), None
+        for blk in hg.decoder.up_blocks:
+            w, b = self._folded(blk, x.device)
+            ua = buf(Fn, 2 * hh, 2 * ww, out.shape[-1])
+            ops.upsample2_f32_cl(rec, out, ua)
+            ub = None
+            if skip is not None:
+                ub = buf(Fn, 2 * hh, 2 * ww, skip.shape[-1])
+                ops.upsample2_f32_cl(rec, skip, ub)
+            hh, ww = 2 * hh, 2 * ww
+            y = buf(Fn, hh, ww, w.shape[0])
+            ops.conv_cl_tf32(rec, ua, ops.pack_conv_weight_f32(w), w.shape[0], 3, y, x2=ub, bias=b, act=1)
+            out, skip = y, feats.pop()
+        return out, skip
+
+    def run(self, real_vid):
+        """real_vid (B, 3, tc, H, W) fp32 on the device -> (grid (B,2,tc,h,w), conf (B,1,tc,h,w) | None)."""
+        B, _, tc, H, W = real_vid.shape
+        self.frames.view(B, tc, 3, H, W).copy_(real_vid.permute(0, 2, 1, 3, 4))
+        self.ref.copy_(real_vid[:, :, tc - 1])
+        self.recA.run()
+        u, s, _ = torch.svd(self.covar.view(-1, 2, 2))                     # region_predictor.py:130-136
+        self.affine.view(-1, 2, 2).copy_(u @ torch.diag_embed(s ** 0.5))
+        self.recB.run()
+        return self.grid, self.conf

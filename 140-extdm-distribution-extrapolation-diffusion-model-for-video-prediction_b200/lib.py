@@ -39,6 +39,13 @@ PROTOTYPES = {
     "extdm_last_error": [],
     "extdm_sizeof_gemm": [],
     "extdm_conv_gemm": [C.POINTER(ExtdmGemm), _P],
+    "extdm_image_to_cl": [_P, _I, _I, _P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _P],
+    "extdm_avgpool2_f32_cl": [_P, _P, _L, _I, _I, _I, _P],
+    "extdm_upsample2_f32_cl": [_P, _P, _L, _I, _I, _I, _P],
+    "extdm_region_moments": [_P, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P],
+    "extdm_sparse_motion": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _I, _P, _P],
+    "extdm_flow_compose": [_P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P],
+    "extdm_bg_head": [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P],
     "extdm_groupnorm_stats": [_P, _P, _I, _L, _I, _I, _P],
     "extdm_groupnorm_apply": [_P, _P, _I, _P, _P, _P, _L, _I, _P, _P, _I, _L, _I, _I, _F, _P],
     "extdm_chan_layernorm": [_P, _L, _I, _P, _L, _I, _P, _P, _L, _L, _F, _P],

@@ -239,19 +239,24 @@ def pack_conv_weight_f32(w, cin_pad=None, splits=None):
         blk = torch.zeros(co, kh, kw, cp, device=w.device, dtype=torch.float32)
         blk[..., : e - b] = w[:, b:e].permute(0, 2, 3, 1)
         parts.append(blk)
-    return torch.cat(parts, dim=3).reshape(co, -1).contiguous()
+    out = torch.cat(parts, dim=3).reshape(co, -1).contiguous()
+    # round to the nearest tf32 (the tensor core would truncate the low 13 mantissa bits)
+    bits = out.view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
-def conv_cl_tf32(rec, x, w, n, k, out, *, x2=None, bias=None, act=0, taps=None):
+def conv_cl_tf32(rec, x, w, n, k, out, *, x2=None, bias=None, act=0, taps=None, round_out=True):
     """k x k 'same' convolution of fp32 channels-last x (F, H, W, C) [| x2] in tf32 (fp32 accumulate), fp32 output
     (F, H, W, n') -- the LFAE conditioning convolutions (the reference's cuDNN path runs them in TF32 as well).
-    w: pack_conv_weight_f32 layout; channel counts are multiples of 32."""
+    w: pack_conv_weight_f32 layout; channel counts are multiples of 32.  round_out: the output feeds another tf32
+    convolution (stored rounded to tf32); False for the heads whose logits are consumed in fp32."""
     for t in (x, x2, w, out):
         if t is not None and t.dtype != torch.float32:
             raise ValueError("conv_cl_tf32: fp32 tensors expected")
-    v = lambda t: None if t is None else t.view(BF16).view(t.shape[0], 1, t.shape[1], t.shape[2], 2 * t.shape[3])
-    conv_cl(rec, v(x), w.view(BF16), n, k, out.view(out.shape[0], 1, *out.shape[1:]), x2=v(x2), bias=bias, act=act,
-            out_fp32=True, taps=taps, tf32=True)
+    # frames ride on the T axis so that one 128-row tile spans several small frames (the hourglass goes down to 1x1)
+    v = lambda t: None if t is None else t.view(BF16).view(1, t.shape[0], t.shape[1], t.shape[2], 2 * t.shape[3])
+    conv_cl(rec, v(x), w.view(BF16), n, k, out.view(1, *out.shape), x2=v(x2), bias=bias, act=act,
+            out_fp32=True, taps=taps, tf32=2 if round_out else 1)
 
 
 def conv_tiles_per_sample(T, H, W):
@@ -521,3 +526,53 @@ def cl_to_ncthw(rec, x, y):
     B, Cc = y.shape[:2]
     rest = y.numel() // (B * Cc)
     rec.emit("extdm_cl_to_ncthw", (_p(x), _p(y), B, Cc, rest, 1), keep=(x, y))
+
+
+# ----------------------------------------------------------------------------- LFAE conditioning stage (fp32)
+def image_to_cl(rec, a, a_div, out, *, b=None, b_div=1, kern=None, stride=1):
+    """NCHW fp32 image(s) -> (F, H/stride, W/stride, cpad) fp32 channels-last, optionally through the anti-alias filter."""
+    F_, h, w, cpad = out.shape
+    H, W = a.shape[2], a.shape[3]
+    ks = 1 if kern is None else kern.shape[-1]
+    rec.emit("extdm_image_to_cl", (_p(a), a.shape[1], a_div, _p(b) if b is not None else None,
+                                   0 if b is None else b.shape[1], b_div, _p(kern) if kern is not None else None, ks,
+                                   stride, _p(out), F_, H, W, cpad), keep=(a, b, kern, out), meta=dict(tag=f"{H}->{h}"))
+
+
+def avgpool2_f32_cl(rec, x, y):
+    F_, H, W, Cc = x.shape
+    rec.emit("extdm_avgpool2_f32_cl", (_p(x), _p(y), F_, H, W, Cc), keep=(x, y),
+             meta=dict(bytes=5.0 * y.numel() * 4))
+
+
+def upsample2_f32_cl(rec, x, y):
+    F_, H, W, Cc = x.shape
+    rec.emit("extdm_upsample2_f32_cl", (_p(x), _p(y), F_, H, W, Cc), keep=(x, y),
+             meta=dict(bytes=1.25 * y.numel() * 4))
+
+
+def region_moments(rec, logits, K, crop, temperature, shift, covar):
+    F_, h, w, ldc = logits.shape
+    rec.emit("extdm_region_moments", (_p(logits), ldc, F_, K, h, w, crop, C.c_float(temperature), _p(shift), _p(covar)),
+             keep=(logits, shift, covar))
+
+
+def sparse_motion(rec, src, shift, covar, affine, bg, tc, revert_axis_swap, use_covar, region_var, inp, motion):
+    F_, h, w, cpad = inp.shape
+    K = shift.shape[1]
+    rec.emit("extdm_sparse_motion", (_p(src), src.shape[-1], _p(shift), _p(covar), _p(affine),
+                                     _p(bg) if bg is not None else None, F_, K, tc, h, w, int(revert_axis_swap),
+                                     int(use_covar), C.c_float(region_var), _p(inp), cpad, _p(motion)),
+             keep=(src, shift, covar, affine, bg, inp, motion))
+
+
+def flow_compose(rec, head, motion, K, tc, grid, conf):
+    F_, h, w, ldc = head.shape
+    rec.emit("extdm_flow_compose", (_p(head), ldc, _p(motion), F_, K, tc, h, w, _p(grid),
+                                    _p(conf) if conf is not None else None), keep=(head, motion, grid, conf))
+
+
+def bg_head(rec, feat, fcw, fcb, bg_type, out):
+    F_, hh, ww, Cc = feat.shape
+    rec.emit("extdm_bg_head", (_p(feat), F_, hh * ww, Cc, _p(fcw), _p(fcb), fcw.shape[0], bg_type, _p(out)),
+             keep=(feat, fcw, fcb, out))

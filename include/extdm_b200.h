@@ -79,6 +79,8 @@ typedef struct ExtdmGemm {
    * reference's GPU convolutions run at (cudnn.allow_tf32 defaults to True, never changed by scripts/DM/valid.py).  All
    * channel counts, element strides and W's row pitch are then given in 2-byte units, i.e. twice the fp32 element
    * counts (an fp32 tensor of C channels is described exactly like a bf16 tensor of 2C channels; C % 32 == 0).
+   * 2: as 1, and the stored fp32 outputs are rounded to the nearest tf32 value (for outputs that feed another tf32
+   * product: the tensor core ignores the low 13 mantissa bits, rounding where a value is produced halves the error).
    * Used by the LFAE conditioning stage (region / background / flow predictors). */
   int tf32;
 } ExtdmGemm;
@@ -286,6 +288,40 @@ int extdm_im2col7_image(const float* img, void* a, long long F, int H, int W, vo
 /* Generic layout helpers. */
 int extdm_ncthw_to_cl(const float* x, void* y, int B, int C, long long T, long long HW, void* stream);
 int extdm_cl_to_ncthw(const void* x, float* y, int B, int C, long long T, long long HW, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LFAE conditioning stage: fp32 channels-last kernels around the tf32 convolutions
+ * (ExtdmGemm.tf32) of RegionPredictor / BGMotionPredictor / PixelwiseFlowPredictor.
+ */
+
+/* AntiAliasInterpolation2d (model/LFAE/util.py:224-271) + NCHW -> channels-last: out (F, H/stride, W/stride, cpad) fp32,
+ * channels [0, ca) from a[(f / a_div)], [ca, ca+cb) from b[(f / b_div)] (b may be NULL), the rest zero.  kern: ks*ks
+ * Gaussian taps (ks == 1: no filter). */
+int extdm_image_to_cl(const float* a, int ca, int a_div, const float* b, int cb, int b_div, const float* kern, int ks,
+                      int stride, float* out, int F, int H, int W, int cpad, void* stream);
+/* AvgPool2d(2) / nearest x2 up-sampling of (F, H, W, C) fp32 (DownBlock2d / UpBlock2d, util.py:97-131). */
+int extdm_avgpool2_f32_cl(const float* x, float* y, long long F, int H, int W, int C, void* stream);
+int extdm_upsample2_f32_cl(const float* x, float* y, long long F, int H, int W, int C, void* stream);
+/* RegionPredictor head, pca_based (region_predictor.py:95-140): logits (F, h, w, ldc) = 'same' 7x7 convolution output;
+ * softmax(logits / temperature) over the window cropped by `crop` = 3 - pad pixels per side; shift (F, K, 2), covar
+ * (F, K, 2, 2). */
+int extdm_region_moments(const float* logits, int ldc, int F, int K, int h, int w, int crop, float temperature,
+                         float* shift, float* covar, void* stream);
+/* PixelwiseFlowPredictor heat-maps + sparse motions + deformed sources (pixelwise_flow_predictor.py:48-112) for F = B*tc
+ * frames; source parameters / image are those of each video's last conditioning frame.  shift (F,K,2), covar / affine
+ * (F,K,2,2), bg (F,3,3) or NULL; src (F, h, w, src_ld) channels 0..2; inp (F, h, w, cpad) channel 4k + {0: heat, 1..3:
+ * warped source}; motion (F, K+1, h, w, 2). */
+int extdm_sparse_motion(const float* src, int src_ld, const float* shift, const float* covar, const float* affine,
+                        const float* bg, int F, int K, int tc, int h, int w, int revert_axis_swap, int use_covar,
+                        float region_var, float* inp, int cpad, float* motion, void* stream);
+/* mask softmax, flow = sum_k mask_k * motion_k, occlusion = sigmoid (pixelwise_flow_predictor.py:140-152).  head (F, h, w,
+ * ldc): channels [0, K] mask logits, K+1 occlusion logit.  grid (B, 2, tc, h, w), conf (B, 1, tc, h, w) or NULL. */
+int extdm_flow_compose(const float* head, int ldc, const float* motion, int F, int K, int tc, int h, int w, float* grid,
+                       float* conf, void* stream);
+/* BGMotionPredictor head (bg_motion_predictor.py:52-64): spatial mean of feat (F, hw, C), Linear(C -> n_out), 3x3 matrix.
+ * bg_type 1 shift (n_out 2), 2 affine (6), 3 perspective (8).  out (F, 3, 3). */
+int extdm_bg_head(const float* feat, int F, int hw, int C, const float* fcw, const float* fcb, int n_out, int bg_type,
+                  float* out, void* stream);
 
 #ifdef __cplusplus
 }
