@@ -178,7 +178,7 @@ def gemm(rec, *, a0, c0, dims, strides0, box, start, count, taps, w, n, out, out
     ktot = len(taps) * (c0 + (c1 if a1 is not None else 0))
     if tf32:
         ktot //= 2                                       # channel counts are in 2-byte units: K in fp32 elements
-    meta = dict(flops=2.0 * rows * n * ktot, rows=rows, n=n, k=ktot, taps=len(taps),
+    meta = dict(flops=2.0 * rows * n * ktot, rows=rows, n=n, k=ktot, taps=len(taps), tf32=bool(tf32),
                 bytes=2.0 * rows * (c0 + (c1 if a1 is not None else 0)) + 2.0 * n * ktot
                 + rows * n * (4.0 if out_fp32 else 2.0))
     rec.emit("extdm_conv_gemm", (C.byref(g),), keep=(g, a0, a1, w, out, bias, res, col_scale, col_shift, gn_partials),

@@ -224,15 +224,21 @@ def main():
     dec = model.generator.decoder(B, tc + tp, 64, 64, 32, 32, True)
     n_rounds = math.ceil(total_pred / tp)
     n_ddim = model.diffusion.sampling_timesteps
-    launches_per_round = len(runner.prologue) + n_ddim * (len(runner.step) + 2) + len(dec.rec)
+    # conditioning stage (region / background / flow predictors + the cond_fea encoder), once per round
+    cond_recs = [r_ for cr in model._cond_runners.values() for r_ in (cr.recA, cr.recB)]
+    cond_recs += [r_.rec for k_, r_ in model.generator._runners.items() if k_[0] == "enc"]
+    launches_per_round = len(runner.prologue) + n_ddim * (len(runner.step) + 2) + len(dec.rec) + \
+        sum(len(r_) for r_ in cond_recs)
     gpu_launches = launches_per_round * n_rounds * args.steps
     peaks = load_peaks()
     table = {}
     top = None
-    for rec_, mult in ((runner.prologue, 1), (runner.step, n_ddim), (dec.rec, 1)):
+    for rec_, mult in [(runner.prologue, 1), (runner.step, n_ddim), (dec.rec, 1)] + [(r_, 1) for r_ in cond_recs]:
         rec_.run()
         torch.cuda.synchronize()
         for name, meta, ms in rec_.run_timed():
+            if meta.get("tf32"):
+                name += "[tf32]"                          # the conditioning convolutions: fp32 operands, kind::tf32
             t = table.setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
             t["ms"] += ms * mult
             t["flops"] += meta.get("flops", 0.0) * mult
@@ -252,8 +258,15 @@ def main():
     # one C-ABI entry point): `achieved` is algorithmic FLOPs of ALL its launches in a round over their summed
     # CUDA-event durations; `top_launch` is its single most expensive shape; `other_kernels` are the HBM-bound ones.
     others = {}
+    if "extdm_conv_gemm[tf32]" in table:
+        t = table["extdm_conv_gemm[tf32]"]
+        tf = t["flops"] / (t["ms"] * 1e-3) / 1e12
+        others["extdm_conv_gemm[tf32]"] = {"bound": "tensor", "achieved": tf, "peak": peak_tf / 2, "unit": "TFLOP/s",
+                                           "frac": tf / (peak_tf / 2), "peak_source": "half the measured bf16 peak "
+                                           "(tf32 runs at half the bf16 rate)",
+                                           "share_of_kernel_time": t["ms"] / total_kernel_ms}
     for name, t in table.items():
-        if name != "extdm_conv_gemm" and t["bytes"] > 0:
+        if not name.startswith("extdm_conv_gemm") and t["bytes"] > 0:
             gbs = t["bytes"] / (t["ms"] * 1e-3) / 1e9
             others[name] = {"bound": "hbm", "achieved": gbs, "peak": peak_bw, "unit": "GB/s", "frac": gbs / peak_bw,
                             "share_of_kernel_time": t["ms"] / total_kernel_ms}

@@ -22,7 +22,9 @@ runner = next(iter(model.unet._runners.values()))
 dec = next(r for k, r in model.generator._runners.items() if k[0] != "enc")
 steps = cfg["diffusion_params"]["model_params"]["sampling_timesteps"]
 rows = {}
-for label, rec, mult in (("prologue", runner.prologue, 1), ("step", runner.step, steps), ("decode", dec.rec, 1)):
+cond = [("cond", r_, 1) for cr in model._cond_runners.values() for r_ in (cr.recA, cr.recB)]
+cond += [("cond", r_.rec, 1) for k_, r_ in model.generator._runners.items() if k_[0] == "enc"]
+for label, rec, mult in [("prologue", runner.prologue, 1), ("step", runner.step, steps), ("decode", dec.rec, 1)] + cond:
     rec.run()
     torch.cuda.synchronize()
     best = None
@@ -31,7 +33,8 @@ for label, rec, mult in (("prologue", runner.prologue, 1), ("step", runner.step,
         best = cur if best is None else [(n, m, min(t, t2)) for (n, m, t), (_, _, t2) in zip(best, cur)]
     for name, meta, ms in best:
         if name == "extdm_conv_gemm":
-            key = (label, f"gemm rows={meta['rows']} n={meta['n']} k={meta['k']} taps={meta['taps']}")
+            key = (label, f"gemm{'[tf32]' if meta.get('tf32') else ''} rows={meta['rows']} n={meta['n']} k={meta['k']} "
+                          f"taps={meta['taps']}")
         else:
             key = (label, name.replace("extdm_", "") + (" " + meta["tag"] if "tag" in meta else ""))
         r = rows.setdefault(key, dict(ms=0.0, n=0, flops=0.0, bytes=0.0))
