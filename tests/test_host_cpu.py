@@ -93,7 +93,7 @@ def test_c_abi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(cdll, name), f"{name} declared in the header but not exported"
     assert declared == set(lib.PROTOTYPES), declared ^ set(lib.PROTOTYPES)
-    assert lib.load().extdm_abi_version() == 2
+    assert lib.load().extdm_abi_version() == 3
     assert ctypes.sizeof(lib.ExtdmGemm) == lib.load().extdm_sizeof_gemm()
 
 
@@ -170,3 +170,45 @@ def test_result_wire_format(tmp_path):
     del sd[k]
     with pytest.raises(RuntimeError):
         evaluate.load_dm_checkpoint(fd, {"diffusion": sd})
+
+
+def test_pack_weights_conv3d_and_tf32():
+    """Host-side packing for the 27-tap extrapolator convolution (ada_u22) and for the tf32 GEMM mode: the packed
+    matrices reproduce F.conv3d / F.conv2d when contracted against explicitly gathered taps."""
+    import torch.nn.functional as F
+    from extdm_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    # ---- 3x3x3: K index ((kt*3 + ky)*3 + kx)*Cin + ci, taps in the same order
+    w = torch.randn(4, 3, 3, 3, 3, generator=g)
+    x = torch.randn(1, 3, 5, 6, 7, generator=g)
+    ref = F.conv3d(x, w, padding=1)
+    wp = ops.pack_conv3d_weight(w).float()                           # bf16-rounded
+    taps = ops.conv3d_taps(3)
+    assert len(taps) == 27 and taps[0] == (-1, -1, -1) and taps[13] == (0, 0, 0) and taps[-1] == (1, 1, 1)
+    xp = F.pad(x, (1, 1, 1, 1, 1, 1))
+    cols = torch.cat([xp[0, :, 1 + dt:6 + dt, 1 + dy:7 + dy, 1 + dx:8 + dx] for dx, dy, dt in taps], dim=0)  # (27*3,T,H,W)
+    got = torch.einsum("ok,kthw->othw", wp, cols)
+    assert (got - ref[0]).abs().max() <= 2e-2 * ref.abs().max()
+    # ---- tf32 packing: channel groups zero-padded to multiples of 32, values rounded to the nearest tf32
+    w2 = torch.randn(5, 35, 3, 3, generator=g)
+    p2 = ops.pack_conv_weight_f32(w2, splits=[(0, 32, 32), (32, 35, 32)])
+    assert p2.shape == (5, 9 * 64)
+    v = p2.view(5, 3, 3, 64)
+    assert torch.count_nonzero(v[..., 35:]) == 0
+    assert (v[..., :32] - w2[:, :32].permute(0, 2, 3, 1)).abs().max() <= 2.0 ** -11 * w2.abs().max()
+    assert (v[..., 32:35] - w2[:, 32:].permute(0, 2, 3, 1)).abs().max() <= 2.0 ** -11 * w2.abs().max()
+    assert (p2.view(torch.int32) & 0x1FFF).abs().max() == 0          # low 13 mantissa bits cleared = exact tf32 values
+
+
+def test_wrapper_registry():
+    """`--DM_arch` / `--Unet3D_arch` strings of the reference's scripts map to classes / variants (valid.py:83-99)."""
+    from extdm_b200 import flow_diffusion_class
+    from extdm_b200.flow_diffusion import FlowDiffusion, FlowDiffusionU22
+    from extdm_b200.manifest import UNET_ARCHITECTURES, UnetConfig
+    assert flow_diffusion_class("VideoFlowDiffusion_multi_w_ref") is FlowDiffusion
+    assert flow_diffusion_class("VideoFlowDiffusion_multi_w_ref_u22") is FlowDiffusionU22
+    with pytest.raises(NotImplementedError):
+        flow_diffusion_class("VideoFlowDiffusion_nope")
+    assert UNET_ARCHITECTURES["DenoiseNet_STWAtt_w_w_ref_adaptor_cross_multi_traj_ada_u22"] == "u22"
+    c = UnetConfig("u22", 2, 5)
+    assert (c.window, c.dim_head, c.channels, c.resample_slot, c.extrap_kt) == ((4, 4, 4), 32, 259, 6, 3)
