@@ -147,6 +147,9 @@ def main():
     ap.add_argument("--batch", type=int, default=WORKLOAD["batch_per_gpu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-kernels", action="store_true", help="also print the per-kernel time table")
+    ap.add_argument("--ncu-range", action="store_true",
+                    help="for `ncu --profile-from-start off`: after the warm-up, bracket ONE step with "
+                         "cudaProfilerStart/Stop and exit without printing a bench line")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -208,6 +211,14 @@ def main():
 
     for _ in range(max(args.warmup, 3)):
         step(False)
+    if args.ncu_range:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step(False)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        sys.stderr.write("ncu range done (no bench value is reported from a profiled run)\n")
+        return
     step(True)
     clocks = ClockSampler(local)
     if rank == 0:

@@ -16,7 +16,7 @@ for r in csv.DictReader(lines):
 
 
 def short(name):
-    name = re.sub(r"^void\s+", "", name)
+    name = re.sub(r"^void\s+", "", name).replace("<unnamed>::", "").replace("(anonymous namespace)::", "")
     m = re.match(r"(extdm::)?([A-Za-z0-9_]+)(<[^>]*>)?", name)
     if name.startswith("extdm::") and m:
         return "extdm::" + m.group(2) + (m.group(3) or "")
