@@ -35,4 +35,27 @@ def smoke():
     rel = ((out - ref).norm() / ref.norm()).item()
     print(f"[smoke] DDIM(2 steps) UNet3D 'ada' tc={tc} tp={tp}: rel-L2 vs oracle = {rel:.3e}")
     assert rel < 3e-2, rel
+
+    # ---- decode: Generator.forward_with_flow (warp / occlusion blend / conv decoder) on the same latent flow
+    from . import configs
+    from .lfae import Generator
+    fp = configs.dataset("kth")[0]["flow_params"]["model_params"]
+    gen = Generator(num_regions=fp["num_regions"], num_channels=3, revert_axis_swap=True, **fp["generator_params"]).eval()
+    base = gen.state_dict()
+    gsd = synth_state_dict({k: tuple(v.shape) for k, v in base.items()}, seed=21, base=base)
+    gen.load_state_dict(gsd)
+    gen = gen.cuda()
+    src = torch.rand(B, 3, 64, 64, generator=g)
+    ident = torch.stack(torch.meshgrid(torch.linspace(-1, 1, 32), torch.linspace(-1, 1, 32), indexing="xy"), -1)
+    flow = ident[None] + 0.1 * out[:, :2, 0].permute(0, 2, 3, 1).clamp(-1, 1)
+    occ = ((out[:, 2:3, 0] + 1) * 0.5).clamp(0, 1)
+    got = gen.forward_with_flow(src.cuda(), flow.cuda(), occ.cuda())
+    with torch.no_grad():
+        want = O.generator_forward_with_flow(O.SD(gsd), src, flow, occ)
+    mse = ((got["prediction"].cpu() - want["prediction"]) ** 2).mean().item()
+    warp_err = (got["deformed"].cpu() - want["deformed"]).abs().max().item()
+    import math
+    psnr = 99.0 if mse == 0 else 10 * math.log10(1.0 / mse)
+    print(f"[smoke] forward_with_flow 64x64: decoded frame PSNR vs oracle = {psnr:.1f} dB, warped image max-abs {warp_err:.1e}")
+    assert psnr >= 35.0 and warp_err <= 2e-5, (psnr, warp_err)
     return rel

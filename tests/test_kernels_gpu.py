@@ -609,3 +609,137 @@ def test_conv_tf32_matches_torch(F_, H, W, c0, c1, n, k):
     got = out[..., :n].permute(0, 3, 1, 2).cpu()
     err = (got - ref).abs().max().item() / ref.abs().max().item()
     assert err <= 2e-3, err
+
+
+# ----------------------------------------------------------------------------- LFAE conditioning kernels (fp32)
+def _tf32_round(t):
+    return ((t.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scale", [0.5, 0.25, 1])
+def test_image_to_cl_matches_antialias(scale):
+    """AntiAliasInterpolation2d (util.py:224-271) + NCHW -> channels-last, two concatenated sources, frame divisors."""
+    from extdm_b200.lfae import AntiAliasDown
+    g = torch.Generator().manual_seed(3)
+    a, b = torch.rand(2, 3, 32, 32, generator=g), torch.rand(6, 3, 32, 32, generator=g)
+    down = AntiAliasDown(3, scale)
+    st = int(round(1 / scale))
+    ref = torch.cat([down(a).repeat_interleave(3, 0), down(b)], 1).permute(0, 2, 3, 1)       # frame f <- a[f // 3]
+    out = torch.full((6, 32 // st, 32 // st, 32), 7.0, device="cuda")
+    kern = down.weight[0, 0].contiguous().cuda() if scale != 1 else None
+    ops.image_to_cl(ops.IMMEDIATE, a.cuda(), 3, out, b=b.cuda(), b_div=1, kern=kern, stride=st)
+    torch.cuda.synchronize()
+    assert torch.count_nonzero(out[..., 6:]) == 0
+    assert (out[..., :6].cpu() - ref).abs().max().item() <= 2.0 ** -10          # stored rounded to tf32
+
+
+@pytest.mark.gpu
+def test_pool_upsample_f32():
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(5, 6, 8, 32, generator=g)
+    xc = x.cuda()
+    y = torch.empty(5, 3, 4, 32, device="cuda")
+    ops.avgpool2_f32_cl(ops.IMMEDIATE, xc, y)
+    ref = F.avg_pool2d(x.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+    assert (y.cpu() - ref).abs().max().item() <= 2.0 ** -10 * ref.abs().max().item()
+    u = torch.empty(5, 12, 16, 32, device="cuda")
+    ops.upsample2_f32_cl(ops.IMMEDIATE, xc, u)
+    torch.cuda.synchronize()
+    assert torch.equal(u.cpu(), F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2).permute(0, 2, 3, 1))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("crop", [3, 0])
+def test_region_moments_matches_torch(crop):
+    """RegionPredictor head, pca_based (region_predictor.py:95-140): softmax / temperature, shift, covariance."""
+    from extdm_b200.lfae import coordinate_grid
+    g = torch.Generator().manual_seed(5)
+    Fn, K, h, w, ldc, T = 3, 10, 32, 32, 16, 0.1
+    logits = torch.randn(Fn, h, w, ldc, generator=g) * 0.3
+    shift, covar = torch.zeros(Fn, K, 2, device="cuda"), torch.zeros(Fn, K, 2, 2, device="cuda")
+    ops.region_moments(ops.IMMEDIATE, logits.cuda(), K, crop, T, shift, covar)
+    torch.cuda.synchronize()
+    lg = logits[..., :K].permute(0, 3, 1, 2)[:, :, crop:h - crop, crop:w - crop]
+    hh, ww = lg.shape[2:]
+    heat = F.softmax(lg.reshape(Fn, K, -1) / T, dim=2).reshape(Fn, K, hh, ww).unsqueeze(-1)
+    grid = coordinate_grid(hh, ww, heat)[None, None]
+    rs = (heat * grid).sum(dim=(2, 3))
+    d = grid - rs[:, :, None, None, :]
+    rc = (d.unsqueeze(-1) * d.unsqueeze(-2) * heat.unsqueeze(-1)).sum(dim=(2, 3))
+    assert (shift.cpu() - rs).abs().max().item() <= 2e-5
+    assert (covar.cpu() - rc).abs().max().item() <= 2e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("use_covar,with_bg", [(True, True), (False, False)])
+def test_sparse_motion_and_flow_compose_match_torch(use_covar, with_bg):
+    """Heat-maps, sparse motions, deformed sources and the mask-softmax flow of PixelwiseFlowPredictor
+    (pixelwise_flow_predictor.py:48-153) against the torch restatement in extdm_b200.lfae."""
+    from extdm_b200 import lfae
+    g = torch.Generator().manual_seed(6)
+    B, tc, K, h, w = 2, 3, 10, 16, 16
+    Fn = B * tc
+    img = torch.rand(Fn, 3, h, w, generator=g)                                   # already down-sampled frames
+    shift = torch.rand(Fn, K, 2, generator=g) - 0.5
+    m = torch.randn(Fn, K, 2, 2, generator=g) * 0.2 + torch.eye(2) * 0.5
+    covar = m @ m.transpose(-1, -2) * 0.05 + torch.eye(2) * 0.01
+    affine = torch.randn(Fn, K, 2, 2, generator=g) * 0.2 + torch.eye(2)
+    bg = torch.eye(3).repeat(Fn, 1, 1)
+    bg[:, :2] += torch.randn(Fn, 2, 3, generator=g) * 0.05
+    src_of = torch.arange(Fn) // tc * tc + tc - 1
+    # ---- torch side: the module's forward up to the hourglass input, re-using its helpers
+    pfp = lfae.PixelwiseFlowPredictor(block_expansion=8, num_blocks=2, max_features=16, num_regions=K, num_channels=3,
+                                      estimate_occlusion_map=True, scale_factor=1, use_covar_heatmap=use_covar,
+                                      revert_axis_swap=True)
+    captured = {}
+    pfp.hourglass.register_forward_pre_hook(lambda mod, args: captured.setdefault("inp", args[0]))
+    drv = {"shift": shift, "covar": covar, "affine": affine}
+    src = {k: v[src_of] for k, v in drv.items()}
+    with torch.no_grad():
+        pfp(source_image=img[src_of], driving_region_params=drv, source_region_params=src,
+            bg_params=bg if with_bg else None)
+    ref_inp = captured["inp"].permute(0, 2, 3, 1)                                # (F, h, w, 4(K+1))
+    # ---- kernel
+    xd = torch.zeros(Fn, h, w, 32, device="cuda")
+    xd[..., :3] = img.permute(0, 2, 3, 1).cuda()
+    cpad = 64
+    inp, motion = torch.empty(Fn, h, w, cpad, device="cuda"), torch.empty(Fn, K + 1, h, w, 2, device="cuda")
+    ops.sparse_motion(ops.IMMEDIATE, xd, shift.cuda(), covar.cuda(), affine.cuda(), bg.cuda() if with_bg else None, tc,
+                      True, use_covar, 0.01, inp, motion)
+    torch.cuda.synchronize()
+    assert torch.count_nonzero(inp[..., 4 * (K + 1):]) == 0
+    assert (inp[..., :4 * (K + 1)].cpu() - ref_inp).abs().max().item() <= 2e-3   # tf32-rounded storage of O(1) values
+    # ---- flow composition from random head logits and the kernel's own motions
+    head = torch.randn(Fn, h, w, 16, generator=g)
+    grid, conf = torch.empty(B, 2, tc, h, w, device="cuda"), torch.empty(B, 1, tc, h, w, device="cuda")
+    ops.flow_compose(ops.IMMEDIATE, head.cuda(), motion, K, tc, grid, conf)
+    torch.cuda.synchronize()
+    mask = F.softmax(head[..., :K + 1], dim=-1)                                  # (F, h, w, K+1)
+    mo = motion.cpu().permute(0, 2, 3, 1, 4)                                     # (F, h, w, K+1, 2)
+    flow = (mo * mask.unsqueeze(-1)).sum(3)                                      # (F, h, w, 2)
+    ref_grid = flow.reshape(B, tc, h, w, 2).permute(0, 4, 1, 2, 3)
+    ref_conf = torch.sigmoid(head[..., K + 1]).reshape(B, 1, tc, h, w)
+    assert (grid.cpu() - ref_grid).abs().max().item() <= 2e-5 * (1.0 + ref_grid.abs().max().item())
+    assert (conf.cpu() - ref_conf).abs().max().item() <= 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bg_type,n_out", [("affine", 6), ("perspective", 8), ("shift", 2)])
+def test_bg_head_matches_torch(bg_type, n_out):
+    g = torch.Generator().manual_seed(8)
+    Fn, Cc = 5, 128
+    feat = torch.randn(Fn, 2, 2, Cc, generator=g)
+    fcw, fcb = torch.randn(n_out, Cc, generator=g) * 0.1, torch.randn(n_out, generator=g) * 0.1
+    out = torch.empty(Fn, 3, 3, device="cuda")
+    ops.bg_head(ops.IMMEDIATE, feat.cuda(), fcw.cuda(), fcb.cuda(), {"shift": 1, "affine": 2, "perspective": 3}[bg_type], out)
+    torch.cuda.synchronize()
+    p = F.linear(feat.mean(dim=(1, 2)), fcw, fcb)
+    ref = torch.eye(3).repeat(Fn, 1, 1)
+    if bg_type == "shift":
+        ref[:, :2, 2] = p
+    else:
+        ref[:, :2, :] = p[:, :6].view(Fn, 2, 3)
+        if bg_type == "perspective":
+            ref[:, 2, :2] = p[:, 6:]
+    assert (out.cpu() - ref).abs().max().item() <= 1e-5
