@@ -594,9 +594,9 @@ int extdm_stw_tc_launch(const void* x, void* y, const float* gamma, const void* 
     cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
     cudaMemcpyFromSymbol(h, g_stw_prof, sizeof(h));
     const double n = h[7] ? static_cast<double>(h[7]) : 1.0;
-    fprintf(stderr, "[stw_tc prof] B=%d T=%d H=%d W=%d shift=%d pairs/CTA=%.0f cycles/pair: qkv_wait %.0f drainKV+ln %.0f proj_wait %.0f "
-            "drainQ+epi %.0f S3 %.0f attn %.0f S4 %.0f issue %.0f\n", B, T, H, W, sd | sh | sw, n, h[0] / n, h[1] / n,
-            h[2] / n, h[3] / n, h[4] / n, h[5] / n, h[6] / n, 0.0);
+    fprintf(stderr, "[stw_tc prof] B=%d T=%d H=%d W=%d shift=%d pairs/CTA=%.0f cycles/pair: masks+qkv_wait %.0f drainKV+ln %.0f "
+            "proj_wait %.0f drainQ+epilogue+S3 %.0f attention(+issue qkv) %.0f S4 %.0f issue_proj %.0f\n", B, T, H, W, sd | sh | sw, n, h[0] / n, h[1] / n,
+            h[2] / n, h[3] / n, h[4] / n, h[5] / n, h[6] / n);
   }
   EXTDM_CHECK_LAUNCH();
   return EXTDM_OK;
