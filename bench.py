@@ -281,6 +281,10 @@ def main():
             gbs = t["bytes"] / (t["ms"] * 1e-3) / 1e9
             others[name] = {"bound": "hbm", "achieved": gbs, "peak": peak_bw, "unit": "GB/s", "frac": gbs / peak_bw,
                             "share_of_kernel_time": t["ms"] / total_kernel_ms}
+            if name in ("extdm_stw_fused", "extdm_temporal_fused", "extdm_window_attention"):
+                # fused attention layers: the HBM figure is their algorithmic traffic (read x, write y) over time; what
+                # limits them is instruction issue + MUFU in the score / softmax phase
+                others[name]["limited_by"] = "instruction issue / MUFU (softmax), not HBM"
     roofline = {
         "bound": "tensor", "kernel": "extdm_conv_gemm (tcgen05 implicit GEMM: conv_gemm_kernel / conv_halo_kernel), all "
                                      f"{gemm['n']} launches of one round",
