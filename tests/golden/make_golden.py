@@ -36,6 +36,10 @@ UNET_CASES = {
     "unet_u12_c2p3": ("u12", 2, 3, (1, 2, 4, 4), 1),
     "unet_base_c3p2": ("base", 3, 2, (1, 2, 4, 8), 1),
     "unet_u22_c2p5": ("u22", 2, 5, (1, 2, 4, 4), 1),
+    # the shipped (tc, tp) of the benchmark configurations: KTH, BAIR, SMMNIST
+    "unet_ada_c10p20": ("ada", 10, 20, (1, 2, 4, 4), 1),
+    "unet_u12_c2p10": ("u12", 2, 10, (1, 2, 4, 4), 1),
+    "unet_base_c10p5": ("base", 10, 5, (1, 2, 4, 8), 1),
 }
 
 

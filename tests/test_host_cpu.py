@@ -19,7 +19,10 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 @pytest.mark.parametrize("name,variant,tc,tp,dm", [("unet_ada_c2p5", "ada", 2, 5, (1, 2, 4, 4)),
                                                    ("unet_u12_c2p3", "u12", 2, 3, (1, 2, 4, 4)),
                                                    ("unet_base_c3p2", "base", 3, 2, (1, 2, 4, 8)),
-                                                   ("unet_u22_c2p5", "u22", 2, 5, (1, 2, 4, 4))])
+                                                   ("unet_u22_c2p5", "u22", 2, 5, (1, 2, 4, 4)),
+                                                   ("unet_ada_c10p20", "ada", 10, 20, (1, 2, 4, 4)),
+                                                   ("unet_u12_c2p10", "u12", 2, 10, (1, 2, 4, 4)),
+                                                   ("unet_base_c10p5", "base", 10, 5, (1, 2, 4, 8))])
 def test_unet_manifest_matches_reference(name, variant, tc, tp, dm):
     fx = torch.load(os.path.join(GOLD, name + ".pt"))
     ref = {k: tuple(v) for k, v in fx["manifest"].items()}

@@ -54,7 +54,8 @@ def build_unet(fx):
     return u, sd
 
 
-@pytest.mark.parametrize("name", ["unet_ada_c2p5", "unet_base_c3p2", "unet_u12_c2p3", "unet_u22_c2p5"])
+@pytest.mark.parametrize("name", ["unet_ada_c2p5", "unet_base_c3p2", "unet_u12_c2p3", "unet_u22_c2p5",
+                                  "unet_ada_c10p20", "unet_u12_c2p10", "unet_base_c10p5"])
 def test_unet_forward_matches_reference(name):
     fx = torch.load(os.path.join(GOLD, name + ".pt"))
     u, _ = build_unet(fx)

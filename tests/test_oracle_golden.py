@@ -25,7 +25,7 @@ def unet_inputs(variant, tc, tp, B, seed):
                 time=torch.full((B,), 545, dtype=torch.long))
 
 
-@pytest.mark.parametrize("name", ["unet_ada_c2p5", "unet_u12_c2p3", "unet_base_c3p2", "unet_u22_c2p5"])
+@pytest.mark.parametrize("name", ["unet_ada_c2p5", "unet_u12_c2p3", "unet_base_c3p2", "unet_u22_c2p5", "unet_ada_c10p20"])
 def test_unet_forward(name):
     torch.set_num_threads(8)
     fx = torch.load(os.path.join(GOLD, name + ".pt"))
