@@ -42,6 +42,10 @@ _DATASETS = {
             "DenoiseNet_STWAtt_w_w_ref_adaptor_cross_multi_traj_ada"),
     "cityscapes": (_config(128, 2, 5, 28, num_regions=20, scale_factor=0.25, bg_type="perspective"),
                    "VideoFlowDiffusion_multi_w_ref", "DenoiseNet_STWAtt_w_w_ref_adaptor_cross_multi_traj_ada"),
+    # BASELINE.json words Cityscapes as 64x64: the shipped scale_factor 0.25 cannot run at 64 (the 5-block hourglass
+    # would reach 16 -> 0), so the 64x64 variant uses scale_factor 0.5 like BAIR
+    "cityscapes64": (_config(64, 2, 5, 28, num_regions=20, scale_factor=0.5, bg_type="perspective"),
+                     "VideoFlowDiffusion_multi_w_ref", "DenoiseNet_STWAtt_w_w_ref_adaptor_cross_multi_traj_ada"),
     # the pairing the reference's valid_DM_cityscapes.sh:8-9 names
     "cityscapes_u22": (_config(128, 2, 5, 28, num_regions=20, scale_factor=0.25, bg_type="perspective"),
                        "VideoFlowDiffusion_multi_w_ref_u22",

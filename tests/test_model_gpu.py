@@ -209,7 +209,7 @@ def test_pipeline_matches_reference(request):
 
 
 @pytest.mark.parametrize("name,B", [("smmnist", 1), ("bair", 2), ("ucf", 2), ("cityscapes", 1), ("kth", 1),
-                                    ("cityscapes_u22", 1)])
+                                    ("cityscapes_u22", 1), ("cityscapes64", 2)])
 def test_every_dataset_config_samples(name, B):
     """Every configuration BASELINE.json names builds and runs one sample_one_video round on the CUDA path:
     output shapes as the reference's, finite values, frames in [0, 1]."""

@@ -14,7 +14,7 @@ import torch  # noqa: E402
 import extdm_b200  # noqa: E402,F401
 from extdm_b200 import configs  # noqa: E402
 
-names = sys.argv[1:] or ["kth", "bair", "smmnist", "ucf", "cityscapes", "cityscapes_u22"]
+names = sys.argv[1:] or ["kth", "bair", "smmnist", "ucf", "cityscapes", "cityscapes64", "cityscapes_u22"]
 B = int(os.environ.get("EXTDM_BENCH_BATCH", "32"))
 print("| config | UNet | tc -> total | rounds | batch | ms / rollout | predicted frames/s |")
 print("|---|---|---|---|---|---|---|")
