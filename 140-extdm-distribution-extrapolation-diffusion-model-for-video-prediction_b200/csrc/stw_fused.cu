@@ -100,7 +100,7 @@ struct StwSmem {
 //   z = chanLN(x); u = LayerNorm(z); y = x + z + to_out(attn(u)), rotary over the frame index, T5 relative-position
 //   bias (heads, 2T-1) in p.bias_table, no projection bias; key slots >= T are masked out.
 template <int NTOK, int DH, int C, bool TEMPORAL>
-__global__ void __launch_bounds__(256, TEMPORAL ? 2 : 1) stw_fused_kernel(const __grid_constant__ StwParams p) {
+__global__ void __launch_bounds__(256, (TEMPORAL && DH == 16) ? 2 : 1) stw_fused_kernel(const __grid_constant__ StwParams p) {
   using L = StwSmem<NTOK, DH, C>;
   constexpr int HEADS = 8, HID = L::HID, XP = L::XP, HP = L::HP, BP = L::BP;
   constexpr int WD = NTOK / 16;          // window = (WD, 4, 4)
@@ -514,7 +514,7 @@ static int launch_stw(const StwParams& p, cudaStream_t st) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const int resident = sms * (TEMPORAL ? 2 : 1);
+  const int resident = sms * ((TEMPORAL && DH == 16) ? 2 : 1);
   const int grid = p.n_windows < resident ? p.n_windows : resident;
   stw_fused_kernel<NTOK, DH, C, TEMPORAL><<<grid, 256, smem, st>>>(p);
   EXTDM_CHECK_LAUNCH();
@@ -1047,7 +1047,7 @@ extern "C" int extdm_stw_fused_pre(const void* h, const void* res, const float* 
 }
 
 extern "C" int extdm_temporal_fused_supported(int C, int heads, int dh, int T) {
-  return heads == 8 && dh == 16 && C == 64 && T >= 1 && T <= 32;
+  return heads == 8 && (dh == 16 || dh == 32) && C == 64 && T >= 1 && T <= 32;
 }
 
 extern "C" int extdm_temporal_fused(const void* x, void* y, const float* gamma, const float* ln_w, const float* ln_b,
@@ -1055,7 +1055,7 @@ extern "C" int extdm_temporal_fused(const void* x, void* y, const float* gamma, 
                                     const float* rope_sin, int B, int T, int HW, int C, int heads, int dh, float eps,
                                     void* stream) {
   if (!extdm_temporal_fused_supported(C, heads, dh, T)) {
-    extdm_set_error("temporal_fused: supported for C = 64, 8 heads x 16, T <= 32", __FILE__, __LINE__);
+    extdm_set_error("temporal_fused: supported for C = 64, 8 heads x 16 or 32, T <= 32", __FILE__, __LINE__);
     return EXTDM_ERR_ARG;
   }
   StwParams p;
@@ -1077,5 +1077,7 @@ extern "C" int extdm_temporal_fused(const void* x, void* y, const float* gamma, 
   p.Dp = 32;
   p.n_windows = B * HW;
   p.eps = eps;
+  // dim_head 32 (u12 / base / ada_u22): the register-resident Wq/Wk/Wv fragments double, one CTA per SM
+  if (dh == 32) return launch_stw<32, 32, 64, true>(p, static_cast<cudaStream_t>(stream));
   return launch_stw<32, 16, 64, true>(p, static_cast<cudaStream_t>(stream));
 }

@@ -117,6 +117,11 @@ class UnetRunner:
     # no faster on B200 (800 vs 716 + 98 us per level-0 pair: the attention kernel is compute bound and the extra
     # element-wise work lands on its critical path), so it is off by default.
     fuse_gn_stw = False
+    # The fused temporal kernel also exists for dim_head 32 (u12 / base / ada_u22; parity green in
+    # test_temporal_fused_layer), but with its doubled register-resident weights it runs one CTA per SM and the short
+    # sequences of those configurations (T = 12 ... 15 padded to 32 tokens) waste half of every tile: measured SMMNIST
+    # 1655 -> 1543 frames/s, BAIR 3205 -> 3226.  Off by default until it has a 16-token variant.
+    fuse_temporal_dh32 = False
 
     def __init__(self, packed, B, H=32, W=32, fea_hw=16):
         cfg = packed.cfg
@@ -144,7 +149,8 @@ class UnetRunner:
     def _temporal(self, rec, x, p):
         cfg, pk = self.cfg, self.pk
         B, T, H, W, C = x.shape
-        if self.fuse_stw and ops.temporal_fused_supported(C, cfg.heads, cfg.dim_head, T):
+        if self.fuse_stw and ops.temporal_fused_supported(C, cfg.heads, cfg.dim_head, T) and \
+                (cfg.dim_head == 16 or self.fuse_temporal_dh32):
             y = self.buf(B, T, H, W, C)
             ops.temporal_fused(rec, x, y, pk.f32[p + ".fn.norm.gamma"], pk.f32[p + ".fn.fn.fn.norm.weight"],
                                pk.f32[p + ".fn.fn.fn.norm.bias"], pk.w[p + ".fn.fn.fn.attn.to_qkv.weight"],

@@ -558,12 +558,12 @@ def test_frame_range_pool_and_resize():
     assert got[:, :, :T - t0].abs().max() == 0
 
 
-@pytest.mark.parametrize("T,H", [(30, 8), (12, 4), (7, 8), (32, 4)])
-def test_temporal_fused_layer(T, H):
+@pytest.mark.parametrize("T,H,dh", [(30, 8, 16), (12, 4, 16), (7, 8, 16), (32, 4, 16), (12, 8, 32), (15, 4, 32), (7, 8, 32)])
+def test_temporal_fused_layer(T, H, dh):
     """Whole temporal attention layer (chanLN -> LayerNorm -> qkv -> rotary/T5-bias attention over frames -> to_out ->
     double residual) in one kernel vs the oracle's temporal_attention (CPU fp32)."""
     from oracle import extdm_oracle as O
-    B, C, heads, dh = 2, 64, 8, 16
+    B, C, heads = 2, 64, 8
     hid = heads * dh
     x = rnd(B, C, T, H, H, seed=1)
     rel_emb = rnd(32, heads, seed=7) * 0.5                   # T5 bucket embedding
