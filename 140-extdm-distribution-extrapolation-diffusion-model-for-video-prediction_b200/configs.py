@@ -4,12 +4,12 @@ own `yaml.safe_load(...)` dict is accepted unchanged by `FlowDiffusion`."""
 import copy
 
 
-def _config(frame_shape, tc, tp, total_pred, num_regions=10, scale_factor=0.5, bg_type="affine"):
+def _config(frame_shape, tc, tp, total_pred, num_regions=10, scale_factor=0.5, bg_type="affine", split="test"):
     return {
         "dataset_params": {
             "frame_shape": frame_shape,
             "train_params": {"type": "train", "cond_frames": tc, "pred_frames": tp},
-            "valid_params": {"total_videos": 256, "type": "valid", "cond_frames": tc, "pred_frames": total_pred},
+            "valid_params": {"total_videos": 256, "type": split, "cond_frames": tc, "pred_frames": total_pred},
         },
         "flow_params": {"model_params": {
             "num_regions": num_regions, "num_channels": 3, "estimate_affine": True, "revert_axis_swap": True,
@@ -32,12 +32,13 @@ def _config(frame_shape, tc, tp, total_pred, num_regions=10, scale_factor=0.5, b
 
 # name -> (config, DM wrapper, Unet3D architecture)   -- SURVEY.md App. A
 _DATASETS = {
-    "kth": (_config(64, 10, 20, 40), "VideoFlowDiffusion_multi_w_ref",
+    "kth": (_config(64, 10, 20, 40, split="valid"), "VideoFlowDiffusion_multi_w_ref",
             "DenoiseNet_STWAtt_w_w_ref_adaptor_cross_multi_traj_ada"),
     "smmnist": (_config(64, 10, 5, 10), "VideoFlowDiffusion_multi1248",
                 "DenoiseNet_STWAtt_w_wo_ref_adaptor_cross_multi"),
     "bair": (_config(64, 2, 10, 28), "VideoFlowDiffusion_multi_w_ref",
              "DenoiseNet_STWAtt_w_w_ref_adaptor_cross_multi_traj_u12"),
+    # ucf.yaml's valid_params say 16 predicted frames; BASELINE.json names the 4 -> 12 rollout (2 rounds either way)
     "ucf": (_config(64, 4, 8, 12, num_regions=64), "VideoFlowDiffusion_multi_w_ref",
             "DenoiseNet_STWAtt_w_w_ref_adaptor_cross_multi_traj_ada"),
     "cityscapes": (_config(128, 2, 5, 28, num_regions=20, scale_factor=0.25, bg_type="perspective"),

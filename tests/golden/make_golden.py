@@ -217,6 +217,91 @@ def gen_pipeline_full():
     print("pipeline_full", {k: tuple(v.shape) for k, v in out.items()}, "unused noises", len(queue))
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# End-to-end fixtures for every BASELINE.json configuration: the UNMODIFIED reference wrapper run
+# through the autoregressive loop of scripts/DM/valid.py:167-172 at the shipped (tc, tp), 10 DDIM steps, eta = 1,
+# dynamic thresholding, injected noise, LAPACK SVD (this container has no GPU), estimate_occlusion_map = True.
+PIPELINE_CASES = {
+    # name: (config yaml, --DM_arch wrapper, UNet variant, rounds, DDIM steps)
+    "rollout_smmnist": ("smmnist", "VideoFlowDiffusion_multi1248", "base", 2, 10),          # the full 10 -> 10 rollout
+    "rollout_bair": ("bair", "VideoFlowDiffusion_multi_w_ref", "u12", 3, 10),               # the full 2 -> 28 rollout
+    "rollout_ucf": ("ucf", "VideoFlowDiffusion_multi_w_ref", "ada", 2, 10),                 # the full 4 -> 12 rollout
+    "rollout_cityscapes": ("cityscapes", "VideoFlowDiffusion_multi_w_ref", "ada", 2, 10),   # 128x128, sf 0.25, perspective
+    "rollout_cityscapes_u22": ("cityscapes", "VideoFlowDiffusion_multi_w_ref_u22", "u22", 1, 10),
+}
+PIPELINE_SEEDS = dict(generator=21, region_predictor=22, bg_predictor=23, diffusion=11)
+
+
+def smooth_clip(B, tc, hw, seed, gray):
+    """A smooth clip in [0, 1] (coarse noise, tri-linearly up-sampled): natural-video-like content.  On white noise a
+    0.1-pixel flow difference already dominates the frame PSNR.  gray: one channel replicated to three
+    (data/video_dataset.py:26-33 does that to the KTH / SMMNIST clips)."""
+    c = 1 if gray else 3
+    coarse = torch.rand((B, c, 4, 8, 8), generator=torch.Generator().manual_seed(seed))
+    vid = torch.nn.functional.interpolate(coarse, size=(tc, hw, hw), mode="trilinear", align_corners=True).clamp(0, 1)
+    return vid.expand(B, 3, tc, hw, hw).contiguous()
+
+
+def round_noise(B, tp, steps, seed, rnd_i):
+    """The `steps` Gaussian tensors one sample_one_video round consumes: the initial latent, then one per DDIM
+    iteration but the last (Diffusion.py:218,251)."""
+    return [rnd((B, 3, tp, 32, 32), seed + 100 * rnd_i + i) for i in range(steps)]
+
+
+def build_ref_pipeline(dataset, dm_arch, variant, steps=None):
+    cfg = yaml.safe_load(open(os.path.join(ref_shims.REF_ROOT, f"config/DM/{dataset}.yaml")))
+    cfg["flow_params"]["model_params"]["generator_params"]["pixelwise_flow_predictor_params"][
+        "estimate_occlusion_map"] = True                       # scripts/DM/valid.py:81 with --estimate_occlusion_map
+    if steps is not None:
+        cfg["diffusion_params"]["model_params"]["sampling_timesteps"] = steps
+    wmod = importlib.import_module("model.BaseDM_adaptor." + dm_arch)
+    kw = dict(config=cfg, pretrained_pth="", is_train=False)
+    if dm_arch.endswith("_u22"):
+        kw["device_ids"] = ["cpu", "cpu", "cpu"]
+    elif dm_arch != "VideoFlowDiffusion_multi1248":
+        kw["Unet3D_architecture"] = UNET_MODULES[variant]
+    fd = wmod.FlowDiffusion(**kw).eval()
+    mans = {}
+    for part, seed in PIPELINE_SEEDS.items():
+        m = getattr(fd, part)
+        base = m.state_dict()
+        mans[part] = manifest_of(base)
+        m.load_state_dict(synth_state_dict(mans[part], seed=seed, base=base), strict=True)
+    return fd, cfg, mans
+
+
+def gen_rollout(name):
+    dataset, dm_arch, variant, rounds, steps = PIPELINE_CASES[name]
+    fd, cfg, mans = build_ref_pipeline(dataset, dm_arch, variant, steps)
+    tc, tp = fd.cond_frame_num, fd.pred_frame_num
+    hw = cfg["dataset_params"]["frame_shape"]
+    B, in_seed, nz_seed = 1, 900, 1000
+    cond = smooth_clip(B, tc, hw, in_seed, gray=dataset in ("smmnist", "kth"))
+    out_rounds = []
+    real_randn, real_randn_like = torch.randn, torch.randn_like
+    for r in range(rounds):
+        queue = round_noise(B, tp, steps, nz_seed, r)
+        torch.randn = lambda *a, **k: queue.pop(0)
+        torch.randn_like = lambda *a, **k: queue.pop(0)
+        try:
+            with torch.no_grad():
+                ret = fd.sample_one_video(cond_scale=1.0, real_vid=cond.clone())
+        finally:
+            torch.randn, torch.randn_like = real_randn, real_randn_like
+        assert not queue, f"{len(queue)} noise tensors left"
+        out_rounds.append({"cond_in": cond.clone(), "real_vid_grid": ret["real_vid_grid"].clone(),
+                           "real_vid_conf": ret["real_vid_conf"].clone(),
+                           "sample_vid_grid": ret["sample_vid_grid"].clone(),
+                           "sample_vid_conf": ret["sample_vid_conf"].clone(),
+                           "sample_out_vid": ret["sample_out_vid"].half()})
+        cond = ret["sample_out_vid"][:, :, -tc:].clone()             # scripts/DM/valid.py:171
+        print(name, "round", r, "flow abs-mean", float(ret["sample_vid_grid"].abs().mean()), flush=True)
+    torch.save(dict(kind="rollout", dataset=dataset, dm_arch=dm_arch, variant=variant, rounds=rounds, steps=steps,
+                    cfg=cfg, B=B, tc=tc, tp=tp, hw=hw, weight_seeds=PIPELINE_SEEDS, input_seed=in_seed, noise_seed=nz_seed,
+                    manifests={k: v for k, v in mans.items() if k != "diffusion"}, out=out_rounds),
+               os.path.join(HERE, name + ".pt"))
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -235,6 +320,11 @@ if __name__ == "__main__":
         gen_pipeline()
     if "pipeline_full" in which:
         gen_pipeline_full()
+    if "rollout" in which:
+        which = which + list(PIPELINE_CASES)
+    for n in which:
+        if n in PIPELINE_CASES:
+            gen_rollout(n)
 
 
 def gen_metrics():
