@@ -286,11 +286,11 @@ extern "C" int extdm_window_attention(const void* qkv, void* out, const float* b
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define LAUNCH_WIN(N, D)                                                                                            \
   do {                                                                                                              \
-    static size_t configured = 0;                                                                                   \
-    if (smem > configured) {                                                                                        \
+    static SmemConfigured configured;                                                                               \
+    if (!configured.covers(smem)) {                                                                                   \
       int rc = set_smem(window_attention_kernel<N, D>, smem);                                                       \
       if (rc) return rc;                                                                                            \
-      configured = smem;                                                                                            \
+      configured.set(smem);                                                                                         \
     }                                                                                                               \
     window_attention_kernel<N, D><<<grid, 256, smem, st>>>(                                                         \
         reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), bias_table, rope_cos,   \
@@ -319,11 +319,11 @@ extern "C" int extdm_temporal_attention(const void* qkv, void* out, const float*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define LAUNCH_TMP(N, D)                                                                                            \
   do {                                                                                                              \
-    static size_t configured = 0;                                                                                   \
-    if (smem > configured) {                                                                                        \
+    static SmemConfigured configured;                                                                               \
+    if (!configured.covers(smem)) {                                                                                   \
       int rc = set_smem(temporal_attention_kernel<N, D>, smem);                                                     \
       if (rc) return rc;                                                                                            \
-      configured = smem;                                                                                            \
+      configured.set(smem);                                                                                         \
     }                                                                                                               \
     temporal_attention_kernel<N, D><<<grid, 256, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),           \
                                                              reinterpret_cast<__nv_bfloat16*>(out), rel_bias,       \

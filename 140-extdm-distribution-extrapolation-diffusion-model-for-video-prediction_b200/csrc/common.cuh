@@ -23,6 +23,31 @@ void extdm_set_error(const char* msg, const char* file, int line);
 
 namespace extdm {
 
+// ---------------------------------------------------------------- per-device launch configuration
+// cudaFuncSetAttribute and the SM count belong to a DEVICE, not to the process: a second GPU used from the same process
+// (FlowDiffusionU22 accepts device_ids) must be configured on its own.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d & (kMaxDevices - 1);
+}
+inline int device_sm_count() {
+  static int sms[kMaxDevices] = {};
+  const int d = current_device();
+  if (sms[d] <= 0) {
+    cudaDeviceGetAttribute(&sms[d], cudaDevAttrMultiProcessorCount, d);
+    if (sms[d] <= 0) sms[d] = 148;
+  }
+  return sms[d];
+}
+// largest dynamic-shared-memory size one kernel instantiation has been configured for, per device
+struct SmemConfigured {
+  size_t bytes[kMaxDevices] = {};
+  bool covers(size_t need) const { return bytes[current_device()] >= need; }
+  void set(size_t need) { bytes[current_device()] = need; }
+};
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -810,31 +810,22 @@ static int encode_a(CUtensorMap* map, const void* base, int channels, const long
   return encode_map(map, base, 5, dims, strides, bx, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
 }
 
-static int sm_count() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  return sms;
-}
+static int sm_count() { return device_sm_count(); }
 
 constexpr int kSmemBudget = 232448 - 4608;       // 227 KB minus alignment slack, barriers, bias and GN scratch
 
 template <int BN, bool GN, bool RESB, bool SIMPLE>
 static int launch_halo(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensorMap& mb, GemmDev& dev, int m_tiles,
                        int smem_bytes, cudaStream_t stream) {
-  static int configured = 0;
-  if (smem_bytes > configured) {
+  static SmemConfigured configured;
+  if (!configured.covers(smem_bytes)) {
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, GN, RESB, SIMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          smem_bytes);
     if (e != cudaSuccess) {
       extdm_set_error(cudaGetErrorString(e), __FILE__, __LINE__);
       return EXTDM_ERR_CUDA;
     }
-    configured = smem_bytes;
+    configured.set(smem_bytes);
   }
   dev.n_tiles_n = (dev.n + BN - 1) / BN;
   dev.total_tiles = m_tiles * dev.n_tiles_n;
@@ -850,15 +841,15 @@ static int launch(const CUtensorMap& ma0, const CUtensorMap& ma1, const CUtensor
                   cudaStream_t stream) {
   constexpr int kStageBytes = kATileBytes + BN * kBlockK * 2;
   constexpr int smem_bytes = STAGES * kStageBytes + (2 * STAGES + 4) * 8 + 16 + 4096 + 1024;
-  static bool configured = false;
-  if (!configured) {
+  static SmemConfigured configured;
+  if (!configured.covers(smem_bytes)) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, GN, SIMPLE, TF32>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) {
       extdm_set_error(cudaGetErrorString(e), __FILE__, __LINE__);
       return EXTDM_ERR_CUDA;
     }
-    configured = true;
+    configured.set(smem_bytes);
   }
   dev.n_tiles_n = (dev.n + BN - 1) / BN;
   dev.total_tiles = m_tiles * dev.n_tiles_n;

@@ -500,19 +500,16 @@ template <int NTOK, int DH, int C, bool TEMPORAL = false>
 static int launch_stw(const StwParams& p, cudaStream_t st) {
   using L = StwSmem<NTOK, DH, C>;
   constexpr size_t smem = L::total;
-  static bool configured = false;
-  static int sms = 0;
-  if (!configured) {
+  static SmemConfigured configured;
+  const int sms = device_sm_count();
+  if (!configured.covers(smem)) {
     cudaError_t e = cudaFuncSetAttribute(stw_fused_kernel<NTOK, DH, C, TEMPORAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) {
       extdm_set_error(cudaGetErrorString(e), __FILE__, __LINE__);
       return EXTDM_ERR_CUDA;
     }
-    configured = true;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    configured.set(smem);
   }
   const int resident = sms * ((TEMPORAL && DH == 16) ? 2 : 1);
   const int grid = p.n_windows < resident ? p.n_windows : resident;
@@ -927,19 +924,16 @@ template <int NTOK, int DH, int C>
 static int launch_stw16(const StwParams& p, cudaStream_t st) {
   using L = Stw16Smem<NTOK, DH, C>;
   constexpr size_t smem = L::total;
-  static bool configured = false;
-  static int sms = 0;
-  if (!configured) {
+  static SmemConfigured configured;
+  const int sms = device_sm_count();
+  if (!configured.covers(smem)) {
     cudaError_t e = cudaFuncSetAttribute(stw_fused16_kernel<NTOK, DH, C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) {
       extdm_set_error(cudaGetErrorString(e), __FILE__, __LINE__);
       return EXTDM_ERR_CUDA;
     }
-    configured = true;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    configured.set(smem);
   }
   const int grid = p.n_windows < sms ? p.n_windows : sms;
   stw_fused16_kernel<NTOK, DH, C><<<grid, 512, smem, st>>>(p);

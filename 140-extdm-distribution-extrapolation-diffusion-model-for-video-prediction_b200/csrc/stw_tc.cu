@@ -567,22 +567,25 @@ int extdm_stw_tc_launch(const void* x, void* y, const float* gamma, const void* 
   while ((1 << p.lw) < nww) ++p.lw;
   while ((1 << p.lh) < nwh) ++p.lh;
   constexpr int smem = Smem::total + 1024;
-  static bool configured = false;
-  static int sms = 0;
-  if (!configured) {
+  static SmemConfigured configured;
+  const int sms = device_sm_count();
+  if (!configured.covers(smem)) {
     cudaError_t e = cudaFuncSetAttribute(stw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
       extdm_set_error(cudaGetErrorString(e), __FILE__, __LINE__);
       return EXTDM_ERR_CUDA;
     }
-    configured = true;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    configured.set(smem);
   }
   const int n_pairs = (p.n_windows + 1) / 2;
   const int grid = n_pairs < sms ? n_pairs : sms;
-  static const bool prof = getenv("EXTDM_STW_PROF") != nullptr;
+  static const bool prof_env = getenv("EXTDM_STW_PROF") != nullptr;
+  bool prof = prof_env;
+  if (prof) {                                           // the profile read-back synchronises: illegal during graph capture
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(static_cast<cudaStream_t>(stream), &cs);
+    if (cs != cudaStreamCaptureStatusNone) prof = false;
+  }
   p.prof = prof ? 1 : 0;
   if (prof) {
     unsigned long long z[8] = {};

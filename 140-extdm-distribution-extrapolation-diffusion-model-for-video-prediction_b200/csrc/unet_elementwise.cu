@@ -929,10 +929,10 @@ extern "C" int extdm_time_mlp(const long long* time, const float* w1, const floa
   if (td > 256 || B * td * 4 > 200 * 1024) return bad_arg("time_mlp: 4*dim <= 256 and B*4*dim floats must fit in shared memory");
   time_mlp_kernel<<<B, 256, 5 * dim * sizeof(float), STREAM>>>(time, w1, b1, w2, b2, scratch, dim);
   EXTDM_CHECK_LAUNCH();
-  static bool configured = false;
-  if (!configured) {
+  static SmemConfigured configured;
+  if (!configured.covers(200 * 1024)) {
     cudaFuncSetAttribute(time_ss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    configured = true;
+    configured.set(200 * 1024);
   }
   const int grid = grid_for(static_cast<long long>(n_ss) * 32, 256, 148 * 2);
   time_ss_kernel<<<grid, 256, static_cast<size_t>(B) * td * sizeof(float), STREAM>>>(scratch, wss, bss, out, B, td, n_ss);

@@ -50,9 +50,7 @@ class GaussianDiffusion(nn.Module):
         self.ddim_sampling_eta = ddim_sampling_eta
         self.use_dynamic_thres = use_dynamic_thres
         self.dynamic_thres_percentile = dynamic_thres_percentile
-        self._graphs = {}
         self.use_cuda_graph = True
-        self.register_load_state_dict_post_hook(lambda m, k: m._graphs.clear())
 
     # ------------------------------------------------------------------ schedule scalars (host, fp32)
     def ddim_schedule(self):
@@ -103,8 +101,13 @@ class GaussianDiffusion(nn.Module):
                 noise[i] = torch.randn(shape, device=dev)
         if trace is not None or not self.use_cuda_graph:
             return self._run_loop(r, sched, x_cond, cond_fea, noise, trace).clone()
-        key = (id(r), tuple(shape))
-        if key not in self._graphs:
+        # Captured graphs hold raw pointers into the runner's weight and activation buffers, so they live ON the runner:
+        # Unet3D.invalidate() (load_state_dict, device move) drops runner and graphs together.  The schedule scalars are
+        # baked into the capture, hence part of the key.
+        graphs = r.ddim_graphs
+        key = (tuple(shape), float(self.ddim_sampling_eta), float(self.dynamic_thres_percentile),
+               int(self.sampling_timesteps), int(self.num_timesteps))
+        if key not in graphs:
             st = dict(noise=torch.zeros_like(noise), s=torch.zeros(B, device=dev))
             st["x_cond"], st["cond_fea"] = r.cond_frames, r.cond_fea
             self._run_loop(r, sched, x_cond, cond_fea, noise, None, st)          # warm-up (lazy inits)
@@ -112,8 +115,8 @@ class GaussianDiffusion(nn.Module):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._run_loop(r, sched, None, None, st["noise"], None, st)
-            self._graphs[key] = (g, st)
-        g, st = self._graphs[key]
+            graphs[key] = (g, st)
+        g, st = graphs[key]
         r.set_conditioning(x_cond.float(), cond_fea.float())
         st["noise"].copy_(noise)
         g.replay()

@@ -55,7 +55,9 @@ class FlowDiffusion(nn.Module):
         self.bg_predictor = BGMotionPredictor(num_channels=flow_params["num_channels"],
                                               **flow_params["bg_predictor_params"]).to(dev)
         if ckpt is not None:
-            self.generator.load_state_dict(ckpt["generator"], strict=False)
+            # VideoFlowDiffusion_multi_w_ref.py:51 (and _u22) load the generator with strict=False; multi1248 / multi
+            # (VideoFlowDiffusion_multi1248.py:50) load it strictly
+            self.generator.load_state_dict(ckpt["generator"], strict=kind != "w_ref")
             self.region_predictor.load_state_dict(ckpt["region_predictor"])
             self.bg_predictor.load_state_dict(ckpt["bg_predictor"])
         for m in (self.generator, self.region_predictor, self.bg_predictor):

@@ -679,6 +679,10 @@ class CondRunner:
             out, skip = y, feats.pop()
         return out, skip
 
+    def recorders(self):
+        """The stage's launch lists, in execution order (bench.py / tools/kernel_table.py account for them)."""
+        return [self.recA, self.recB]
+
     def run(self, real_vid):
         """real_vid (B, 3, tc, H, W) fp32 on the device -> (grid (B,2,tc,h,w), conf (B,1,tc,h,w) | None)."""
         B, _, tc, H, W = real_vid.shape

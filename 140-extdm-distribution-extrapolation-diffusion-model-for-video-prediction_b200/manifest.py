@@ -2,8 +2,9 @@
 architecture hyper-parameters only.  They let the product build parameter containers whose
 `state_dict()` / `load_state_dict()` key sets are identical to the reference's (SURVEY.md section 8b:
 `model.diffusion.load_state_dict(ckpt['diffusion'])`, scripts/DM/valid.py:111-112) without copying
-its module definitions.  tests/test_manifest.py checks them against manifests captured from the
-reference itself (tests/golden/*.pt).
+its module definitions.  tests/test_host_cpu.py::test_unet_manifest_matches_reference checks key sets and shapes of
+every variant (ada, u12, base, ada_u22; mini and shipped tc / tp) against manifests captured from the reference
+itself (tests/golden/unet_*.pt); test_wrapper_state_dicts_match_reference does the same for the wrappers' parts.
 """
 import math
 

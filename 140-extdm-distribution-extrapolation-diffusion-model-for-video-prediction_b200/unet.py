@@ -140,6 +140,7 @@ class UnetRunner:
         self.prologue = ops.Recorder(record=True)
         self.step = ops.Recorder(record=True)
         self.taps = {}                      # name -> buffer, for layer-by-layer parity tests
+        self.ddim_graphs = {}               # CUDA graphs of the sampling loop over these buffers (GaussianDiffusion)
         self._build()
 
     # ------------------------------------------------------------------ helpers

@@ -1,7 +1,9 @@
-"""Import shims that let the UNMODIFIED reference (/root/reference) import and run on CPU.
+"""Import shims that let the UNMODIFIED reference import and run (on CPU, or on a GPU as it is).
 
-Only used by tests/golden/make_golden.py (fixture generation, run in the build container where
-/root/reference exists).  Nothing in the product, the gpu tests, smoke() or bench.py imports this.
+Used by tests/golden/make_golden.py (fixture generation in the build container, from /root/reference) and by
+bench.py's reference legs (`--impl reference`, `cpu_baseline`, `gpu_eager_reference`), which run the copy staged under
+oracle/_ref/ by oracle/make_ref.py -- /root/reference does not exist on the GPU box.  Test infrastructure: nothing in
+the product package, the gpu tests or smoke() imports this.
 
 The reference depends on packages absent from this image:
   einops_exts.rearrange_many, timm.models.layers.{DropPath,trunc_normal_}, xformers.ops,
@@ -16,7 +18,12 @@ import math
 import torch
 from torch import nn
 
-REF_ROOT = "/root/reference"
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# the build container reads the reference where it lies; elsewhere the staged copy (oracle/make_ref.py)
+REF_ROOT = os.environ.get("EXTDM_REFERENCE") or \
+    ("/root/reference" if os.path.isdir("/root/reference/model") else os.path.join(_HERE, "_ref"))
 
 
 class _RotaryEmbedding(nn.Module):
@@ -37,6 +44,23 @@ class _RotaryEmbedding(nn.Module):
         half = torch.stack((-x2, x1), dim=-1).reshape(t_rot.shape)
         out = t_rot * ang.cos() + half * ang.sin()
         return torch.cat((out, t_pass), dim=-1)
+
+
+_REAL_CUDA = (nn.Module.cuda, torch.Tensor.cuda)
+
+
+def cuda_identity(on):
+    """The reference hard-codes `.cuda()` at VideoFlowDiffusion_multi_w_ref.py:49,58 (and the other wrappers): patch it
+    to the identity to run the unmodified code on the host cores; restore it to run the same code on a GPU."""
+    if on:
+        nn.Module.cuda = lambda self, *a, **k: self
+        torch.Tensor.cuda = lambda self, *a, **k: self
+    else:
+        nn.Module.cuda, torch.Tensor.cuda = _REAL_CUDA
+
+
+def available():
+    return os.path.isdir(os.path.join(REF_ROOT, "model", "BaseDM_adaptor"))
 
 
 def install():
@@ -74,8 +98,7 @@ def install():
     sk.draw = mod("skimage.draw", disk=lambda *a, **k: None)
 
     if not torch.cuda.is_available():
-        nn.Module.cuda = lambda self, *a, **k: self
-        torch.Tensor.cuda = lambda self, *a, **k: self
+        cuda_identity(True)
     if REF_ROOT not in sys.path:
         sys.path.insert(0, REF_ROOT)
     install._done = True

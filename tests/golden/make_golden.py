@@ -14,10 +14,9 @@ import yaml
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-sys.path.insert(0, HERE)
 sys.path.insert(0, ROOT)
 
-import ref_shims  # noqa: E402
+from oracle import ref_shims  # noqa: E402
 
 ref_shims.install()
 import extdm_b200  # noqa: E402

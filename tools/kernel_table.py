@@ -22,7 +22,7 @@ runner = next(iter(model.unet._runners.values()))
 dec = next(r for k, r in model.generator._runners.items() if k[0] != "enc")
 steps = cfg["diffusion_params"]["model_params"]["sampling_timesteps"]
 rows = {}
-cond = [("cond", r_, 1) for cr in model._cond_runners.values() for r_ in (cr.recA, cr.recB)]
+cond = [("cond", r_, 1) for cr in model._cond_runners.values() for r_ in cr.recorders()]
 cond += [("cond", r_.rec, 1) for k_, r_ in model.generator._runners.items() if k_[0] == "enc"]
 for label, rec, mult in [("prologue", runner.prologue, 1), ("step", runner.step, steps), ("decode", dec.rec, 1)] + cond:
     rec.run()
