@@ -950,6 +950,14 @@ int extdm_stw_tc_launch(const void* x, void* y, const float* gamma, const void* 
                         const float* proj_bias, const float* bias_table, const float* rope_cos, const float* rope_sin,
                         int B, int T, int H, int W, int sd, int sh, int sw, float eps, void* stream);
 
+// tcgen05 edition of the dim_head-32 layers (attn_tc32.cu): (2,4,4) windows and temporal sequences, C = 64
+int extdm_stw_tc32_launch(const void* x, void* y, const float* gamma, const void* wqkv, const void* wproj,
+                          const float* proj_bias, const float* bias_table, const float* rope_cos, const float* rope_sin,
+                          int B, int T, int H, int W, int C, int sd, int sh, int sw, float eps, void* stream);
+int extdm_temporal_tc32_launch(const void* x, void* y, const float* gamma, const float* ln_w, const float* ln_b,
+                               const void* wqkv, const void* wout, const float* rel_bias, const float* rope_cos,
+                               const float* rope_sin, int B, int T, int HW, int C, float eps, void* stream);
+
 extern "C" int extdm_stw_fused_supported(int C, int heads, int dh, int wd, int wh, int ww) {
   const int ntok = wd * wh * ww;
   if (heads != 8 || wh != 4 || ww != 4) return 0;
@@ -1012,6 +1020,14 @@ static int stw_fused_impl(const void* x, void* y, const float* gamma, const void
     return launch_stw16<64, 16, 64>(p, st);
   }
   if (ntok == 64 && C == 128) return launch_stw<64, 16, 128>(p, st);
+  // (2,4,4) windows, 8 heads x 32: every product on tcgen05 (attn_tc32.cu); EXTDM_ATTN32_LEGACY=1 keeps the mma.sync
+  // kernel (A/B partner in the tests)
+  static const bool legacy32 = getenv("EXTDM_ATTN32_LEGACY") != nullptr;
+  if (!legacy32) {
+    const int rc = extdm_stw_tc32_launch(x, y, gamma, wqkv, wproj, proj_bias, bias_table, rope_cos, rope_sin, B, T, H, W,
+                                         C, sd, sh, sw, eps, stream);
+    if (rc != -1) return rc;
+  }
   return launch_stw<32, 32, 64>(p, st);       // (2,4,4) windows: the 16-warp layout would need 233 KB of shared memory
 }
 
@@ -1071,7 +1087,15 @@ extern "C" int extdm_temporal_fused(const void* x, void* y, const float* gamma, 
   p.Dp = 32;
   p.n_windows = B * HW;
   p.eps = eps;
-  // dim_head 32 (u12 / base / ada_u22): the register-resident Wq/Wk/Wv fragments double, one CTA per SM
-  if (dh == 32) return launch_stw<32, 32, 64, true>(p, static_cast<cudaStream_t>(stream));
+  // dim_head 32 (u12 / base / ada_u22): tcgen05 kernel (attn_tc32.cu); the mma.sync one behind EXTDM_ATTN32_LEGACY
+  if (dh == 32) {
+    static const bool legacy32 = getenv("EXTDM_ATTN32_LEGACY") != nullptr;
+    if (!legacy32) {
+      const int rc = extdm_temporal_tc32_launch(x, y, gamma, ln_w, ln_b, wqkv, wout, rel_bias, rope_cos, rope_sin, B, T,
+                                                HW, C, eps, stream);
+      if (rc != -1) return rc;
+    }
+    return launch_stw<32, 32, 64, true>(p, static_cast<cudaStream_t>(stream));
+  }
   return launch_stw<32, 16, 64, true>(p, static_cast<cudaStream_t>(stream));
 }

@@ -482,7 +482,13 @@ def test_lfae_helpers():
 
 @pytest.mark.parametrize("window,dh,C,T,H,shifted", [((4, 4, 4), 16, 64, 7, 16, True), ((4, 4, 4), 16, 64, 7, 16, False),
                                                      ((4, 4, 4), 16, 128, 6, 8, True), ((2, 4, 4), 32, 64, 5, 8, True),
-                                                     ((4, 4, 4), 16, 64, 30, 32, True)])
+                                                     ((4, 4, 4), 16, 64, 30, 32, True),
+                                                     # dim_head 32 / (2,4,4): the tcgen05 kernel of attn_tc32.cu -- BAIR
+                                                     # (T = 12) and SMMNIST (T = 14) shapes, padded depth (T = 5), a
+                                                     # depth no larger than the window (no depth shift), partial tile
+                                                     ((2, 4, 4), 32, 64, 12, 32, True), ((2, 4, 4), 32, 64, 14, 16, False),
+                                                     ((2, 4, 4), 32, 64, 5, 8, False), ((2, 4, 4), 32, 64, 2, 4, True),
+                                                     ((2, 4, 4), 32, 64, 3, 4, False)])
 @pytest.mark.parametrize("impl", ["default", "EXTDM_STW8", "EXTDM_STW16"])
 def test_stw_fused_layer(window, dh, C, T, H, shifted, impl):
     """Whole Residual(PreNorm(STWAttentionLayer)) in one kernel vs the oracle's stw_attention (CPU fp32), for each of
@@ -499,7 +505,7 @@ def test_stw_fused_layer(window, dh, C, T, H, shifted, impl):
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         return
     from oracle import extdm_oracle as O
-    B, heads = 2, 8
+    B, heads = (3 if H == 4 else 2), 8
     hid = heads * dh
     N = window[0] * window[1] * window[2]
     x = rnd(B, C, T, H, H, seed=1)
@@ -512,6 +518,8 @@ def test_stw_fused_layer(window, dh, C, T, H, shifted, impl):
     xc = to_cl(x)
     y = torch.zeros_like(xc)
     shift = tuple(w // 2 for w in window) if shifted else (0, 0, 0)
+    if T <= window[0]:
+        shift = (0,) + shift[1:]                            # get_window_size: a dim no larger than its window is not shifted
     rc, rs = _rope_tables(N, dh)
     assert ops.stw_fused_supported(C, heads, dh, window)
     ops.stw_fused(R, xc, y, sd["fn.norm.gamma"].reshape(-1).to(DEV), sd["fn.fn.attn.qkv.weight"].to(DEV).to(BF),
@@ -558,7 +566,8 @@ def test_frame_range_pool_and_resize():
     assert got[:, :, :T - t0].abs().max() == 0
 
 
-@pytest.mark.parametrize("T,H,dh", [(30, 8, 16), (12, 4, 16), (7, 8, 16), (32, 4, 16), (12, 8, 32), (15, 4, 32), (7, 8, 32)])
+@pytest.mark.parametrize("T,H,dh", [(30, 8, 16), (12, 4, 16), (7, 8, 16), (32, 4, 16), (12, 8, 32), (15, 4, 32), (7, 8, 32),
+                                    (12, 32, 32), (14, 16, 32), (17, 4, 32), (32, 8, 32), (16, 3, 32), (1, 4, 32)])
 def test_temporal_fused_layer(T, H, dh):
     """Whole temporal attention layer (chanLN -> LayerNorm -> qkv -> rotary/T5-bias attention over frames -> to_out ->
     double residual) in one kernel vs the oracle's temporal_attention (CPU fp32)."""
