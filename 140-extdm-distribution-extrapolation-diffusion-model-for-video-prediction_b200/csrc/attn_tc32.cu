@@ -58,13 +58,16 @@ struct Lay {
   static constexpr int vt = k + 16384;                       // V^T: 2 k-blocks x [64][64] SW128
   static constexpr int p = vt + 16384;                       // 2 heads x 2 k-blocks x [128][64] SW128
   static constexpr int bias = p + 2 * 32768;                 // [8][TP][TP] bf16 * log2(e), chunk-swizzled
-  static constexpr int rope = bias + 16384;                  // cos, sin [32][16] fp32
+  static constexpr int rope = bias + 16384;                  // cos, sin [16 pairs][32 positions] fp32 (transposed: lanes = positions)
   static constexpr int vec = rope + 4096;                    // gamma, ln_w, ln_b, proj bias: 4 x C fp32
   static constexpr int stat = vec + 16 * C;                  // [128] (mean, rstd) of the channel LayerNorm
   static constexpr int ml = stat + 1024;                     // [2 heads][128 rows][2 halves] (max, sum)
   static constexpr int bars = ml + 4096;                     // 4 mbarriers + TMEM slot
   static constexpr int total = bars + 64;
 };
+
+// EXTDM_ATTN32_PROF=1: per-phase cycle counts of CTA 0 (thread 0's view, waits included), printed by the launcher
+__device__ unsigned long long g_prof32[16];
 
 struct P32 {
   const __nv_bfloat16* x;
@@ -81,6 +84,7 @@ struct P32 {
   int B, T, H, W;              // temporal: H = pixels per frame, W = 1
   int sd, sh, sw, Dp, n_units, n_tiles, lw, lh;
   float eps;
+  int prof;
 };
 
 // TP = tokens per attention unit in the tile (32: a (2,4,4) window or a sequence of 17..32 frames; 16: T <= 16)
@@ -183,7 +187,10 @@ __global__ void __launch_bounds__(NTH, 1) attn_tc32_kernel(const __grid_constant
   int tile = blockIdx.x;
   load_stage(0, 0);
   prefetch_tokens(tile);
-  for (int i = tid; i < 32 * 16; i += NTH) { s_cos[i] = p.rcos[i]; s_sin[i] = p.rsin[i]; }
+  for (int i = tid; i < 32 * 16; i += NTH) {                // global [pos][pair] -> shared [pair][pos]
+    s_cos[(i & 15) * 32 + (i >> 4)] = p.rcos[i];
+    s_sin[(i & 15) * 32 + (i >> 4)] = p.rsin[i];
+  }
   for (int i = tid; i < C; i += NTH) {
     s_gamma[i] = p.gamma[i];
     s_lnw[i] = TEMPORAL ? p.ln_w[i] : 1.f;
@@ -234,8 +241,18 @@ __global__ void __launch_bounds__(NTH, 1) attn_tc32_kernel(const __grid_constant
   const uint32_t tlane = tmem_u + (static_cast<uint32_t>(dq * 32) << 16);
 
   uint32_t gc = 0;                                          // groups processed by this CTA (mbarrier phases)
+  const bool prof = p.prof && blockIdx.x == 0 && tid == 0;
+  long long tk = 0;
+  auto tick = [&](int slot) {
+    if (prof) {
+      const long long now = clock64();
+      g_prof32[slot] += static_cast<unsigned long long>(now - tk);
+      tk = now;
+    }
+  };
   for (; tile < p.n_tiles; tile += gridDim.x) {
     const int next_tile = tile + gridDim.x;
+    if (prof) { tk = clock64(); g_prof32[15] += 1; }
     // ---- channel LayerNorm of the tile, in place: 4 threads per token, C/4 channels each
     cp_wait<0>();
     __syncthreads();
@@ -294,6 +311,7 @@ __global__ void __launch_bounds__(NTH, 1) attn_tc32_kernel(const __grid_constant
       }
     }
 
+    tick(0);                                                // token wait + LayerNorm
     for (int g = 0; g < 4; ++g, ++gc) {
       const int buf = gc & 1;
       uint8_t* st = sm + L::stage + buf * L::STAGE;
@@ -311,6 +329,7 @@ __global__ void __launch_bounds__(NTH, 1) attn_tc32_kernel(const __grid_constant
       fence_proxy_async();                                  // A tile / weight stage -> visible to the tensor-core proxy
       tc_fence_before();
       __syncthreads();
+      tick(1);                                              // previous out-proj + weight stage wait
 
       // ---- QKV_g = LN(x) . Wqkv_g^T
       if (warp == 0) {
@@ -329,6 +348,7 @@ __global__ void __launch_bounds__(NTH, 1) attn_tc32_kernel(const __grid_constant
       }
       mbar_wait(bar_qkv, gc & 1);
       tc_fence_after();
+      tick(2);                                              // QKV product
       if (g == 3 && next_tile < p.n_tiles) prefetch_tokens(next_tile);     // the A tile is free: next tile's raw tokens
 
       // ---- drain: thread = token, 48 of the 192 columns; q-scale + rotary; Q, K row-major, V transposed
@@ -349,7 +369,7 @@ __global__ void __launch_bounds__(NTH, 1) attn_tc32_kernel(const __grid_constant
             const float sc = region == 0 ? qscale : 1.0f;
 #pragma unroll
             for (int pr = 0; pr < 8; ++pr) {
-              const float cs = s_cos[pos * 16 + (d0 >> 1) + pr], sn = s_sin[pos * 16 + (d0 >> 1) + pr];
+              const float cs = s_cos[((d0 >> 1) + pr) * 32 + pos], sn = s_sin[((d0 >> 1) + pr) * 32 + pos];
               const float x0 = f[2 * pr] * sc, x1 = f[2 * pr + 1] * sc;
               f[2 * pr] = x0 * cs - x1 * sn;
               f[2 * pr + 1] = x1 * cs + x0 * sn;
@@ -373,6 +393,7 @@ __global__ void __launch_bounds__(NTH, 1) attn_tc32_kernel(const __grid_constant
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
+      tick(3);                                              // QKV drain
 
       // ---- S_h = Q_h . K_h^T for the group's two heads
       if (warp == 0) {
@@ -390,6 +411,7 @@ __global__ void __launch_bounds__(NTH, 1) attn_tc32_kernel(const __grid_constant
       }
       mbar_wait(bar_s, gc & 1);
       tc_fence_after();
+      tick(4);                                              // score product
 
       // ---- softmax: warp = (lane quarter, head of the group, column half); thread = query row
       {
@@ -469,6 +491,7 @@ __global__ void __launch_bounds__(NTH, 1) attn_tc32_kernel(const __grid_constant
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
+      tick(5);                                              // softmax
 
       // ---- O_h = P_h . V_h
       if (warp == 0) {
@@ -490,6 +513,7 @@ __global__ void __launch_bounds__(NTH, 1) attn_tc32_kernel(const __grid_constant
       }
       mbar_wait(bar_o, gc & 1);
       tc_fence_after();
+      tick(6);                                              // PV product
 
       // ---- O_g -> bf16 A tile of the output projection (over the group's Q slots)
       {
@@ -505,6 +529,7 @@ __global__ void __launch_bounds__(NTH, 1) attn_tc32_kernel(const __grid_constant
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
+      tick(7);                                              // O drain
 
       // ---- D (+)= O_g . Wproj[:, 64g : 64g+64]^T
       if (warp == 0) {
@@ -555,6 +580,7 @@ __global__ void __launch_bounds__(NTH, 1) attn_tc32_kernel(const __grid_constant
       }
     }
     tc_fence_before();                                      // TMEM reads done before the next tile's products overwrite it
+    tick(8);                                                // last out-proj wait + epilogue
   }
   cp_wait<0>();
   tc_fence_before();
@@ -579,7 +605,29 @@ int launch32(const P32& p, cudaStream_t st) {
   }
   const int sms = device_sm_count();
   const int grid = p.n_tiles < sms ? p.n_tiles : sms;
-  attn_tc32_kernel<C, TP, TEMPORAL><<<grid, NTH, smem, st>>>(p);
+  static const bool prof_env = getenv("EXTDM_ATTN32_PROF") != nullptr;
+  bool prof = prof_env;
+  if (prof) {                                               // the read-back synchronises: not during graph capture
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    if (cs != cudaStreamCaptureStatusNone) prof = false;
+  }
+  P32 q = p;
+  q.prof = prof ? 1 : 0;
+  if (prof) {
+    unsigned long long z[16] = {};
+    cudaMemcpyToSymbol(g_prof32, z, sizeof(z));
+  }
+  attn_tc32_kernel<C, TP, TEMPORAL><<<grid, NTH, smem, st>>>(q);
+  if (prof) {
+    unsigned long long h[16];
+    cudaStreamSynchronize(st);
+    cudaMemcpyFromSymbol(h, g_prof32, sizeof(h));
+    const double n = h[15] ? static_cast<double>(h[15]) : 1.0;
+    fprintf(stderr, "[attn32 prof] temporal=%d TP=%d tiles/CTA=%.0f cycles/tile: ln %.0f | per tile (4 groups): stage_wait %.0f qkv_mma %.0f "
+            "drain %.0f s_mma %.0f softmax %.0f pv_mma %.0f o_drain %.0f | epilogue %.0f\n", (int)TEMPORAL, TP, n, h[0] / n, h[1] / n,
+            h[2] / n, h[3] / n, h[4] / n, h[5] / n, h[6] / n, h[7] / n, h[8] / n);
+  }
   EXTDM_CHECK_LAUNCH();
   return EXTDM_OK;
 }

@@ -1020,10 +1020,10 @@ static int stw_fused_impl(const void* x, void* y, const float* gamma, const void
     return launch_stw16<64, 16, 64>(p, st);
   }
   if (ntok == 64 && C == 128) return launch_stw<64, 16, 128>(p, st);
-  // (2,4,4) windows, 8 heads x 32: every product on tcgen05 (attn_tc32.cu); EXTDM_ATTN32_LEGACY=1 keeps the mma.sync
-  // kernel (A/B partner in the tests)
-  static const bool legacy32 = getenv("EXTDM_ATTN32_LEGACY") != nullptr;
-  if (!legacy32) {
+  // (2,4,4) windows, 8 heads x 32: the all-tcgen05 kernel (attn_tc32.cu) behind EXTDM_STW32_TC=1 until its phases are
+  // overlapped -- first version, B200, BAIR level 0: 422 us vs 345 us for the mma.sync kernel (gpurun_out/attn32_bench.log)
+  static const bool tc32 = getenv("EXTDM_STW32_TC") != nullptr;
+  if (tc32) {
     const int rc = extdm_stw_tc32_launch(x, y, gamma, wqkv, wproj, proj_bias, bias_table, rope_cos, rope_sin, B, T, H, W,
                                          C, sd, sh, sw, eps, stream);
     if (rc != -1) return rc;

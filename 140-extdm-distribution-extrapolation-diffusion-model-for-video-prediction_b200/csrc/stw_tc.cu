@@ -143,7 +143,10 @@ __global__ void __launch_bounds__(NTH, 1) stw_tc_kernel(const __grid_constant__ 
     *reinterpret_cast<uint4*>(s_wp + (j >> 3) * 8192 + sw128(r, j & 7)) =
         *reinterpret_cast<const uint4*>(p.wproj + r * HID + j * 8);
   }
-  for (int i = tid; i < NTOK * (DH / 2); i += NTH) { s_cos[i] = p.rcos[i]; s_sin[i] = p.rsin[i]; }
+  for (int i = tid; i < NTOK * (DH / 2); i += NTH) {    // global [pos][pair] -> shared [pair][pos]: lanes (= tokens) read
+    s_cos[(i & 7) * NTOK + (i >> 3)] = p.rcos[i];       // consecutive words (the [pos][pair] layout was an 8-way bank conflict)
+    s_sin[(i & 7) * NTOK + (i >> 3)] = p.rsin[i];
+  }
   for (int i = tid; i < C; i += NTH) { s_gamma[i] = p.gamma[i]; s_pbias[i] = p.proj_bias ? p.proj_bias[i] : 0.f; }
   for (int i = tid; i < HEADS * TBLP; i += NTH) {
     const int h = i / TBLP, e = i % TBLP;
@@ -290,7 +293,7 @@ __global__ void __launch_bounds__(NTH, 1) stw_tc_kernel(const __grid_constant__ 
       const float sc = region == 0 ? qscale : 1.0f;
 #pragma unroll
       for (int pr = 0; pr < 8; ++pr) {
-        const float cs = s_cos[pos * 8 + pr], sn = s_sin[pos * 8 + pr];
+        const float cs = s_cos[pr * NTOK + pos], sn = s_sin[pr * NTOK + pos];
         const float x0 = f[2 * pr] * sc, x1 = f[2 * pr + 1] * sc;
         f[2 * pr] = x0 * cs - x1 * sn;
         f[2 * pr + 1] = x1 * cs + x0 * sn;

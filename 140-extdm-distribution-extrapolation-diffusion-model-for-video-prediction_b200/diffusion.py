@@ -130,9 +130,9 @@ class GaussianDiffusion(nn.Module):
         r.run_prologue()
         r.x.copy_(noise[0])
         q = float(self.dynamic_thres_percentile)
+        ss = r.ss_for_times([s_[0] for s_ in sched])       # evaluated once per schedule, outside the captured loop
         for i, (time, time_next, c_recip, c_recipm1, san, c, sigma) in enumerate(sched):
-            r.time.fill_(time)
-            r.run_step()
+            r.run_step(ss[i])
             ops.ddim_threshold(rec, r.x, r.out, c_recip, c_recipm1, q, s)
             nz = noise[i + 1] if (time_next > 0 and i + 1 < noise.shape[0]) else None
             if time_next > 0 and nz is None:

@@ -117,11 +117,10 @@ class UnetRunner:
     # no faster on B200 (800 vs 716 + 98 us per level-0 pair: the attention kernel is compute bound and the extra
     # element-wise work lands on its critical path), so it is off by default.
     fuse_gn_stw = False
-    # The fused temporal kernel also exists for dim_head 32 (u12 / base / ada_u22; parity green in
-    # test_temporal_fused_layer), but with its doubled register-resident weights it runs one CTA per SM and the short
-    # sequences of those configurations (T = 12 ... 15 padded to 32 tokens) waste half of every tile: measured SMMNIST
-    # 1655 -> 1543 frames/s, BAIR 3205 -> 3226.  Off by default until it has a 16-token variant.
-    fuse_temporal_dh32 = False
+    # dim_head 32 (u12 / base / ada_u22): the fused temporal layer runs on the tcgen05 kernel of csrc/attn_tc32.cu
+    # (16-token packing for T <= 16: eight pixel sequences per M = 128 tile).  The earlier mma.sync edition
+    # (EXTDM_ATTN32_LEGACY=1) padded T = 12 ... 15 to 32 tokens and lost to the un-fused path.
+    fuse_temporal_dh32 = True
 
     def __init__(self, packed, B, H=32, W=32, fea_hw=16):
         cfg = packed.cfg
@@ -139,6 +138,10 @@ class UnetRunner:
         self.ss = torch.zeros(B, packed.n_ss, **f32)
         self.prologue = ops.Recorder(record=True)
         self.step = ops.Recorder(record=True)
+        # time embedding + the 20 per-block (scale, shift) MLPs: depends on the timestep and the weights only, so the
+        # sampler evaluates it once per schedule (ss_for_times) instead of once per DDIM step and round
+        self.time_rec = ops.Recorder(record=True)
+        self._ss_tables = {}
         self.taps = {}                      # name -> buffer, for layer-by-layer parity tests
         self.ddim_graphs = {}               # CUDA graphs of the sampling loop over these buffers (GaussianDiffusion)
         self._build()
@@ -455,7 +458,7 @@ class UnetRunner:
         d = cfg.dim
         x = self._temporal(st, x0, "init_temporal_attn")
         self.taps["init_temporal_attn"] = x
-        ops.time_mlp(st, self.time, pk.f32["time_mlp.1.weight"], pk.f32["time_mlp.1.bias"],
+        ops.time_mlp(self.time_rec, self.time, pk.f32["time_mlp.1.weight"], pk.f32["time_mlp.1.bias"],
                      pk.f32["time_mlp.3.weight"], pk.f32["time_mlp.3.bias"], pk.wss, pk.bss, self.ss, d)
 
         levels = cfg.levels
@@ -522,8 +525,27 @@ class UnetRunner:
     def run_prologue(self):
         self.prologue.run()
 
-    def run_step(self):
+    def run_step(self, ss=None):
+        """One Unet3D forward on the static buffers.  ss: pre-computed (scale, shift) rows for this timestep
+        (ss_for_times); None evaluates the time MLPs from self.time."""
+        if ss is None:
+            self.time_rec.run()
+        else:
+            self.ss.copy_(ss)
         self.step.run()
+
+    def ss_for_times(self, times):
+        """(len(times), B, n_ss): the ResnetBlocks' time-conditioned (scale, shift) for each sampling timestep
+        (...cross_multi.py:812-817, :185-188), cached per schedule."""
+        key = tuple(int(t) for t in times)
+        if key not in self._ss_tables:
+            rows = []
+            for t in key:
+                self.time.fill_(t)
+                self.time_rec.run()
+                rows.append(self.ss.clone())
+            self._ss_tables[key] = torch.stack(rows)
+        return self._ss_tables[key]
 
 
 class Unet3D(ParamTree):

@@ -489,15 +489,26 @@ def test_lfae_helpers():
                                                      ((2, 4, 4), 32, 64, 12, 32, True), ((2, 4, 4), 32, 64, 14, 16, False),
                                                      ((2, 4, 4), 32, 64, 5, 8, False), ((2, 4, 4), 32, 64, 2, 4, True),
                                                      ((2, 4, 4), 32, 64, 3, 4, False)])
-@pytest.mark.parametrize("impl", ["default", "EXTDM_STW8", "EXTDM_STW16"])
-def test_stw_fused_layer(window, dh, C, T, H, shifted, impl):
+@pytest.mark.parametrize("impl", ["default", "EXTDM_STW8", "EXTDM_STW16", "EXTDM_STW32_TC"])
+def test_stw_fused_layer(window, dh, C, T, H, shifted, impl, request):
     """Whole Residual(PreNorm(STWAttentionLayer)) in one kernel vs the oracle's stw_attention (CPU fp32), for each of
     the three implementations of the C = 64 / 64-token layer (tcgen05 projections = default, 8-warp mma.sync,
     16-warp mma.sync).  The library reads the switch once per process, so the non-default ones run in a child process."""
     if impl != "default":
+        import subprocess, sys, os
+        if impl == "EXTDM_STW32_TC":                       # all-tcgen05 kernel of the (2,4,4) / dim_head-32 layer
+            if window != (2, 4, 4):
+                pytest.skip("EXTDM_STW32_TC selects the tcgen05 kernel of the (2,4,4) / dim_head-32 layer")
+            if os.environ.get(impl):
+                pytest.skip("already inside the child process")
+            env = dict(os.environ, **{impl: "1"})
+            me = request.node.name.replace(impl, "default")
+            r = subprocess.run([sys.executable, "-m", "pytest", f"{__file__}::{me}", "-q", "-x"], env=env,
+                               capture_output=True, text=True)
+            assert r.returncode == 0 and "1 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+            return
         if not (window == (4, 4, 4) and C == 64):
             pytest.skip("alternative implementations exist for C = 64 / (4,4,4) only")
-        import subprocess, sys, os
         env = dict(os.environ, **{impl: "1"})
         shifted_id = {(7, True): "window0", (7, False): "window1", (30, True): "window4"}[(T, shifted)]
         r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-k",
@@ -518,8 +529,8 @@ def test_stw_fused_layer(window, dh, C, T, H, shifted, impl):
     xc = to_cl(x)
     y = torch.zeros_like(xc)
     shift = tuple(w // 2 for w in window) if shifted else (0, 0, 0)
-    if T <= window[0]:
-        shift = (0,) + shift[1:]                            # get_window_size: a dim no larger than its window is not shifted
+    # get_window_size (...cross_multi.py:393-406): a dim no larger than its window is not shifted
+    shift = tuple(0 if size <= w else sft for size, w, sft in zip((T, H, H), window, shift))
     rc, rs = _rope_tables(N, dh)
     assert ops.stw_fused_supported(C, heads, dh, window)
     ops.stw_fused(R, xc, y, sd["fn.norm.gamma"].reshape(-1).to(DEV), sd["fn.fn.attn.qkv.weight"].to(DEV).to(BF),
