@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libextdm_b200.so")
 BUILD = os.path.join(HERE, "build")
-SOURCES = ["api.cu", "conv_gemm.cu", "unet_elementwise.cu", "attention.cu", "stw_fused.cu", "stw_tc.cu", "attn_tc32.cu", "traj.cu", "lfae_cond.cu", "sampler.cu", "warp.cu"]
+SOURCES = ["api.cu", "conv_gemm.cu", "unet_elementwise.cu", "attention.cu", "stw_fused.cu", "stw_tc.cu", "attn_ws32.cu", "traj.cu", "lfae_cond.cu", "sampler.cu", "warp.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

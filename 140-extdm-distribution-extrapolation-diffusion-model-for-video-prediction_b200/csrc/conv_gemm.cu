@@ -1037,3 +1037,13 @@ extern "C" int extdm_conv_gemm(const ExtdmGemm* g, void* stream_) {
   }
 #undef PLAIN
 }
+
+// bf16 row-major matrix [rows][cols] -> 2-D tiled map with 128-byte swizzle, box = [box_rows][64 columns]; used by the
+// attention kernels of the other translation units (declared in common.cuh)
+int extdm_encode_matrix_map(CUtensorMap* map, const void* base, int rows, int cols, int box_rows) {
+  using namespace extdm;
+  cuuint64_t d[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t st[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t bx[2] = {64u, (cuuint32_t)box_rows};
+  return encode_map(map, base, 2, d, st, bx, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+}

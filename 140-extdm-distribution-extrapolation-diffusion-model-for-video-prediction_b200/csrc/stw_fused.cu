@@ -950,11 +950,12 @@ int extdm_stw_tc_launch(const void* x, void* y, const float* gamma, const void* 
                         const float* proj_bias, const float* bias_table, const float* rope_cos, const float* rope_sin,
                         int B, int T, int H, int W, int sd, int sh, int sw, float eps, void* stream);
 
-// tcgen05 edition of the dim_head-32 layers (attn_tc32.cu): (2,4,4) windows and temporal sequences, C = 64
-int extdm_stw_tc32_launch(const void* x, void* y, const float* gamma, const void* wqkv, const void* wproj,
+// tcgen05 edition of the dim_head-32 layers, C = 64 (attn_ws32.cu): (2,4,4) windows and temporal sequences; warp-specialised
+// (drain / softmax / issue / load roles), softmax output kept in tensor memory
+int extdm_stw_ws32_launch(const void* x, void* y, const float* gamma, const void* wqkv, const void* wproj,
                           const float* proj_bias, const float* bias_table, const float* rope_cos, const float* rope_sin,
                           int B, int T, int H, int W, int C, int sd, int sh, int sw, float eps, void* stream);
-int extdm_temporal_tc32_launch(const void* x, void* y, const float* gamma, const float* ln_w, const float* ln_b,
+int extdm_temporal_ws32_launch(const void* x, void* y, const float* gamma, const float* ln_w, const float* ln_b,
                                const void* wqkv, const void* wout, const float* rel_bias, const float* rope_cos,
                                const float* rope_sin, int B, int T, int HW, int C, float eps, void* stream);
 
@@ -1020,11 +1021,12 @@ static int stw_fused_impl(const void* x, void* y, const float* gamma, const void
     return launch_stw16<64, 16, 64>(p, st);
   }
   if (ntok == 64 && C == 128) return launch_stw<64, 16, 128>(p, st);
-  // (2,4,4) windows, 8 heads x 32: the all-tcgen05 kernel (attn_tc32.cu) behind EXTDM_STW32_TC=1 until its phases are
-  // overlapped -- first version, B200, BAIR level 0: 422 us vs 345 us for the mma.sync kernel (gpurun_out/attn32_bench.log)
-  static const bool tc32 = getenv("EXTDM_STW32_TC") != nullptr;
-  if (tc32) {
-    const int rc = extdm_stw_tc32_launch(x, y, gamma, wqkv, wproj, proj_bias, bias_table, rope_cos, rope_sin, B, T, H, W,
+  // (2,4,4) windows, 8 heads x 32: every product on tcgen05 (attn_ws32.cu).  B200, BAIR level 0 (393 k tokens): 243 us vs
+  // 345 us for the mma.sync kernel below, which stays as the fallback for geometries the tcgen05 kernel does not take
+  // (H/4 or W/4 not a power of two) and as A/B partner behind EXTDM_ATTN32_LEGACY=1.
+  static const bool legacy32 = getenv("EXTDM_ATTN32_LEGACY") != nullptr;
+  if (!legacy32) {
+    const int rc = extdm_stw_ws32_launch(x, y, gamma, wqkv, wproj, proj_bias, bias_table, rope_cos, rope_sin, B, T, H, W,
                                          C, sd, sh, sw, eps, stream);
     if (rc != -1) return rc;
   }
@@ -1087,11 +1089,11 @@ extern "C" int extdm_temporal_fused(const void* x, void* y, const float* gamma, 
   p.Dp = 32;
   p.n_windows = B * HW;
   p.eps = eps;
-  // dim_head 32 (u12 / base / ada_u22): tcgen05 kernel (attn_tc32.cu); the mma.sync one behind EXTDM_ATTN32_LEGACY
+  // dim_head 32 (u12 / base / ada_u22): tcgen05 kernel (attn_ws32.cu); the mma.sync one behind EXTDM_ATTN32_LEGACY
   if (dh == 32) {
     static const bool legacy32 = getenv("EXTDM_ATTN32_LEGACY") != nullptr;
     if (!legacy32) {
-      const int rc = extdm_temporal_tc32_launch(x, y, gamma, ln_w, ln_b, wqkv, wout, rel_bias, rope_cos, rope_sin, B, T,
+      const int rc = extdm_temporal_ws32_launch(x, y, gamma, ln_w, ln_b, wqkv, wout, rel_bias, rope_cos, rope_sin, B, T,
                                                 HW, C, eps, stream);
       if (rc != -1) return rc;
     }

@@ -117,7 +117,7 @@ class UnetRunner:
     # no faster on B200 (800 vs 716 + 98 us per level-0 pair: the attention kernel is compute bound and the extra
     # element-wise work lands on its critical path), so it is off by default.
     fuse_gn_stw = False
-    # dim_head 32 (u12 / base / ada_u22): the fused temporal layer runs on the tcgen05 kernel of csrc/attn_tc32.cu
+    # dim_head 32 (u12 / base / ada_u22): the fused temporal layer runs on the tcgen05 kernel of csrc/attn_ws32.cu
     # (16-token packing for T <= 16: eight pixel sequences per M = 128 tile).  The earlier mma.sync edition
     # (EXTDM_ATTN32_LEGACY=1) padded T = 12 ... 15 to 32 tokens and lost to the un-fused path.
     fuse_temporal_dh32 = True

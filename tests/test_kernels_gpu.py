@@ -483,22 +483,22 @@ def test_lfae_helpers():
 @pytest.mark.parametrize("window,dh,C,T,H,shifted", [((4, 4, 4), 16, 64, 7, 16, True), ((4, 4, 4), 16, 64, 7, 16, False),
                                                      ((4, 4, 4), 16, 128, 6, 8, True), ((2, 4, 4), 32, 64, 5, 8, True),
                                                      ((4, 4, 4), 16, 64, 30, 32, True),
-                                                     # dim_head 32 / (2,4,4): the tcgen05 kernel of attn_tc32.cu -- BAIR
+                                                     # dim_head 32 / (2,4,4): the tcgen05 kernel of attn_ws32.cu -- BAIR
                                                      # (T = 12) and SMMNIST (T = 14) shapes, padded depth (T = 5), a
                                                      # depth no larger than the window (no depth shift), partial tile
                                                      ((2, 4, 4), 32, 64, 12, 32, True), ((2, 4, 4), 32, 64, 14, 16, False),
                                                      ((2, 4, 4), 32, 64, 5, 8, False), ((2, 4, 4), 32, 64, 2, 4, True),
                                                      ((2, 4, 4), 32, 64, 3, 4, False)])
-@pytest.mark.parametrize("impl", ["default", "EXTDM_STW8", "EXTDM_STW16", "EXTDM_STW32_TC"])
+@pytest.mark.parametrize("impl", ["default", "EXTDM_STW8", "EXTDM_STW16", "EXTDM_ATTN32_LEGACY"])
 def test_stw_fused_layer(window, dh, C, T, H, shifted, impl, request):
     """Whole Residual(PreNorm(STWAttentionLayer)) in one kernel vs the oracle's stw_attention (CPU fp32), for each of
     the three implementations of the C = 64 / 64-token layer (tcgen05 projections = default, 8-warp mma.sync,
     16-warp mma.sync).  The library reads the switch once per process, so the non-default ones run in a child process."""
     if impl != "default":
         import subprocess, sys, os
-        if impl == "EXTDM_STW32_TC":                       # all-tcgen05 kernel of the (2,4,4) / dim_head-32 layer
+        if impl == "EXTDM_ATTN32_LEGACY":                  # the mma.sync kernel of the (2,4,4) / dim_head-32 layer (fallback)
             if window != (2, 4, 4):
-                pytest.skip("EXTDM_STW32_TC selects the tcgen05 kernel of the (2,4,4) / dim_head-32 layer")
+                pytest.skip("EXTDM_ATTN32_LEGACY selects the mma.sync kernel of the (2,4,4) / dim_head-32 layer")
             if os.environ.get(impl):
                 pytest.skip("already inside the child process")
             env = dict(os.environ, **{impl: "1"})

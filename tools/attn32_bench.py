@@ -1,5 +1,5 @@
 """Time the dim_head-32 attention layers at the BAIR / SMMNIST level-0 shapes (CUDA events, 20 launches each).
-   python tools/attn32_bench.py            # tcgen05 kernel (attn_tc32.cu)
+   python tools/attn32_bench.py            # tcgen05 kernel (attn_ws32.cu); EXTDM_ATTN32_PROF=1 prints per-role cycles
    EXTDM_ATTN32_LEGACY=1 python tools/attn32_bench.py   # the mma.sync kernels"""
 import os
 import sys
