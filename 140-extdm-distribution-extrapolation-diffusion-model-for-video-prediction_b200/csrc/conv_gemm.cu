@@ -406,15 +406,20 @@ __device__ __forceinline__ void epilogue_simple(const GemmDev& p, uint64_t* acc_
         gst[0] += __shfl_xor_sync(0xffffffffu, gst[0], 4);
         gst[0] += __shfl_xor_sync(0xffffffffu, gst[0], 2);
         gst[0] += __shfl_xor_sync(0xffffffffu, gst[0], 1);
-        constexpr int kCpg = BN / 8;                   // columns per GroupNorm group
-        constexpr int kRec = BN == 256 ? 2 : 1;        // records per (tile, quarter)
-        float* rec = p.gn_part + ((static_cast<long long>(tc.m_tile) * 4 + q) * kRec + (BN == 256 ? (ch & 1) : 0)) * 16;
+        // Channels per GroupNorm group over ALL p.n output channels (the tile may be one of several n-tiles): a 16-column
+        // chunk holds two groups (cpg 8), one group (16) or a 1/2, 1/4 slice of a group (32, 64).  Slices of one group go
+        // to different records (krec per (m-tile, quarter)) so that no two warps ever add into the same float; every
+        // float of every record is written by exactly one (n-tile, warp), groupnorm_apply folds the records.
+        const int cpg = p.n >> 3;
+        const int krec = cpg >= 32 ? (cpg >> 4) : 1;
+        const int gcol = n0 + ch * 16;                 // first output channel of this chunk
+        float* rec = p.gn_part + ((static_cast<long long>(tc.m_tile) * 4 + q) * krec + ((gcol >> 4) & (krec - 1))) * 16;
         const int stat = lane >> 4;                    // lanes 0 / 8 -> sums, 16 / 24 -> sums of squares
-        if (kCpg == 8) {
-          if ((lane & 7) == 0) rec[stat * 8 + 2 * ch + ((lane >> 3) & 1)] = gst[0];
+        if (cpg == 8) {
+          if ((lane & 7) == 0) rec[stat * 8 + (gcol >> 3) + ((lane >> 3) & 1)] = gst[0];
         } else {
           const float tot = gst[0] + __shfl_xor_sync(0xffffffffu, gst[0], 8);       // lo8 + hi8 of this chunk
-          if ((lane & 15) == 0) rec[stat * 8 + (kCpg == 16 ? ch : (ch >> 1))] = tot;
+          if ((lane & 15) == 0) rec[stat * 8 + gcol / cpg] = tot;
         }
       }
     }
@@ -922,7 +927,21 @@ extern "C" int extdm_conv_gemm(const ExtdmGemm* g, void* stream_) {
   }
 
   int bn = g->block_n;
-  if (bn == 0) bn = g->n <= 16 ? 16 : (g->n <= 64 ? 64 : (g->n <= 128 || g->n % 256 ? 128 : 256));
+  if (bn == 0) {
+    bn = g->n <= 16 ? 16 : (g->n <= 64 ? 64 : (g->n <= 128 || g->n % 256 ? 128 : 256));
+    // Small-M shapes (the 8 x 8 and 4 x 4 UNet levels, small batches): with few 128-row tiles a wide n-tile leaves most
+    // SMs idle and the launch is latency bound (profiles/kernel_table_r2.md: rows = 15360, n = 256 at 47 TFLOP/s).
+    // Narrower n-tiles multiply the CTA count; the A tile is re-read from L2 once per n-tile, which is free at these sizes.
+    static const bool no_split = getenv("EXTDM_GEMM_NO_NSPLIT") != nullptr;
+    // Measured on B200 (gpurun_out/configs_r2[e-h].md): halving while the narrower tiling still fits the resident CTA slots
+    // (2 per SM) gains 3-5 % on BAIR / UCF / Cityscapes, but the K >= 4096 convolutions of the 512-channel SMMNIST level
+    // lose 8 % with tiles narrower than one wave allows (BN <= 128 tiles are shared-memory bound).
+    if (!no_split && !g->tf32) {
+      const long long ktot_ = static_cast<long long>(g->ntaps) * (dev.nk0 + dev.nk1) * kBlockK;
+      const long long slots = (ktot_ >= 4096 ? 1ll : 2ll) * sm_count();
+      while (bn > 64 && g->n % (bn / 2) == 0 && static_cast<long long>(m_tiles) * (g->n / (bn / 2)) <= slots) bn /= 2;
+    }
+  }
   if (bn != 16 && bn != 64 && bn != 128 && bn != 256) {
     extdm_set_error("extdm_conv_gemm: block_n must be 16, 64, 128 or 256", __FILE__, __LINE__);
     return EXTDM_ERR_ARG;
@@ -987,8 +1006,9 @@ extern "C" int extdm_conv_gemm(const ExtdmGemm* g, void* stream_) {
   rc = encode_map(&mb, g->w, 2, wd, ws, wb, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
   if (rc) return rc;
 
-  if (g->gn_partials && (g->n != bn || bn < 64 || !simple || g->box[3] != 1)) {
-    extdm_set_error("extdm_conv_gemm: gn_partials needs n in {64,128,256} (= block_n), a bias-only bf16 epilogue, box[3] == 1",
+  if (g->gn_partials && ((g->n != 64 && g->n != 128 && g->n != 256 && g->n != 512) || g->n % bn || bn < 64 || !simple ||
+                         g->box[3] != 1)) {
+    extdm_set_error("extdm_conv_gemm: gn_partials needs n in {64,128,256,512}, block_n | n, a bias-only bf16 epilogue, box[3] == 1",
                     __FILE__, __LINE__);
     return EXTDM_ERR_ARG;
   }

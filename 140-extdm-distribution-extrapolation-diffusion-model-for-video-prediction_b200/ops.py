@@ -266,9 +266,10 @@ def conv_tiles_per_sample(T, H, W):
 
 
 def gn_parts_per_sample(T, H, W, Cc):
-    """GroupNorm partial records (16 floats each) one sample's convolution epilogue writes: one per (128-row tile,
-    TMEM lane quarter), two for 256 channels (include/extdm_b200.h: ExtdmGemm.gn_partials)."""
-    return conv_tiles_per_sample(T, H, W) * 4 * (2 if Cc == 256 else 1)
+    """GroupNorm partial records (16 floats each) one sample's convolution epilogue writes: per (128-row tile, TMEM lane
+    quarter) one record, or C/128 of them when a group is wider than a 16-column chunk (C = 256: 2, C = 512: 4) --
+    include/extdm_b200.h: ExtdmGemm.gn_partials."""
+    return conv_tiles_per_sample(T, H, W) * 4 * max(1, Cc // 128)
 
 
 GN_CHUNKS = 32          # EXTDM_GN_CHUNKS

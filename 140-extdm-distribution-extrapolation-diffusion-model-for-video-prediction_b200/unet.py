@@ -238,7 +238,7 @@ class UnetRunner:
         B, T, H, W, _ = x.shape
         h1 = self.buf(B, T, H, W, cout)
         # GroupNorm statistics come out of the convolution's epilogue (per-tile partial sums), not a second pass
-        fused = cfg.groups == 8 and cout in (64, 128, 256)
+        fused = cfg.groups == 8 and cout in (64, 128, 256, 512)
         npart = ops.gn_parts_per_sample(T, H, W, cout) if fused else None
         gnp = self.gn_ws if fused else None
         ops.conv_cl(rec, x, pk.w[p + ".block1.proj.weight"], cout, 3, h1, x2=x2, bias=pk.f32[p + ".block1.proj.bias"],

@@ -71,9 +71,11 @@ typedef struct ExtdmGemm {
   /* Optional GroupNorm(8) statistics of the stored (bf16) output, fused into the epilogue.  Every epilogue warp writes
    * its own slots of a 16-float record [8 group sums | 8 group sums of squares]; record index =
    * (tile*4 + q)*R + r with tile = 128-row tile (ordered D1 fastest .. D4 slowest, so a sample's tiles are
-   * contiguous), q = 32-row quarter of the tile, R = 2 and r = 16-column chunk parity for n = 256, R = 1 otherwise.
-   * A group's statistic is the sum over the sample's records.  Requires n == block_n in {64,128,256}, a bias(+act)-only
-   * bf16 epilogue, box[3] == 1.  Consumed by extdm_groupnorm_apply (n_part = records per sample). */
+   * contiguous), q = 32-row quarter of the tile, R = max(1, n/128) records because a group wider than a 16-column chunk
+   * (n = 256: 2 chunks, n = 512: 4) is summed per chunk, r = (first column of the chunk / 16) mod R.  The output may be
+   * cut into several n-tiles (block_n | n): each writes the slots of its own groups.  A group's statistic is the sum
+   * over the sample's records.  Requires n in {64,128,256,512}, a bias(+act)-only bf16 epilogue, box[3] == 1.
+   * Consumed by extdm_groupnorm_apply (n_part = records per sample). */
   float* gn_partials;
   /* 1: the A tensors and W hold fp32 and the product runs as tcgen05 kind::tf32 (fp32 accumulate) -- the precision the
    * reference's GPU convolutions run at (cudnn.allow_tf32 defaults to True, never changed by scripts/DM/valid.py).  All

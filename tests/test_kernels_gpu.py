@@ -161,7 +161,10 @@ def test_groupnorm_silu(C, T, H):
     close(from_cl(y2), F.silu(F.group_norm(xf, 8, g, b, eps=1e-5)), rel=1e-2, what="groupnorm plain")
 
 
-@pytest.mark.parametrize("C,T,H,B", [(64, 5, 32, 2), (128, 3, 16, 3), (256, 7, 8, 2), (256, 30, 4, 2), (64, 30, 32, 4)])
+@pytest.mark.parametrize("C,T,H,B", [(64, 5, 32, 2), (128, 3, 16, 3), (256, 7, 8, 2), (256, 30, 4, 2), (64, 30, 32, 4),
+                                     # n-split tiles (few 128-row tiles -> narrower n-tiles, several CTAs fill one record)
+                                     # and the 512-channel level of the SMMNIST UNet (a group = 64 columns = 4 chunks)
+                                     (512, 14, 4, 2), (256, 12, 4, 32), (128, 12, 8, 4), (512, 14, 4, 32)])
 def test_conv_epilogue_groupnorm_partials(C, T, H, B):
     """conv(1,3,3) whose epilogue emits the per-tile GroupNorm partial sums, followed by groupnorm_apply: equals
     conv -> GroupNorm -> SiLU of the fp32 statement; the partials equal sums over the stored bf16 tensor."""
