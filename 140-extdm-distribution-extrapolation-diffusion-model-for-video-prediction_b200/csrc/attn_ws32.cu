@@ -61,14 +61,14 @@ struct Lay {
   static constexpr int vt = k + 16384;                       // 2 x V^T: 2 k-blocks x [64][64] SW128, ping-pong by group
   static constexpr int o = vt + 2 * 16384;                   // [128][64] SW128: O_g (A of the output projection)
   static constexpr int bias = o + 16384;                     // [8][TP][TP] bf16 * log2(e), chunk-swizzled
-  static constexpr int rope = bias + 16384;                  // cos, sin [16 pairs][32 positions] fp32
+  static constexpr int rope = bias + 16384;                  // (cos, sin) float2 [16 pairs][32 positions]
   static constexpr int vec = rope + 4096;                    // gamma, ln_w, ln_b, proj bias: 4 x 64 fp32
   static constexpr int stat = vec + 1024;                    // 2 x [128] (mean, rstd), ping-pong by tile
   static constexpr int bars = stat + 2048;                   // mbarriers + TMEM slot
   static constexpr int total = bars + 128;
 };
 enum Bar { B_QKV_DONE = 0, B_QKV_FREE, B_QK_READY, B_S_DONE, B_P_READY, B_O_DONE, B_O_READY, B_D_DONE, B_D_FREE,
-           B_A_READY, B_WQ_READY /* two: one per ring slot */, B_WQ_READY1, B_WP_READY, B_TOK_READY, B_COUNT };
+           B_A_READY, B_WQ_READY /* two: one per ring slot */, B_WQ_READY1, B_WP_READY, B_COUNT };
 
 // EXTDM_ATTN32_PROF=1: cycle counts of CTA 0, one thread per role, printed by the launcher
 //   [0..3] drain: wait QKV | drain QKV | wait O | drain O      [4..7] softmax: wait S | softmax | LN | epilogue
@@ -94,7 +94,7 @@ struct P32 {
 };
 
 // TP = tokens per attention unit in the tile (32: a (2,4,4) window or a sequence of 17..32 frames; 16: T <= 16)
-template <int TP, bool TEMPORAL>
+template <int TP, bool TEMPORAL, bool PROF>
 __global__ void __launch_bounds__(NTH, 1) attn_ws32_kernel(const __grid_constant__ P32 p,
                                                            const __grid_constant__ CUtensorMap map_wq,
                                                            const __grid_constant__ CUtensorMap map_wp) {
@@ -106,8 +106,7 @@ __global__ void __launch_bounds__(NTH, 1) attn_ws32_kernel(const __grid_constant
   uint8_t* s_k = sm + L::k;
   uint8_t* s_o = sm + L::o;
   uint8_t* s_bias = sm + L::bias;
-  float* s_cos = reinterpret_cast<float*>(sm + L::rope);
-  float* s_sin = s_cos + 32 * 16;
+  float2* s_rope = reinterpret_cast<float2*>(sm + L::rope);   // (cos, sin) [16 pairs][32 positions]
   float* s_gamma = reinterpret_cast<float*>(sm + L::vec);
   float* s_lnw = s_gamma + C;
   float* s_lnb = s_lnw + C;
@@ -160,8 +159,7 @@ __global__ void __launch_bounds__(NTH, 1) attn_ws32_kernel(const __grid_constant
 
   // ---- one-time staging (all threads): resident Wproj, rope / bias tables, vectors; barriers; TMEM
   for (int i = tid; i < 32 * 16; i += NTH) {                // global [pos][pair] -> shared [pair][pos]
-    s_cos[(i & 15) * 32 + (i >> 4)] = p.rcos[i];
-    s_sin[(i & 15) * 32 + (i >> 4)] = p.rsin[i];
+    s_rope[(i & 15) * 32 + (i >> 4)] = make_float2(p.rcos[i], p.rsin[i]);
   }
   for (int i = tid; i < C; i += NTH) {
     s_gamma[i] = p.gamma[i];
@@ -196,11 +194,10 @@ __global__ void __launch_bounds__(NTH, 1) attn_ws32_kernel(const __grid_constant
     mbar_init(bars + B_O_READY, NS);
     mbar_init(bars + B_D_DONE, 1);
     mbar_init(bars + B_D_FREE, ND);
-    mbar_init(bars + B_A_READY, ND);                       // tile 0: drain group (prologue); later tiles: softmax group
+    mbar_init(bars + B_A_READY, ND);
     mbar_init(bars + B_WQ_READY, 1);                        // expect_tx arrival of the thread that issues the TMA loads
     mbar_init(bars + B_WQ_READY1, 1);
     mbar_init(bars + B_WP_READY, 1);
-    mbar_init(bars + B_TOK_READY, ND);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -213,10 +210,10 @@ __global__ void __launch_bounds__(NTH, 1) attn_ws32_kernel(const __grid_constant
   tc_fence_after();
   const uint32_t tmem_u = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-  const bool prof = p.prof && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 8 || warp == 16);
-  long long tk = prof ? clock64() : 0;
+  const bool prof = PROF && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 8 || warp == 16);
+  long long tk = (PROF && prof) ? clock64() : 0;
   auto tick = [&](int slot) {
-    if (prof) {
+    if (PROF && prof) {
       const long long now = clock64();
       g_prof_ws[slot] += static_cast<unsigned long long>(now - tk);
       tk = now;
@@ -460,7 +457,8 @@ __global__ void __launch_bounds__(NTH, 1) attn_ws32_kernel(const __grid_constant
             const float sc = region == 0 ? qscale : 1.0f;
 #pragma unroll
             for (int pr = 0; pr < 8; ++pr) {
-              const float cs = s_cos[((d0 >> 1) + pr) * 32 + pos], sn = s_sin[((d0 >> 1) + pr) * 32 + pos];
+              const float2 rp = s_rope[((d0 >> 1) + pr) * 32 + pos];
+              const float cs = rp.x, sn = rp.y;
               const float x0 = f[2 * pr] * sc, x1 = f[2 * pr + 1] * sc;
               f[2 * pr] = x0 * cs - x1 * sn;
               f[2 * pr + 1] = x1 * cs + x0 * sn;
@@ -486,15 +484,23 @@ __global__ void __launch_bounds__(NTH, 1) attn_ws32_kernel(const __grid_constant
       tick(1);
       // ---- per-tile work of this group, spread over the tile's groups:
       //   g == 0  request the next tile's tokens (their buffer's last reader, QKV(G-1), retired before QKV(G))
-      //   g == 1  hand the landed tokens to the softmax group (LayerNorm); the previous tile's epilogue
+      //   g == 1  the previous tile's epilogue (its last out-proj retired a drain ago)
+      //   g == 2  the next tile's channel LayerNorm, in place on the landed tokens
       const int g = G & 3, it = G >> 2;
       if (g == 0 && it + 1 < my_tiles) { load_tokens(it + 1, tid); cp_commit(); tick(7); }
       if (g == 0 && it >= 1) {                              // the previous tile's residual rows -> L1, for the epilogue a group later
         const int d = row_pixel(first + (it - 1) * stride, row);
         if (d >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.x + static_cast<long long>(d) * C + dw * 32));
       }
-      if (g == 1 && it + 1 < my_tiles) { cp_wait_all(); mbar_arrive(bars + B_TOK_READY); }
       if (g == 1 && it >= 1) { epilogue(it - 1); tick(12); }
+      if (g == 2 && it + 1 < my_tiles) {                    // the softmax chain is the critical one: LayerNorm runs here
+        cp_wait_all();
+        group_barrier(1, ND);                               // every thread's copies landed; epilogue(it-1) has read its stats
+        layernorm(it + 1, tid);
+        fence_proxy_async();
+        mbar_arrive(bars + B_A_READY);
+        tick(6);
+      }
     }
     epilogue(my_tiles - 1);
   } else {
@@ -505,6 +511,7 @@ __global__ void __launch_bounds__(NTH, 1) attn_ws32_kernel(const __grid_constant
     const int stid = tid - 256;                             // 0..255 within the group
     const uint32_t tlane = tmem_u + (static_cast<uint32_t>(dq * 32) << 16);
     constexpr float kMask = -100.0f * kL2e;
+    uint32_t same = 0xffffffffu;                            // keys of this row's window that share its Swin region id
     auto drain_o = [&](int G) {                             // O of head hh -> bf16 -> chunks [4 hh, 4 hh + 4) of the O tile
       mbar_wait(bars + B_O_DONE, G & 1);
       tc_fence_after();
@@ -575,15 +582,19 @@ __global__ void __launch_bounds__(NTH, 1) attn_ws32_kernel(const __grid_constant
           for (int j = 0; j < TP; ++j)
             if (j >= p.T) s[j] = -1.0e30f;                  // padded frames are not keys
         } else {
-          const Unit w = decode(tile * NU + dq);            // TP == 32: the warp's 32 lanes are one window
-          if (unit_masked(w)) {                             // -100 where the Swin region ids of query and key differ
-            const int code = region_code(w, lane);
-            uint32_t same = 0;
+          if (g == 0) {                                     // per tile: TP == 32, the warp's 32 lanes are one window
+            const Unit w = decode(tile * NU + dq);
+            same = 0xffffffffu;
+            if (unit_masked(w)) {                           // -100 where the Swin region ids of query and key differ
+              const int code = region_code(w, lane);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const uint32_t bal = __ballot_sync(0xffffffffu, code == c);
-              if (code == c) same = bal;
+              for (int c = 0; c < 8; ++c) {
+                const uint32_t bal = __ballot_sync(0xffffffffu, code == c);
+                if (code == c) same = bal;
+              }
             }
+          }
+          if (same != 0xffffffffu) {
 #pragma unroll
             for (int j = 0; j < TP; ++j)
               if (!((same >> j) & 1u)) s[j] += kMask;
@@ -599,7 +610,6 @@ __global__ void __launch_bounds__(NTH, 1) attn_ws32_kernel(const __grid_constant
         const float f = __fdividef(1.0f, (l4[0] + l4[1]) + (l4[2] + l4[3]));
         // P (bf16 pairs, K = 128 keys -> 64 columns) over the head's S columns: the row's own block, zeros elsewhere
         uint32_t pw[16];
-        const uint32_t z[16] = {};
         if (TP == 32) {
 #pragma unroll
           for (int e = 0; e < 16; ++e) pw[e] = pack_bf16(s[(2 * e) % TP] * f, s[(2 * e + 1) % TP] * f);
@@ -613,10 +623,13 @@ __global__ void __launch_bounds__(NTH, 1) attn_ws32_kernel(const __grid_constant
           }
         }
         tick(14);
+        {                                                   // (one x64 store with aliased zero registers measured slower)
+          const uint32_t z[16] = {};
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          if (b == dq) tmem_st16(sb + b * 16, pw);
-          else tmem_st16(sb + b * 16, z);
+          for (int b = 0; b < 4; ++b) {
+            if (b == dq) tmem_st16(sb + b * 16, pw);
+            else tmem_st16(sb + b * 16, z);
+          }
         }
         tmem_st_wait();
         tc_fence_before();
@@ -625,17 +638,8 @@ __global__ void __launch_bounds__(NTH, 1) attn_ws32_kernel(const __grid_constant
       tick(5);
       // ---- O of this head, as soon as its PV product retires: the output projection and the next group's scores wait on it
       drain_o(G);
-      // ---- the next tile's channel LayerNorm (its raw tokens were requested by the drain group a group ago); the stats
-      // buffer it writes was last read by epilogue(it-1), which the drain group finished before its drain of this group
-      if (g == 1 && it + 1 < my_tiles) {
-        mbar_wait(bars + B_TOK_READY, it & 1);
-        layernorm(it + 1, stid);
-        fence_proxy_async();
-        mbar_arrive(bars + B_A_READY);
-        tick(6);
-      }
     }
-    if (prof) g_prof_ws[15] = static_cast<unsigned long long>(n_groups);
+    if (PROF && prof) g_prof_ws[15] = static_cast<unsigned long long>(n_groups);
   }
 
   tc_fence_before();
@@ -651,7 +655,9 @@ int launch_ws(const P32& p, cudaStream_t st) {
   constexpr int smem = Lay::total + 1024;
   static SmemConfigured configured;
   if (!configured.covers(smem)) {
-    cudaError_t e = cudaFuncSetAttribute(attn_ws32_kernel<TP, TEMPORAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(attn_ws32_kernel<TP, TEMPORAL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_ws32_kernel<TP, TEMPORAL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
       extdm_set_error(cudaGetErrorString(e), __FILE__, __LINE__);
       return EXTDM_ERR_CUDA;
@@ -678,7 +684,8 @@ int launch_ws(const P32& p, cudaStream_t st) {
   if (rc) return rc;
   rc = extdm_encode_matrix_map(&map_wp, p.wproj, C, HID, 64);
   if (rc) return rc;
-  attn_ws32_kernel<TP, TEMPORAL><<<grid, NTH, smem, st>>>(q, map_wq, map_wp);
+  if (prof) attn_ws32_kernel<TP, TEMPORAL, true><<<grid, NTH, smem, st>>>(q, map_wq, map_wp);
+  else attn_ws32_kernel<TP, TEMPORAL, false><<<grid, NTH, smem, st>>>(q, map_wq, map_wp);
   if (prof) {
     unsigned long long h[24];
     cudaStreamSynchronize(st);
