@@ -9,11 +9,13 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libextdm_b200.so")
-BUILD = os.path.join(HERE, "build")
+# development only: EXTDM_BUILD_TAG=x EXTDM_NVCC_DEFS="-DFOO" builds libextdm_b200_x.so beside the product (lib.py: EXTDM_LIB)
+TAG = os.environ.get("EXTDM_BUILD_TAG", "")
+OUT = os.path.join(HERE, f"libextdm_b200{'_' + TAG if TAG else ''}.so")
+BUILD = os.path.join(HERE, "build" + ("_" + TAG if TAG else ""))
 SOURCES = ["api.cu", "conv_gemm.cu", "unet_elementwise.cu", "attention.cu", "stw_fused.cu", "stw_tc.cu", "attn_ws32.cu", "traj.cu", "lfae_cond.cu", "sampler.cu", "warp.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+              "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + os.environ.get("EXTDM_NVCC_DEFS", "").split()
 
 
 def _needs(obj, deps):

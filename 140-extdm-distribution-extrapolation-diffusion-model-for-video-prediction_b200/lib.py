@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libextdm_b200.so")
+LIB_PATH = os.environ.get("EXTDM_LIB") or os.path.join(_HERE, "libextdm_b200.so")    # EXTDM_LIB: A/B builds (build.py)
 
 
 class ExtdmGemm(C.Structure):
