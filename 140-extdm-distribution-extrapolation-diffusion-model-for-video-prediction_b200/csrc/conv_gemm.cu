@@ -40,6 +40,8 @@ struct GemmDev {
   float* gn_part;
   // halo kernel (k x k 'same' convolutions whose 128-row tile is bh full-width rows of one frame)
   int kh, kw, stages, a_ext_bytes;
+  int n_phase;    // >= 1: independent products over the same A tiles (ExtdmGemm.n_phase), phase = tile index digit
+  long long phase_out[4];
   int tf32;       // operands are fp32, product runs as kind::tf32 (ExtdmGemm.tf32)
   int prefetch;   // L2 prefetch of the tile two ahead (helps the multi-block shapes, measured per shape)
   int dbg;   // profiling experiments only (EXTDM_GEMM_DBG): 1 = no epilogue stores, 2 = no MMA issue, 4 = no TMA loads,
@@ -55,12 +57,19 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 struct TileCoord {
-  int c1, c2, c3, c4, n0, m_tile;
+  int c1, c2, c3, c4, n0, m_tile, phase;
 };
+// tile index digits, fastest first: n-tile, phase, D1 .. D4 tile -- neighbouring CTAs share the A tile
 __device__ __forceinline__ TileCoord decode_tile(const GemmDev& p, int tile, int BN) {
   TileCoord t;
   const int nt = tile % p.n_tiles_n;
   int tidx = tile / p.n_tiles_n;
+  if (p.n_phase > 1) {
+    t.phase = tidx % p.n_phase;
+    tidx /= p.n_phase;
+  } else {
+    t.phase = 0;
+  }
   t.m_tile = tidx;
   const int t0 = tidx % p.ntile[0]; tidx /= p.ntile[0];
   const int t1 = tidx % p.ntile[1]; tidx /= p.ntile[1];
@@ -101,8 +110,8 @@ __device__ __forceinline__ void epilogue_loop(const GemmDev& p, uint64_t* acc_fu
     const int g1 = tc.c1 + i1, g2 = tc.c2 + i2, g3 = tc.c3 + i3, g4 = tc.c4 + i4;
     const bool row_ok = g1 < p.start[0] + p.count[0] && g2 < p.start[1] + p.count[1] &&
                         g3 < p.start[2] + p.count[2] && g4 < p.start[3] + p.count[3];
-    const long long orow = p.out_base + g1 * p.out_stride[0] + g2 * p.out_stride[1] + g3 * p.out_stride[2] +
-                           g4 * p.out_stride[3];
+    const long long orow = p.out_base + p.phase_out[tc.phase] + g1 * p.out_stride[0] + g2 * p.out_stride[1] +
+                           g3 * p.out_stride[2] + g4 * p.out_stride[3];
     const long long rrow = p.res_base + g1 * p.res_stride[0] + g2 * p.res_stride[1] + g3 * p.res_stride[2] +
                            g4 * p.res_stride[3];
     // The accumulator is drained in groups of 4 chunks (64 columns): the group body is unrolled (static register
@@ -336,8 +345,8 @@ __device__ __forceinline__ void epilogue_simple(const GemmDev& p, uint64_t* acc_
     const int g1 = tc.c1 + i1, g2 = tc.c2 + i2, g3 = tc.c3 + i3, g4 = tc.c4 + i4;
     const bool row_ok = g1 < p.start[0] + p.count[0] && g2 < p.start[1] + p.count[1] &&
                         g3 < p.start[2] + p.count[2] && g4 < p.start[3] + p.count[3];
-    __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + p.out_base + g1 * p.out_stride[0] +
-                          g2 * p.out_stride[1] + g3 * p.out_stride[2] + g4 * p.out_stride[3] + n0;
+    __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + p.out_base + p.phase_out[tc.phase] +
+                          g1 * p.out_stride[0] + g2 * p.out_stride[1] + g3 * p.out_stride[2] + g4 * p.out_stride[3] + n0;
     if (n0 != staged_n0) {                 // uniform over the group's threads; named barrier 2 + grp
       if (staged_n0 >= 0) asm volatile("bar.sync %0, %1;" ::"r"(2 + grp), "n"(kGThreads) : "memory");
       for (int j = gt; j < BN; j += kGThreads) s_bias[j] = (p.bias && n0 + j < p.n) ? __ldg(p.bias + n0 + j) : 0.f;
@@ -508,8 +517,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
             }
           }
         }
+        const int tap0 = tc.phase * p.ntaps;      // phase: own taps, own weight rows
+        const int wrow = tc.n0 + tc.phase * p.n;
         for (int tap = 0; tap < p.ntaps; ++tap) {
-          const int o1 = p.tap[tap][0], o2 = p.tap[tap][1], o3 = p.tap[tap][2];
+          const int o1 = p.tap[tap0 + tap][0], o2 = p.tap[tap0 + tap][1], o3 = p.tap[tap0 + tap][2];
           for (int kc = 0; kc < nk; ++kc) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (p.dbg & 4) {
@@ -523,7 +534,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
               else
                 tma_load_5d(&map_a1, sa, &full_bar[stage], (kc - p.nk0) * kBlockK, tc.c1 + o1, tc.c2 + o2, tc.c3 + o3,
                             tc.c4);
-              tma_load_2d(&map_b, sb, &full_bar[stage], (tap * nk + kc) * kBlockK, tc.n0);
+              tma_load_2d(&map_b, sb, &full_bar[stage], (tap * nk + kc) * kBlockK, wrow);
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -875,6 +886,12 @@ extern "C" int extdm_conv_gemm(const ExtdmGemm* g, void* stream_) {
     extdm_set_error("extdm_conv_gemm: null operand", __FILE__, __LINE__);
     return EXTDM_ERR_ARG;
   }
+  const int n_phase = g->n_phase > 1 ? g->n_phase : 1;
+  if (n_phase > 4 || n_phase * g->ntaps > 64 || (n_phase > 1 && (g->gn_partials || g->tf32 || g->w_rows != n_phase * g->n))) {
+    extdm_set_error("extdm_conv_gemm: n_phase <= 4, n_phase*ntaps <= 64, w_rows == n_phase*n, no gn_partials / tf32", __FILE__,
+                    __LINE__);
+    return EXTDM_ERR_ARG;
+  }
   if (g->a0_channels <= 0 || g->a0_channels % kBlockK || g->a1_channels % kBlockK || g->ntaps < 1 || g->ntaps > 64 ||
       g->n < 1 || g->box[0] * g->box[1] * g->box[2] * g->box[3] != kTileM || g->col_group < 1) {
     extdm_set_error("extdm_conv_gemm: channels must be multiples of 64, 1..64 taps, box product 128", __FILE__,
@@ -916,6 +933,9 @@ extern "C" int extdm_conv_gemm(const ExtdmGemm* g, void* stream_) {
   dev.act = g->act;
   dev.gn_part = g->gn_partials;
   dev.tf32 = g->tf32;
+  dev.n_phase = n_phase;
+  for (int i = 0; i < 4; ++i) dev.phase_out[i] = (n_phase > 1 && i < n_phase) ? g->phase_out_offset[i] : 0;
+  m_tiles *= n_phase;                              // a phase is one more digit of the tile index
   static const int dbg_flags = getenv("EXTDM_GEMM_DBG") ? atoi(getenv("EXTDM_GEMM_DBG")) : 0;
   dev.dbg = dbg_flags;
   // measured on B200 (profiles/kernel_table_r1.md): the prefetch pays when a tile streams two or more 64-channel blocks
@@ -942,6 +962,10 @@ extern "C" int extdm_conv_gemm(const ExtdmGemm* g, void* stream_) {
       while (bn > 64 && g->n % (bn / 2) == 0 && static_cast<long long>(m_tiles) * (g->n / (bn / 2)) <= slots) bn /= 2;
     }
   }
+  if (n_phase > 1 && g->n % bn) {
+    extdm_set_error("extdm_conv_gemm: phases need block_n | n", __FILE__, __LINE__);
+    return EXTDM_ERR_ARG;
+  }
   if (bn != 16 && bn != 64 && bn != 128 && bn != 256) {
     extdm_set_error("extdm_conv_gemm: block_n must be 16, 64, 128 or 256", __FILE__, __LINE__);
     return EXTDM_ERR_ARG;
@@ -959,7 +983,7 @@ extern "C" int extdm_conv_gemm(const ExtdmGemm* g, void* stream_) {
   // measured on B200: the halo kernel wins on every 3x3 / 7x7 shape it supports
   // (level-0 3x3: 96 vs 115 us; two sources: 160 vs 171 us; 7x7: 0.92 vs 1.12 ms)
   static const bool halo_all = getenv("EXTDM_HALO_ALL") != nullptr;
-  bool halo = kk && (simple || kk == 7) && !halo_off && !(kk == 7 && halo7_off) &&
+  bool halo = kk && n_phase == 1 && (simple || kk == 7) && !halo_off && !(kk == 7 && halo7_off) &&
               (halo_all || kk == 3 || dev.nk0 + dev.nk1 >= 2) && g->box[2] == 1 && g->box[3] == 1 && g->box[0] % 8 == 0 &&
               (bn == 64 || bn == 128) && !g->tf32;
   int ebox[4] = {g->box[0], g->box[1] + kk - 1, 1, 1};

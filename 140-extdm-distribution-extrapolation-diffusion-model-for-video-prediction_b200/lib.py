@@ -28,6 +28,7 @@ class ExtdmGemm(C.Structure):
         ("act", C.c_int), ("block_n", C.c_int),
         ("gn_partials", C.c_void_p),
         ("tf32", C.c_int),
+        ("n_phase", C.c_int), ("phase_out_offset", C.c_longlong * 4),
     ]
 
 

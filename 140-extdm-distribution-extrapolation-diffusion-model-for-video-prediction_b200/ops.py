@@ -122,6 +122,14 @@ def pack_upsample_weight(w):
     return out
 
 
+def pack_upsample_weight_merged(w):
+    """The four phase matrices stacked along the output rows -> ((4*Cout, 4*Cin) bf16, [taps of phase p], [(py, px)]):
+    one launch of the phase-aware GEMM computes the whole ConvTranspose (upsample_cl)."""
+    per = pack_upsample_weight(w)
+    order = [(0, 0), (0, 1), (1, 0), (1, 1)]
+    return torch.cat([per[ph][0] for ph in order], dim=0).contiguous(), [per[ph][1] for ph in order], order
+
+
 def conv_taps(k):
     return [(kx - k // 2, ky - k // 2, 0) for ky in range(k) for kx in range(k)]
 
@@ -142,9 +150,15 @@ def std_box(H, W):
 def gemm(rec, *, a0, c0, dims, strides0, box, start, count, taps, w, n, out, out_stride, out_base=0,
          a1=None, c1=0, strides1=None, out_fp32=False, col_group=None, col_group_stride=0, bias=None,
          res=None, res_fp32=False, res_base=0, res_stride=None, col_scale=None, col_shift=None, act=0,
-         block_n=0, gn_partials=None, a1_offset=0, tf32=False):
+         block_n=0, gn_partials=None, a1_offset=0, tf32=False, phases=None):
     """Generic launch of extdm_conv_gemm.  dims/strides: extents and element strides of D1..D4 of the A
-    tensor(s); box/start/count: tile geometry; taps: list of (o1,o2,o3)."""
+    tensor(s); box/start/count: tile geometry; taps: list of (o1,o2,o3).
+    phases: [(taps_p, out_offset_p), ...] -- several products over the same A tiles in one launch (ExtdmGemm.n_phase):
+    phase p uses its own taps, the weight rows [p*n, (p+1)*n) and writes at out_base + out_offset_p."""
+    if phases is not None:
+        taps = phases[0][0]
+        if any(len(tp) != len(taps) for tp, _ in phases):
+            raise ValueError("gemm: every phase needs the same number of taps")
     g = _lib.ExtdmGemm()
     g.a0 = a0.data_ptr()
     g.a1 = 0 if a1 is None else a1.data_ptr() + 2 * a1_offset
@@ -157,8 +171,13 @@ def gemm(rec, *, a0, c0, dims, strides0, box, start, count, taps, w, n, out, out
         g.out_stride[i] = out_stride[i]
         g.res_stride[i] = (res_stride or out_stride)[i]
     g.ntaps = len(taps)
-    for i, t in enumerate(taps):
+    all_taps = taps if phases is None else [t for tp, _ in phases for t in tp]
+    for i, t in enumerate(all_taps):
         g.tap[i][0], g.tap[i][1], g.tap[i][2], g.tap[i][3] = t[0], t[1], t[2], 0
+    n_phase = 1 if phases is None else len(phases)
+    g.n_phase = n_phase
+    for i in range(n_phase if phases is not None else 0):
+        g.phase_out_offset[i] = phases[i][1]
     _chk(w, BF16, "gemm weight")
     if w.shape[1] != len(taps) * (c0 + (c1 if a1 is not None else 0)):
         raise ValueError(f"gemm: weight K {w.shape[1]} != taps*channels {len(taps)}*{c0}+{c1}")
@@ -178,9 +197,11 @@ def gemm(rec, *, a0, c0, dims, strides0, box, start, count, taps, w, n, out, out
     ktot = len(taps) * (c0 + (c1 if a1 is not None else 0))
     if tf32:
         ktot //= 2                                       # channel counts are in 2-byte units: K in fp32 elements
-    meta = dict(flops=2.0 * rows * n * ktot, rows=rows, n=n, k=ktot, taps=len(taps), tf32=bool(tf32),
-                bytes=2.0 * rows * (c0 + (c1 if a1 is not None else 0)) + 2.0 * n * ktot
-                + rows * n * (4.0 if out_fp32 else 2.0))
+    meta = dict(flops=2.0 * rows * n * ktot * n_phase, rows=rows, n=n, k=ktot, taps=len(taps), tf32=bool(tf32),
+                bytes=2.0 * rows * (c0 + (c1 if a1 is not None else 0)) + n_phase * (2.0 * n * ktot
+                + rows * n * (4.0 if out_fp32 else 2.0)))
+    if n_phase > 1:
+        meta["phases"] = n_phase
     rec.emit("extdm_conv_gemm", (C.byref(g),), keep=(g, a0, a1, w, out, bias, res, col_scale, col_shift, gn_partials),
              meta=meta)
 
@@ -225,6 +246,19 @@ def conv_cl(rec, x, w, n, k, out, *, x2=None, bias=None, res=None, res_fp32=Fals
          taps=taps if taps is not None else conv_taps(k), w=w, n=n, out=out, out_stride=ostr, out_base=obase,
          out_fp32=out_fp32, bias=bias, res=res, res_fp32=res_fp32, res_base=rbase, res_stride=rstr,
          col_scale=col_scale, col_shift=col_shift, act=act, block_n=block_n, gn_partials=gn_partials, tf32=tf32)
+
+
+def upsample_cl(rec, x, merged, n, out, *, bias=None):
+    """ConvTranspose3d (1,4,4)/s2/p1 of channels-last x (B, T, H, W, C) -> out (B, T, 2H, 2W, n) as ONE launch: the four
+    sub-pixel phases are 2x2-tap products over the same input tiles (merged = pack_upsample_weight_merged(weight))."""
+    wm, taps, order = merged
+    B, T, H, W, c0 = x.shape
+    bw, bh, bt = std_box(H, W)
+    oB, oT, oH, oW, oC = out.shape
+    gemm(rec, a0=x, c0=c0, dims=(W, H, T, B), strides0=(c0, W * c0, H * W * c0, T * H * W * c0),
+         box=(bw, bh, bt, 1), start=(0, 0, 0, 0), count=(W, H, T, B), taps=taps[0], w=wm, n=n, out=out,
+         out_stride=(2 * oC, 2 * oW * oC, oH * oW * oC, oT * oH * oW * oC), bias=bias,
+         phases=[(taps[i], (py * oW + px) * oC) for i, (py, px) in enumerate(order)])
 
 
 def pack_conv_weight_f32(w, cin_pad=None, splits=None):

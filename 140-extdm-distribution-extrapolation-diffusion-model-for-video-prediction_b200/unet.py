@@ -65,7 +65,7 @@ class PackedUnet:
             elif k.startswith("downs.") and k.endswith(f".{cfg.resample_slot}.weight"):
                 self.w[k] = ops.pack_downsample_weight(t)
             elif k.startswith("ups.") and k.endswith(f".{cfg.resample_slot}.weight"):
-                self.w[k] = ops.pack_upsample_weight(t)
+                self.w[k] = ops.pack_upsample_weight_merged(t)
             elif t.dim() == 5 and t.shape[2] == 3:
                 self.w[k] = ops.pack_conv3d_weight(t)
             elif t.dim() == 5:
@@ -323,8 +323,7 @@ class UnetRunner:
         pk = self.pk
         B, T, H, W, C = x.shape
         y = self.buf(B, T, 2 * H, 2 * W, C)
-        for (py, px), (wm, taps) in pk.w[p + ".weight"].items():
-            ops.conv_cl(rec, x, wm, C, 0, y, bias=pk.f32[p + ".bias"], taps=taps, out_scale=2, out_phase=(py, px))
+        ops.upsample_cl(rec, x, pk.w[p + ".weight"], C, y, bias=pk.f32[p + ".bias"])     # four phases, one launch
         return y
 
     def _stage_u22(self, rec, x, p, cout, has_adaptor, x2=None):

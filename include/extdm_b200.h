@@ -85,6 +85,12 @@ typedef struct ExtdmGemm {
    * product: the tensor core ignores the low 13 mantissa bits, rounding where a value is produced halves the error).
    * Used by the LFAE conditioning stage (region / background / flow predictors). */
   int tf32;
+  /* Phases: n_phase (0 or 1 = none, up to 4) independent products over the SAME A tiles in one launch -- the four
+   * sub-pixel phases of ConvTranspose3d (1,4,4)/s2/p1 (...cross_multi.py:125-127, Upsample).  Phase p uses the taps
+   * tap[p*ntaps .. (p+1)*ntaps), the weight rows [p*n, (p+1)*n) of W (w_rows = n_phase*n, block_n | n) and writes at
+   * out_base + phase_out_offset[p].  n_phase*ntaps <= 64.  Plain (non-halo) kernel only; no gn_partials. */
+  int n_phase;
+  long long phase_out_offset[4];
 } ExtdmGemm;
 
 int extdm_conv_gemm(const ExtdmGemm* g, void* stream);

@@ -119,6 +119,23 @@ def test_downsample_upsample():
         ops.conv_cl(R, xc, wm, C, 0, up, bias=bu, taps=taps, out_scale=2, out_phase=(py, px))
     ref = F.conv_transpose3d(xin, wu.to(BF).float(), bu, stride=(1, 2, 2), padding=(0, 1, 1))
     close(from_cl(up), ref, what="upsample")
+    # the same four phases as ONE launch (ExtdmGemm.n_phase): bit-identical to the per-phase launches
+    up1 = torch.zeros_like(up)
+    ops.upsample_cl(R, xc, ops.pack_upsample_weight_merged(wu), C, up1, bias=bu)
+    assert torch.equal(up1, up)
+
+
+@pytest.mark.parametrize("C,H,B", [(128, 8, 3), (256, 4, 32), (64, 32, 2)])
+def test_upsample_merged_phases(C, H, B):
+    """Phase-merged ConvTranspose at the UNet's other levels (n-split tiles, several frames per tile)."""
+    T = 3
+    x = rnd(B, C, T, H, H, seed=11)
+    xc = to_cl(x)
+    wu, bu = rnd(C, C, 1, 4, 4, seed=12, scale=(4 * C) ** -0.5), rnd(C, seed=13)
+    up = torch.zeros(B, T, 2 * H, 2 * H, C, device=DEV, dtype=BF)
+    ops.upsample_cl(R, xc, ops.pack_upsample_weight_merged(wu), C, up, bias=bu)
+    ref = F.conv_transpose3d(xc.float().permute(0, 4, 1, 2, 3), wu.to(BF).float(), bu, stride=(1, 2, 2), padding=(0, 1, 1))
+    close(from_cl(up), ref, what="upsample merged")
 
 
 def test_tmodulator_layout():
