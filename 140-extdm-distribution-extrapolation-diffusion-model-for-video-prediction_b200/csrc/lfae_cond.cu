@@ -143,6 +143,34 @@ __global__ void region_moments_kernel(const float* __restrict__ logits, int ldc,
   }
 }
 
+// ------------------------------------------------------------------------------------------------ PCA affine
+// region_predictor.py:130-146: u, s, v = svd(covar); affine = u diag(sqrt(s)).  Singular vectors are defined up to a sign
+// and the affine inherits it, so the convention matters: this is the closed form of what the reference computes when it
+// runs on a GPU, i.e. cuSOLVER's batched one-sided Jacobi (gesvdjBatched, the kernel behind torch.svd on CUDA) applied
+// to a symmetric 2x2 matrix [[a, b], [b, c]].  One rotation by theta = atan2(2b, a - c) / 2 in (-pi/4, pi/4] when a >= c
+// gives U = [[cos, -sin], [sin, cos]]; when a < c the rotation angle is atan2(-2b, c - a) / 2 and the two columns swap
+// to sort the singular values, U = [[-sin, cos], [cos, sin]].  An off-diagonal below the Jacobi tolerance is not rotated.
+// Checked against torch.svd on the device for 2e5 random covariances (tests/test_kernels_gpu.py::test_pca_affine_closed_form,
+// tools/svd_probe.py): identical sign pattern on every matrix, |U - U_cusolver| <= 3e-6.
+__global__ void pca_affine_kernel(const float* __restrict__ covar, float* __restrict__ affine, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float a = covar[4 * i], b = covar[4 * i + 1], c = covar[4 * i + 3];
+  const float h = 0.5f * (a - c);
+  const float r = sqrtf(h * h + b * b);
+  const float m = 0.5f * (a + c);
+  const float l1 = sqrtf(fmaxf(m + r, 0.f)), l2 = sqrtf(fmaxf(m - r, 0.f));     // sqrt of the singular values, descending
+  const bool big = a >= c;
+  // columns (a, b) and (b, c): the Jacobi sweep skips the pair when its inner product is below tolerance x the norms
+  const bool skip = fabsf(b) * (a + c) <= 8e-7f * sqrtf((a * a + b * b) * (b * b + c * c));
+  const float th = skip ? 0.f : 0.5f * atan2f(big ? 2.f * b : -2.f * b, big ? a - c : c - a);
+  float sn, cs;
+  sincosf(th, &sn, &cs);
+  const float u00 = big ? cs : -sn, u01 = big ? -sn : cs, u10 = big ? sn : cs, u11 = big ? cs : sn;
+  float* o = affine + 4 * i;
+  o[0] = u00 * l1; o[1] = u01 * l2; o[2] = u10 * l1; o[3] = u11 * l2;
+}
+
 // ------------------------------------------------------------------------------------------------ sparse motions
 // PixelwiseFlowPredictor.create_heatmap_representations / create_sparse_motions / create_deformed_source_image
 // (pixelwise_flow_predictor.py:48-112) for one frame per block.  Driving parameters are per frame, source parameters
@@ -358,6 +386,16 @@ extern "C" int extdm_region_moments(const float* logits, int ldc, int F_, int K,
   }
   region_moments_kernel<<<F_ * K, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, ldc, K, h, w, crop,
                                                                                1.0f / temperature, shift, covar);
+  EXTDM_CHECK_LAUNCH();
+  return EXTDM_OK;
+}
+
+extern "C" int extdm_pca_affine(const float* covar, float* affine, int n, void* stream) {
+  if (!covar || !affine || n < 1) {
+    extdm_set_error("pca_affine: null pointer / empty batch", __FILE__, __LINE__);
+    return EXTDM_ERR_ARG;
+  }
+  pca_affine_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(covar, affine, n);
   EXTDM_CHECK_LAUNCH();
   return EXTDM_OK;
 }

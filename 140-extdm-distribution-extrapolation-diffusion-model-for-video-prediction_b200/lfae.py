@@ -573,12 +573,17 @@ class CondRunner:
     frames on the CUDA kernels: RegionPredictor -> BGMotionPredictor -> PixelwiseFlowPredictor.
 
     Convolutions run on the tcgen05 implicit GEMM in its tf32 mode (fp32 tensors, fp32 accumulate: the precision of the
-    reference's cuDNN path), everything else on the fp32 kernels of csrc/lfae_cond.cu.  The one library call left is
-    the batched 2x2 torch.svd of the region covariances: its sign convention is the reference's own
-    (region_predictor.py:130-136), a closed form would have to guess it.
+    reference's cuDNN path), everything else on the fp32 kernels of csrc/lfae_cond.cu, including the PCA of the region
+    covariances (region_predictor.py:130-136): `pca = "gesvdj"` evaluates the 2x2 SVD in closed form with the
+    singular-vector signs of cuSOLVER's batched Jacobi -- what torch.svd, hence the reference, returns on a GPU -- so
+    the whole stage is one launch list replayed from a CUDA graph.  `pca = "torch"` calls torch.svd between the two
+    halves instead (the fixture tests route it through LAPACK, whose signs differ: DESIGN.md section 1).
 
     The reference evaluates the region predictor twice on each video's last conditioning frame (once as `ref_img`,
     once as driving frame tc-1, same weights, same input); here the source parameters are read from frame tc-1."""
+
+    pca = "gesvdj"           # class-level switch, see above
+    use_cuda_graph = True
 
     @staticmethod
     def supported(rp, bgp, pfp):
@@ -588,6 +593,8 @@ class CondRunner:
 
     def __init__(self, rp, bgp, pfp, dev, B, tc, H, W):
         self.recA, self.recB = ops.Recorder(record=True), ops.Recorder(record=True)
+        self.recP = ops.Recorder(record=True)                  # the closed-form PCA between the two halves
+        self._graph = None
         f32 = dict(device=dev, dtype=torch.float32)
         buf = lambda *s: torch.empty(*s, **f32)
         Fn = B * tc
@@ -609,6 +616,7 @@ class CondRunner:
         self.shift, self.covar = torch.zeros(Fn, K, 2, **f32), torch.zeros(Fn, K, 2, 2, **f32)
         self.affine = torch.zeros(Fn, K, 2, 2, **f32)
         ops.region_moments(self.recA, logits, K, 3 - rp.regions.padding[0], float(rp.temperature), self.shift, self.covar)
+        ops.pca_affine(self.recP, self.covar, self.affine)
         # ---- background predictor (full resolution, [reference | frame] channels)
         rec = self.recB
         self.bg = None
@@ -681,15 +689,31 @@ class CondRunner:
 
     def recorders(self):
         """The stage's launch lists, in execution order (bench.py / tools/kernel_table.py account for them)."""
-        return [self.recA, self.recB]
+        return [self.recA, self.recP, self.recB] if self.pca == "gesvdj" else [self.recA, self.recB]
 
     def run(self, real_vid):
         """real_vid (B, 3, tc, H, W) fp32 on the device -> (grid (B,2,tc,h,w), conf (B,1,tc,h,w) | None)."""
         B, _, tc, H, W = real_vid.shape
         self.frames.view(B, tc, 3, H, W).copy_(real_vid.permute(0, 2, 1, 3, 4))
         self.ref.copy_(real_vid[:, :, tc - 1])
-        self.recA.run()
-        u, s, _ = torch.svd(self.covar.view(-1, 2, 2))                     # region_predictor.py:130-136
-        self.affine.view(-1, 2, 2).copy_(u @ torch.diag_embed(s ** 0.5))
-        self.recB.run()
+        if self.pca != "gesvdj":
+            self.recA.run()
+            u, s, _ = torch.svd(self.covar.view(-1, 2, 2))                 # region_predictor.py:130-136
+            self.affine.view(-1, 2, 2).copy_(u @ torch.diag_embed(s ** 0.5))
+            self.recB.run()
+            return self.grid, self.conf
+        if not self.use_cuda_graph or torch.cuda.is_current_stream_capturing():
+            for rec in (self.recA, self.recP, self.recB):
+                rec.run()
+            return self.grid, self.conf
+        if self._graph is None:                                # static buffers: the launch lists replay as one graph
+            for rec in (self.recA, self.recP, self.recB):      # warm-up (lazy per-kernel attribute set-up)
+                rec.run()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for rec in (self.recA, self.recP, self.recB):
+                    rec.run()
+            self._graph = g
+        self._graph.replay()
         return self.grid, self.conf

@@ -44,6 +44,7 @@ PROTOTYPES = {
     "extdm_avgpool2_f32_cl": [_P, _P, _L, _I, _I, _I, _P],
     "extdm_upsample2_f32_cl": [_P, _P, _L, _I, _I, _I, _P],
     "extdm_region_moments": [_P, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P],
+    "extdm_pca_affine": [_P, _P, _I, _P],
     "extdm_sparse_motion": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _I, _P, _P],
     "extdm_flow_compose": [_P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P],
     "extdm_bg_head": [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P],

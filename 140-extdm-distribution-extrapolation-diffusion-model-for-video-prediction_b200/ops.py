@@ -592,6 +592,11 @@ def region_moments(rec, logits, K, crop, temperature, shift, covar):
              keep=(logits, shift, covar))
 
 
+def pca_affine(rec, covar, affine):
+    """(n, 2, 2) covariances -> u diag(sqrt s) with cuSOLVER's (= torch.svd on CUDA) singular-vector signs."""
+    rec.emit("extdm_pca_affine", (_p(covar), _p(affine), covar.numel() // 4), keep=(covar, affine))
+
+
 def sparse_motion(rec, src, shift, covar, affine, bg, tc, revert_axis_swap, use_covar, region_var, inp, motion):
     F_, h, w, cpad = inp.shape
     K = shift.shape[1]

@@ -315,6 +315,10 @@ int extdm_upsample2_f32_cl(const float* x, float* y, long long F, int H, int W, 
  * (F, K, 2, 2). */
 int extdm_region_moments(const float* logits, int ldc, int F, int K, int h, int w, int crop, float temperature,
                          float* shift, float* covar, void* stream);
+/* PCA affine of the region covariances (region_predictor.py:130-146: u, s, v = svd(covar); affine = u diag(sqrt s)) in
+ * closed form with the singular-vector sign convention of cuSOLVER's batched Jacobi, i.e. of torch.svd on CUDA -- what the
+ * reference itself computes on a GPU.  covar, affine: (n, 2, 2) fp32. */
+int extdm_pca_affine(const float* covar, float* affine, int n, void* stream);
 /* PixelwiseFlowPredictor heat-maps + sparse motions + deformed sources (pixelwise_flow_predictor.py:48-112) for F = B*tc
  * frames; source parameters / image are those of each video's last conditioning frame.  shift (F,K,2), covar / affine
  * (F,K,2,2), bg (F,3,3) or NULL; src (F, h, w, src_ld) channels 0..2; inp (F, h, w, cpad) channel 4k + {0: heat, 1..3:

@@ -173,9 +173,11 @@ def test_pipeline_matches_reference(request):
     torch.backends.cuda.matmul.allow_tf32 = False
     # torch.svd's singular-vector signs differ between LAPACK (the CPU run that produced the fixture) and
     # cuSOLVER, and the reference's PCA affine (region_predictor.py:139-146) inherits them: use LAPACK here.
-    real_svd = torch.svd
+    from extdm_b200.lfae import CondRunner
+    real_svd, real_pca = torch.svd, CondRunner.pca
     torch.svd = lambda a, *args, **kw: tuple(t.to(a.device) for t in real_svd(a.cpu(), *args, **kw))
-    request.addfinalizer(lambda: setattr(torch, "svd", real_svd))
+    CondRunner.pca = "torch"              # the product's default is the closed form with cuSOLVER's signs
+    request.addfinalizer(lambda: (setattr(torch, "svd", real_svd), setattr(CondRunner, "pca", real_pca)))
     # (1) the torch restatement of the conditioning modules in true fp32: module-level parity with the reference
     fd.native_conditioning = False
     cret = fd.condition(real_vid.contiguous().cuda())[0]
@@ -272,6 +274,19 @@ def test_native_conditioning_matches_torch_fp32(name, B):
         e_lib = (cudnn_tf32[key] - exact[key]).abs().max().item()
         print(name, key, "native vs fp32", e_nat, "| cuDNN tf32 vs fp32", e_lib)
         assert e_nat <= max(2 * e_lib, 2e-3), (key, e_nat, e_lib)
+    # the stage replays from a CUDA graph (closed-form PCA, no library call inside): same bits as the eager launch lists,
+    # call after call
+    from extdm_b200.lfae import CondRunner
+    native = {k: v.clone() for k, v in native.items() if torch.is_tensor(v)}
+    again = model.condition(clip)[0]
+    CondRunner.use_cuda_graph = False
+    try:
+        model._cond_runners.clear()
+        eager = model.condition(clip)[0]
+    finally:
+        CondRunner.use_cuda_graph = True
+    for key in ("real_vid_grid", "real_vid_conf"):
+        assert torch.equal(native[key], again[key]) and torch.equal(native[key], eager[key]), key
 
 
 def test_full_size_round_matches_reference(request):
@@ -295,9 +310,11 @@ def test_full_size_round_matches_reference(request):
     real_vid = real_vid.clamp(0, 1).expand(B, 3, tc, 64, 64).contiguous()
     noise = torch.stack([rnd((B, 3, tp, 32, 32), fx["noise_seed"] + i) for i in range(steps)])
     # LAPACK's singular-vector signs, like the CPU run that produced the fixture (see test_pipeline_matches_reference)
-    real_svd = torch.svd
+    from extdm_b200.lfae import CondRunner
+    real_svd, real_pca = torch.svd, CondRunner.pca
     torch.svd = lambda a, *args, **kw: tuple(t.to(a.device) for t in real_svd(a.cpu(), *args, **kw))
-    request.addfinalizer(lambda: setattr(torch, "svd", real_svd))
+    CondRunner.pca = "torch"              # the product's default is the closed form with cuSOLVER's signs
+    request.addfinalizer(lambda: (setattr(torch, "svd", real_svd), setattr(CondRunner, "pca", real_pca)))
     ret = fd.sample_one_video(cond_scale=1.0, real_vid=real_vid.cuda(), noise=noise.cuda())
     want = fx["out"]
     g = rel_l2(ret["sample_vid_grid"].cpu(), want["sample_vid_grid"])

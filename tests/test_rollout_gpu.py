@@ -23,9 +23,11 @@ from rollout_common import ROLLOUTS, build_model, load, psnr, rel_l2, round_nois
 def _lapack_svd(request):
     """torch.svd's singular-vector signs differ between LAPACK (the CPU run that wrote the fixtures) and cuSOLVER and
     the reference's PCA affine inherits them (region_predictor.py:139-146): use LAPACK's on the device as well."""
-    real_svd = torch.svd
+    from extdm_b200.lfae import CondRunner
+    real_svd, real_pca = torch.svd, CondRunner.pca
     torch.svd = lambda a, *args, **kw: tuple(t.to(a.device) for t in real_svd(a.cpu(), *args, **kw))
-    request.addfinalizer(lambda: setattr(torch, "svd", real_svd))
+    CondRunner.pca = "torch"              # the product's default is the closed form with cuSOLVER's signs
+    request.addfinalizer(lambda: (setattr(torch, "svd", real_svd), setattr(CondRunner, "pca", real_pca)))
 
 
 @pytest.mark.parametrize("name", ROLLOUTS)
