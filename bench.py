@@ -561,6 +561,18 @@ def main():
             except Exception as e:                           # reported-only extras never fail the bench
                 per[cname] = {"error": repr(e)}
             torch.cuda.empty_cache()
+        try:                                                 # the headline configuration at larger per-GPU batches
+            mdl = configs.build_model(name, seed=1234, device=dev)
+            for b in (64, 128):
+                measure(name, b, f"{name}_b{b}", mdl)
+                mdl[0].unet._runners.clear()
+                mdl[0].generator._runners.clear()
+                mdl[0]._cond_runners.clear()
+                torch.cuda.empty_cache()
+            del mdl
+        except Exception as e:
+            per[f"{name}_batch_sweep"] = {"error": repr(e)}
+        torch.cuda.empty_cache()
         try:                                                 # BASELINE config 5: UCF-101 large-batch sweep
             mdl = configs.build_model("ucf", seed=1234, device=dev)
             for b in (8, 16, 32, 64, 128):
