@@ -278,7 +278,14 @@ def gpu_eager_reference(model, name, B, total_pred, dev):
                 torch.cuda.synchronize()
                 sec = time.perf_counter() - t0
                 out[key] = {"value": B * total_pred / sec, "unit": "frames/s", "ms_per_step": 1e3 * sec}
-            # ---- parity at full batch: one round, injected noise, cuSOLVER SVD on both sides
+            # ---- parity at full batch: one round, injected noise; the reference's PCA runs on cuSOLVER here, this repo's
+            # in its closed form with the same sign convention.  Smooth, natural-video-like clips (the recipe of the test
+            # fixtures): the white-noise clips of the throughput runs make frame PSNR a measure of the noise, not the path.
+            import torch.nn.functional as F
+            gc = torch.Generator(device="cpu").manual_seed(1000)
+            coarse = torch.rand((B, 1 if name in GRAY else 3, 4, 8, 8), generator=gc)
+            clip = F.interpolate(coarse, size=(tc, hw, hw), mode="trilinear", align_corners=True).clamp(0, 1)
+            clip = clip.expand(B, 3, tc, hw, hw).contiguous()
             steps = fd.diffusion.sampling_timesteps
             g = torch.Generator(device="cpu").manual_seed(77)
             noise = torch.randn(steps, B, 3, tp, 32, 32, generator=g).to(dev)
@@ -296,8 +303,8 @@ def gpu_eager_reference(model, name, B, total_pred, dev):
         rel = lambda a, b: ((a.float() - b.float()).norm() / b.float().norm()).item()
         mse = ((got["sample_out_vid"] - want["sample_out_vid"]) ** 2).mean().item()
         out["parity_full_batch"] = {
-            "what": f"one sample_one_video round, batch {B}, {steps} DDIM steps, injected noise: this repo's path vs the "
-                    "reference on the same GPU in fp32",
+            "what": f"one sample_one_video round, batch {B}, {steps} DDIM steps, injected noise, smooth synthetic clips: "
+                    "this repo's path vs the reference on the same GPU in fp32",
             "cond_flow_max_abs": (got["real_vid_grid"] - want["real_vid_grid"]).abs().max().item(),
             "pred_flow_rel_l2": rel(got["sample_vid_grid"][:, :, tc:], want["sample_vid_grid"][:, :, tc:]),
             "frames_psnr_db": 99.0 if mse == 0 else 10 * math.log10(1.0 / mse)}
