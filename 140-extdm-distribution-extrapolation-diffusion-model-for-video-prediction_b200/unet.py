@@ -261,10 +261,10 @@ class UnetRunner:
             r = x
         if defer_norm2:
             return h2, r, gnp, npart
-        y = self.buf(B, T, H, W, cout)
-        ops.groupnorm_silu(rec, h2, self.gn_ws, pk.f32[p + ".block2.norm.weight"], pk.f32[p + ".block2.norm.bias"], y,
+        # in place: h2 has no other reader, and a line rewritten while it is still dirty in L2 is written back once
+        ops.groupnorm_silu(rec, h2, self.gn_ws, pk.f32[p + ".block2.norm.weight"], pk.f32[p + ".block2.norm.bias"], h2,
                            groups=cfg.groups, res=r, n_part=npart)
-        return y
+        return h2
 
     def _adaptor(self, rec, x, p):
         """MotionAdaptor, in place on frames [tm, T) of x (..._traj_ada.py:659-718)."""
