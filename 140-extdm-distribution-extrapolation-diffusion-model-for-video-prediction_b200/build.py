@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 TAG = os.environ.get("EXTDM_BUILD_TAG", "")
 OUT = os.path.join(HERE, f"libextdm_b200{'_' + TAG if TAG else ''}.so")
 BUILD = os.path.join(HERE, "build" + ("_" + TAG if TAG else ""))
-SOURCES = ["api.cu", "conv_gemm.cu", "unet_elementwise.cu", "attention.cu", "stw_fused.cu", "stw_tc.cu", "attn_ws32.cu", "traj.cu", "lfae_cond.cu", "sampler.cu", "warp.cu"]
+SOURCES = ["api.cu", "conv_gemm.cu", "unet_elementwise.cu", "attention.cu", "stw_fused.cu", "stw_tc.cu", "attn_ws32.cu", "attn_core32.cu", "traj.cu", "lfae_cond.cu", "sampler.cu", "warp.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + os.environ.get("EXTDM_NVCC_DEFS", "").split()
 

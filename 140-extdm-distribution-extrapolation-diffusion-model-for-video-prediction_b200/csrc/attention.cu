@@ -6,6 +6,8 @@
 // One CTA = one window / one pixel, one warp per head.  The tiles (<= 64x64x32) are far below a tcgen05
 // tile (M = 128 rows per CTA), so the contractions run on warp-level mma.sync m16n8k16 bf16 with the
 // scores kept in registers (flash-style: S accumulators are re-used as the A operand of P*V).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/extdm_b200.h"
 
@@ -267,9 +269,25 @@ static int set_smem(K kernel, size_t bytes) {
 
 using namespace extdm;
 
+namespace extdm {
+// attn_core32.cu: tcgen05 edition for (2,4,4) windows, 8 heads x 32 (lane-masked compact scores)
+bool attn_core32_supported(int heads, int dh, int wd, int wh, int ww, int H, int W);
+int attn_core32_launch(const void* qkv, void* out, const float* bias_table, const float* rope_cos, const float* rope_sin,
+                       int B, int T, int H, int W, int sd, int sh, int sw, cudaStream_t st);
+}  // namespace extdm
+
 extern "C" int extdm_window_attention(const void* qkv, void* out, const float* bias_table, const float* rope_cos,
                                       const float* rope_sin, int B, int T, int H, int W, int heads, int dh, int wd,
                                       int wh, int ww, int sd, int sh, int sw, void* stream) {
+  static const bool legacy32 = getenv("EXTDM_WINATT_LEGACY") != nullptr;      // A/B: the mma.sync kernel below
+  // ahead of the mma.sync kernel only with several tiles per SM (measured on B200, batch 32: 90 vs 105 us at the 16 x 16
+  // level, 37 vs 30 / 22 vs 15 us at 8 x 8 / 4 x 4 where a CTA gets one or two tiles and their four head groups run one
+  // after the other); EXTDM_WINATT_TC=1 forces it (tests)
+  static const bool force32 = getenv("EXTDM_WINATT_TC") != nullptr;
+  if (!legacy32 && extdm::attn_core32_supported(heads, dh, wd, wh, ww, H, W) &&
+      (force32 || static_cast<long long>(B) * ((T + 1) / 2) * (H / 4) * (W / 4) >= 4ll * 3 * extdm::device_sm_count()))
+    return extdm::attn_core32_launch(qkv, out, bias_table, rope_cos, rope_sin, B, T, H, W, sd, sh, sw,
+                                     static_cast<cudaStream_t>(stream));
   const int ntok = wd * wh * ww;
   if (H % wh || W % ww || heads < 1 || heads > 8 || !((ntok == 64 && dh == 16) || (ntok == 32 && dh == 32) ||
                                                        (ntok == 64 && dh == 32) || (ntok == 32 && dh == 16))) {

@@ -218,6 +218,35 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       : "memory");
 }
 
+// The same two instructions with the disable-output-lane operand: four 32-bit words, bit i of word j set = TMEM lane
+// 32 j + i keeps its old contents (CUTLASS always passes zeros).  A block-diagonal product (several independent 32-row
+// attention windows in one M = 128 tile) becomes one narrow MMA per window that writes only the window's own rows, all
+// into the SAME columns -- semantics confirmed on B200 by the attention parity tests (csrc/attn_core32.cu).
+__device__ __forceinline__ void umma_bf16_lanes(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t accumulate, uint32_t m0, uint32_t m1, uint32_t m2,
+                                                uint32_t m3) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ts_lanes(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                                   uint32_t accumulate, uint32_t m0, uint32_t m1, uint32_t m2,
+                                                   uint32_t m3) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
+      : "memory");
+}
+
 // K-major operand tile, rows of 64 bf16 (128 B), written by TMA with CU_TENSOR_MAP_SWIZZLE_128B:
 // 8-row groups of 1024 B (SBO = 1024), descriptor version 1 (sm_100), layout type SWIZZLE_128B (=2).
 // Field layout: cute/arch/mma_sm100_desc.hpp (SmemDescriptor).

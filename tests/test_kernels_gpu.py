@@ -328,12 +328,28 @@ def _rope_tables(n, dh):
     return ang.cos().contiguous().to(DEV), ang.sin().contiguous().to(DEV)
 
 
-@pytest.mark.parametrize("window,dh,T,H,shift", [((4, 4, 4), 16, 7, 8, (2, 2, 2)), ((4, 4, 4), 16, 7, 8, (0, 0, 0)),
-                                                 ((2, 4, 4), 32, 5, 8, (1, 2, 2)), ((4, 4, 4), 16, 6, 4, (2, 0, 0)),
-                                                 ((2, 4, 4), 32, 4, 16, (0, 0, 0))])
-def test_window_attention(window, dh, T, H, shift):
-    from oracle import extdm_oracle as O
-    B, heads = 2, 8
+@pytest.mark.parametrize("window,dh,T,H,shift,B", [((4, 4, 4), 16, 7, 8, (2, 2, 2), 2), ((4, 4, 4), 16, 7, 8, (0, 0, 0), 2),
+                                                   ((2, 4, 4), 32, 5, 8, (1, 2, 2), 2), ((4, 4, 4), 16, 6, 4, (2, 0, 0), 2),
+                                                   ((2, 4, 4), 32, 4, 16, (0, 0, 0), 2),
+                                                   # tcgen05 core (attn_core32.cu): tail tiles, odd T, several tiles per CTA
+                                                   ((2, 4, 4), 32, 12, 16, (1, 2, 2), 3), ((2, 4, 4), 32, 15, 4, (1, 0, 0), 5),
+                                                   ((2, 4, 4), 32, 12, 32, (1, 2, 2), 8), ((2, 4, 4), 32, 14, 8, (0, 0, 0), 32)])
+@pytest.mark.parametrize("impl", ["default", "EXTDM_WINATT_TC"])
+def test_window_attention(window, dh, T, H, shift, B, impl, request):
+    """impl EXTDM_WINATT_TC: the tcgen05 core (csrc/attn_core32.cu) at every (2,4,4) x 8 x 32 shape, not only where the
+    dispatcher prefers it; the switch is read once per process, so those cases run in a subprocess."""
+    if impl != "default":
+        import subprocess, sys, os
+        if tuple(window) != (2, 4, 4):
+            pytest.skip("tcgen05 core: (2,4,4) windows only")
+        if os.environ.get(impl):
+            pytest.skip("already inside the child process")
+        me = request.node.name.replace(impl, "default")
+        r = subprocess.run([sys.executable, "-m", "pytest", f"{__file__}::{me}", "-q", "-x"], env=dict(os.environ, **{impl: "1"}),
+                           capture_output=True, text=True)
+        assert r.returncode == 0 and "1 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+        return
+    heads = 8
     hid = heads * dh
     N = window[0] * window[1] * window[2]
     qkv = rnd(B, T, H, H, 3 * hid, seed=1).to(BF)
@@ -341,8 +357,16 @@ def test_window_attention(window, dh, T, H, shift):
     rc, rs = _rope_tables(N, dh)
     out = torch.zeros(B, T, H, H, hid, device=DEV, dtype=BF)
     ops.window_attention(R, qkv, out, tbl, rc, rs, heads, dh, window, shift)
-    # reference (CPU, fp32) with the oracle's partition / mask helpers
-    z = qkv.float().cpu()
+    close(out.cpu(), _window_attention_ref(qkv.float().cpu(), tbl, window, shift, heads, dh), rel=2e-2, atol=5e-3,
+          what="window attention")
+
+
+def _window_attention_ref(z, tbl, window, shift, heads, dh):
+    """CPU fp32 reference with the oracle's partition / mask helpers; z: (B, T, H, W, 3*hid) raw qkv."""
+    from oracle import extdm_oracle as O
+    B, T, H = z.shape[0], z.shape[1], z.shape[2]
+    hid = heads * dh
+    N = window[0] * window[1] * window[2]
     ws, ss = window, shift
     Dp = -(-T // ws[0]) * ws[0]
     z = F.pad(z, (0, 0, 0, 0, 0, 0, 0, Dp - T))
@@ -364,7 +388,7 @@ def test_window_attention(window, dh, T, H, shift):
     o = o.permute(0, 1, 4, 2, 5, 3, 6, 7).reshape(B, Dp, H, H, hid)
     if shifted:
         o = torch.roll(o, shifts=ss, dims=(1, 2, 3))
-    close(out.cpu(), o[:, :T], rel=2e-2, atol=5e-3, what="window attention")
+    return o[:, :T]
 
 
 @pytest.mark.parametrize("T,dh", [(30, 16), (12, 32), (14, 32), (7, 16)])
