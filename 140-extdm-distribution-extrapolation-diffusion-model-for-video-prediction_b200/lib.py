@@ -85,6 +85,7 @@ PROTOTYPES = {
 }
 _RET = {"extdm_last_error": C.c_char_p, "extdm_adaptor_workspace_floats": C.c_longlong}
 
+ABI_VERSION = 4          # extdm_abi_version() of the library this binding mirrors (include/extdm_b200.h)
 _lib = None
 
 
@@ -104,6 +105,9 @@ def load():
             fn = getattr(lib, name)
             fn.argtypes = args
             fn.restype = _RET.get(name, C.c_int)
+        if lib.extdm_abi_version() != ABI_VERSION:
+            raise ExtdmError(f"{LIB_PATH}: ABI version {lib.extdm_abi_version()}, this binding expects {ABI_VERSION} "
+                             "(stale build? run build.py)")
         if lib.extdm_sizeof_gemm() != C.sizeof(ExtdmGemm):
             raise ExtdmError("struct ExtdmGemm: ctypes mirror and compiled library disagree on the layout")
         _lib = lib
