@@ -12,5 +12,5 @@ void extdm_set_error(const char* msg, const char* file, int line) {
 }
 
 extern "C" const char* extdm_last_error(void) { return g_err; }
-extern "C" int extdm_abi_version(void) { return 4; }
+extern "C" int extdm_abi_version(void) { return 5; }
 extern "C" int extdm_sizeof_gemm(void) { return static_cast<int>(sizeof(ExtdmGemm)); }

@@ -418,6 +418,90 @@ __global__ void __launch_bounds__(256) im2col7_image_kernel(const float* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------------ composite init_conv
+// init_conv(init_noise_conv(x)) is two linear 7x7 convolutions in a row (..._traj_ada.py:916,1032-1042): away from the
+// image border they compose to ONE 13x13 convolution of the 3-channel flow (K = 507 instead of 49 * 256), near the border
+// the zero padding of the 256-channel intermediate breaks the composition.  The runner therefore computes
+//   composite 13x13 conv of x  -  (7x7 conv of the intermediate's values on the 3-pixel ring OUTSIDE the image)
+// which is exact everywhere (unet.py: _composite_init).  Two gather kernels feed the GEMMs:
+// (1) x-direction im2col: out[b, t_off + t, y, x, (dx + 6) * 3 + c] = xin[b, c, t, y, x + dx], dx in [-6, 6], zeros outside
+//     the image and in channels 39..63; the 13 rows of the kernel are taps of the GEMM that follows.
+__global__ void __launch_bounds__(256) im2col13x_kernel(const float* __restrict__ xin, __nv_bfloat16* __restrict__ out,
+                                                        int B, int tp, int T, int t_off, int H, int W) {
+  const long long total = static_cast<long long>(B) * tp * H * W * 8;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = i & 7;
+    long long r = i >> 3;
+    const int xx = r % W; r /= W;
+    const int yy = r % H; r /= H;
+    const int t = r % tp;
+    const int b = r / tp;
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = v * 8 + j;
+      float val = 0.f;
+      if (k < 39) {
+        const int x2 = xx + k / 3 - 6, c = k % 3;
+        if (x2 >= 0 && x2 < W) val = __ldg(xin + ((static_cast<long long>(b) * 3 + c) * tp + t) * H * W + yy * W + x2);
+      }
+      o[j] = val;
+    }
+    store8(out + (((static_cast<long long>(b) * T + t_off + t) * H + yy) * W + xx) * 64 + v * 8, o);
+  }
+}
+
+// (2) 7x7 im2col rows (K = 147 -> 192, same layout as im2col7_flow) of the positions of the 3-pixel ring around the image,
+//     strip by strip: top (B, tp, 3, W+6) rows y = -3..-1, bottom (same shape) y = H..H+2, left (B, tp, H, 3) columns
+//     x = -3..-1, right (same shape) x = W..W+2 -- the init_noise GEMM turns them into the intermediate's ring values.
+__global__ void __launch_bounds__(256) im2col7_ring_kernel(const float* __restrict__ xin, __nv_bfloat16* __restrict__ a,
+                                                           int B, int tp, int H, int W) {
+  const long long n_tb = static_cast<long long>(B) * tp * 3 * (W + 6), n_lr = static_cast<long long>(B) * tp * H * 3;
+  const long long total = (2 * n_tb + 2 * n_lr) * 24;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = i % 24;
+    long long r = i / 24;
+    int qx, qy;
+    long long bt;
+    if (r < 2 * n_tb) {
+      const bool bottom = r >= n_tb;
+      if (bottom) r -= n_tb;
+      const int xi = r % (W + 6); r /= (W + 6);
+      const int yi = r % 3;
+      bt = r / 3;
+      qx = xi - 3;
+      qy = bottom ? H + yi : yi - 3;
+    } else {
+      r -= 2 * n_tb;
+      const bool right = r >= n_lr;
+      if (right) r -= n_lr;
+      const int xi = r % 3; r /= 3;
+      const int yi = r % H;
+      bt = r / H;
+      qx = right ? W + xi : xi - 3;
+      qy = yi;
+    }
+    const int t = bt % tp;
+    const int b = bt / tp;
+    const float* src = xin + (static_cast<long long>(b) * 3 * tp + t) * H * W;      // + c * tp * H * W
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = v * 8 + j;
+      float val = 0.f;
+      if (k < 147) {
+        const int tap = k / 3, c = k % 3;
+        const int y2 = qy + tap / 7 - 3, x2 = qx + tap % 7 - 3;
+        if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) val = __ldg(src + static_cast<long long>(c) * tp * H * W + y2 * W + x2);
+      }
+      o[j] = val;
+    }
+    store8(a + i * 8, o);
+  }
+}
+
 // F.interpolate(mode='bilinear', align_corners=False) index math (ATen area_pixel_compute_source_index)
 __device__ __forceinline__ void bilinear_src(int dst, float scale, int in, int& i0, int& i1, float& l1) {
   float s = scale * (dst + 0.5f) - 0.5f;
@@ -911,6 +995,26 @@ extern "C" int extdm_im2col7_flow(const float* cond, const float* x, void* a, in
 
 extern "C" int extdm_im2col7_image(const float* img, void* a, long long F, int H, int W, void* stream) {
   im2col7_image_kernel<<<grid_for(F * H * W * 24, 256), 256, 0, STREAM>>>(img, BFW(a), F, H, W);
+  EXTDM_CHECK_LAUNCH();
+  return EXTDM_OK;
+}
+
+extern "C" int extdm_im2col13x_flow(const float* x, void* out, int B, int tp, int T, int t_off, int H, int W, void* stream) {
+  if (!x || !out || B < 1 || tp < 1 || t_off < 0 || t_off + tp > T) return bad_arg("im2col13x_flow: bad frame range");
+  const long long total = static_cast<long long>(B) * tp * H * W * 8;
+  im2col13x_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(x, BFW(out), B, tp, T, t_off, H, W);
+  EXTDM_CHECK_LAUNCH();
+  return EXTDM_OK;
+}
+
+static long long im2col7_ring_rows(int B, int tp, int H, int W) {
+  return 2ll * B * tp * 3 * (W + 6) + 2ll * B * tp * H * 3;
+}
+
+extern "C" int extdm_im2col7_ring(const float* x, void* a, int B, int tp, int H, int W, void* stream) {
+  if (!x || !a || B < 1 || tp < 1 || H < 7 || W < 7) return bad_arg("im2col7_ring: H, W >= 7");
+  const long long total = im2col7_ring_rows(B, tp, H, W) * 24;
+  im2col7_ring_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(x, BFW(a), B, tp, H, W);
   EXTDM_CHECK_LAUNCH();
   return EXTDM_OK;
 }

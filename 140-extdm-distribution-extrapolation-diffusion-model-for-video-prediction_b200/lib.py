@@ -56,6 +56,8 @@ PROTOTYPES = {
     "extdm_adaptor_normalize": [_P, _L, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "extdm_space_to_depth": [_P, _P, _L, _I, _I, _I, _P],
     "extdm_im2col7_flow": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "extdm_im2col13x_flow": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "extdm_im2col7_ring": [_P, _P, _I, _I, _I, _I, _P],
     "extdm_bilinear_resize_cl": [_P, _P, _L, _I, _I, _I, _I, _I, _P],
     "extdm_time_mlp": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "extdm_head_project": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
@@ -85,7 +87,7 @@ PROTOTYPES = {
 }
 _RET = {"extdm_last_error": C.c_char_p, "extdm_adaptor_workspace_floats": C.c_longlong}
 
-ABI_VERSION = 4          # extdm_abi_version() of the library this binding mirrors (include/extdm_b200.h)
+ABI_VERSION = 5          # extdm_abi_version() of the library this binding mirrors (include/extdm_b200.h)
 _lib = None
 
 

@@ -377,6 +377,25 @@ def im2col7_flow(rec, cond, x, a, t0, nt):
     rec.emit("extdm_im2col7_flow", (_p(cond), _p(x), _p(a), B, tc, tp, t0, nt, H, W), keep=(cond, x, a))
 
 
+def im2col13x_flow(rec, x, out, t_off):
+    """x (B, 3, tp, H, W) fp32 -> frames [t_off, t_off + tp) of out (B, T, H, W, 64) bf16: channel (dx + 6)*3 + c holds
+    x[.., c, .., x + dx] (composite init_conv, csrc/unet_elementwise.cu)."""
+    B, _, tp, H, W = x.shape
+    rec.emit("extdm_im2col13x_flow", (_p(x), _p(out), B, tp, out.shape[1], t_off, H, W), keep=(x, out))
+
+
+def ring_rows(B, tp, H, W):
+    """Rows of the four ring strips (top, bottom, left, right) in im2col7_ring's order."""
+    n_tb, n_lr = B * tp * 3 * (W + 6), B * tp * H * 3
+    return n_tb, n_lr
+
+
+def im2col7_ring(rec, x, a):
+    """x (B, 3, tp, H, W) fp32 -> 7x7 im2col rows (K 147 -> 192) of the 3-pixel ring around each frame."""
+    B, _, tp, H, W = x.shape
+    rec.emit("extdm_im2col7_ring", (_p(x), _p(a), B, tp, H, W), keep=(x, a))
+
+
 def bilinear_resize_cl(rec, x, y):
     h, w, Cc = x.shape[-3:]
     H, W = y.shape[-3:-1]

@@ -86,10 +86,13 @@ class PackedUnet:
             # TrajWarp makes the cond_fea half of init_conv depend on x_t: nothing to hoist, one conv over 512 channels
             self.w["init_noise"] = pack7(self.f32["init_noise_conv.weight"])
             self.w["init_full"] = ops.pack_conv_weight(ic)
+            self.w["init_fea"] = ops.pack_conv_weight(ic[:, 256:])
+            self._pack_composite_init(ic[:, :256, 0])
         else:
             self.w["init_noise"] = pack7(self.f32["init_noise_conv.weight"])
             self.w["init_x"] = ops.pack_conv_weight(ic[:, :256])
             self.w["init_fea"] = ops.pack_conv_weight(ic[:, 256:])
+            self._pack_composite_init(ic[:, :256, 0])
         # all ResnetBlock time-MLPs stacked: one GEMV kernel produces every (scale, shift)
         rows, biases, self.ss_off = [], [], {}
         off = 0
@@ -109,6 +112,41 @@ class PackedUnet:
         self.rope_w = _rope_tables(wd * wh * ww, cfg.dim_head, device)
 
 
+    # taps of the four ring-correction GEMMs (UnetRunner._composite_init): offsets into the strip tensors
+    RING_TAPS = {
+        "top": [(kx + 3, ky + 3, 0) for ky in (-3, -2, -1) for kx in range(-3, 4)],
+        "bottom": [(kx + 3, ky - 3, 0) for ky in (1, 2, 3) for kx in range(-3, 4)],
+        "left": [(kx + 3, ky, 0) for ky in range(-3, 4) for kx in (-3, -2, -1)],
+        "right": [(kx - 3, ky, 0) for ky in range(-3, 4) for kx in (1, 2, 3)],
+    }
+    RING_KERNEL = {          # the (ky, kx) each tap stands for, same order
+        "top": [(ky, kx) for ky in (-3, -2, -1) for kx in range(-3, 4)],
+        "bottom": [(ky, kx) for ky in (1, 2, 3) for kx in range(-3, 4)],
+        "left": [(ky, kx) for ky in range(-3, 4) for kx in (-3, -2, -1)],
+        "right": [(ky, kx) for ky in range(-3, 4) for kx in (1, 2, 3)],
+    }
+
+    def _pack_composite_init(self, w2):
+        """init_conv's weights over the init_noise_conv channels, w2 (Cout, 256, 7, 7), composed with init_noise_conv
+        (256, 3, 7, 7) into one 13x13 kernel over the 3 flow channels (..._traj_ada.py:916,1032-1042: two linear
+        convolutions in a row), plus the negated 7x7 sub-kernels of the ring correction -- see UnetRunner._composite_init."""
+        w1 = self.f32["init_noise_conv.weight"][:, :, 0].double()            # (256, 3, 7, 7)  [m, c, ky, kx]
+        b1 = self.f32["init_noise_conv.bias"].double()
+        w2 = w2.double()                                                       # (Cout, 256, 7, 7)
+        co = w2.shape[0]
+        w12 = torch.zeros(co, 3, 13, 13, dtype=torch.float64, device=w2.device)
+        for a in range(7):                                                     # out(p) = sum_a w2[a] xn(p + a), xn(q) = sum_a' w1[a'] x(q + a')
+            for b in range(7):
+                w12[:, :, a:a + 7, b:b + 7] += torch.einsum("om,mcij->ocij", w2[:, :, a, b], w1)
+        wc = torch.zeros(co, 13, 64, dtype=torch.float64, device=w2.device)    # K index = (dy + 6)*64 + (dx + 6)*3 + c
+        wc[:, :, :39] = w12.permute(0, 2, 3, 1).reshape(co, 13, 39)
+        self.w["init_comp"] = wc.reshape(co, 13 * 64).to(BF16).contiguous()
+        self.f32["init_comp.bias"] = torch.einsum("omab,m->o", w2, b1).float().contiguous()
+        for name, taps in self.RING_KERNEL.items():                           # K index = tap*256 + m, negated
+            blk = torch.stack([w2[:, :, ky + 3, kx + 3] for ky, kx in taps], dim=1)     # (Cout, taps, 256)
+            self.w["init_ring_" + name] = (-blk).reshape(co, -1).to(BF16).contiguous()
+
+
 class UnetRunner:
     """Launch lists + static buffers for one (config, batch, resolution)."""
 
@@ -121,6 +159,9 @@ class UnetRunner:
     # (16-token packing for T <= 16: eight pixel sequences per M = 128 tile).  The earlier mma.sync edition
     # (EXTDM_ATTN32_LEGACY=1) padded T = 12 ... 15 to 32 tokens and lost to the un-fused path.
     fuse_temporal_dh32 = True
+    # init_conv(init_noise_conv(x)) on the predicted frames as one composite 13x13 convolution of the 3-channel flow plus a
+    # ring correction (_composite_init) instead of a 7x7 convolution over 256 channels (K = 12544) per DDIM step
+    composite_init = True
 
     def __init__(self, packed, B, H=32, W=32, fea_hw=16):
         cfg = packed.cfg
@@ -394,10 +435,13 @@ class UnetRunner:
             ops.im2col7_flow(pro, self.cond_frames, self.x, a_c, 0, tc)
             self._im2col_gemm(pro, a_c, pk.w["init_noise"], 256, xn, 0, tc, bias=nb)
             ops.conv_cl(pro, xn, pk.w["init_x"], d, 7, x0, t_range=(0, tc), res=h0, res_fp32=True)
-            ops.im2col7_flow(st, self.cond_frames, self.x, a_p, tc, tp)
-            self._im2col_gemm(st, a_p, pk.w["init_noise"], 256, xn, tc, tp, bias=nb)
-            ops.conv_cl(st, xn, pk.w["init_x"], d, 7, x0, t_range=(tc, T), res=h0, res_fp32=True)
-            self.taps["init_noise_conv"] = xn
+            if self.composite_init and H == 32 and W == 32:
+                self._composite_init(st, x0, res=h0, res_fp32=True, bias=pk.f32["init_comp.bias"])
+            else:
+                ops.im2col7_flow(st, self.cond_frames, self.x, a_p, tc, tp)
+                self._im2col_gemm(st, a_p, pk.w["init_noise"], 256, xn, tc, tp, bias=nb)
+                ops.conv_cl(st, xn, pk.w["init_x"], d, 7, x0, t_range=(tc, T), res=h0, res_fp32=True)
+                self.taps["init_noise_conv"] = xn
         self.taps["init_conv"] = x0
 
         self._build_body(x0)
@@ -446,7 +490,12 @@ class UnetRunner:
                     out_t_offset=-tc, bias=pk.f32["init_traj.fuser.bias"])
         ops.bilinear_resize_frames_cl(st, fpn, cfu, (0, tp), tc)
         self.taps["cond_up"] = cfu
-        ops.conv_cl(st, xn, pk.w["init_full"], d, 7, x0, x2=cfu, t_range=(tc, T), bias=pk.f32["init_conv.bias"])
+        if self.composite_init and H == 32 and W == 32:
+            # the cond_fea half stays a 7x7 convolution (it depends on x_t through TrajWarp); the x half is composed
+            ops.conv_cl(st, cfu, pk.w["init_fea"], d, 7, x0, t_range=(tc, T), bias=pk.f32["init_conv.bias"])
+            self._composite_init(st, x0, res=x0, res_fp32=False, bias=pk.f32["init_comp.bias"])
+        else:
+            ops.conv_cl(st, xn, pk.w["init_full"], d, 7, x0, x2=cfu, t_range=(tc, T), bias=pk.f32["init_conv.bias"])
         self.taps["init_conv"] = x0
         self._build_body(x0)
 
@@ -506,6 +555,44 @@ class UnetRunner:
         ho = self._resblock(st, x, "occlusion_map.0", d, x2=x0, time=False)
         ops.head_project(st, hf, ho, pk.f32["final_conv.1.weight"], pk.f32["final_conv.1.bias"],
                          pk.f32["occlusion_map.1.weight"], pk.f32["occlusion_map.1.bias"], self.out, tm)
+
+    def _composite_init(self, rec, x0, res, res_fp32, bias):
+        """frames [tc, T) of x0 (B, T, H, W, d) (+)= init_conv_x(init_noise_conv(x)), exactly, without the 256-channel
+        intermediate:  xn = b1 + w1 * pad3(x) is zero padded before init_conv's 7x7 window, so
+            w2 * pad3(xn)  =  w2 * xn_ext  -  w2 * ring,
+        with xn_ext = b1 + w1 * pad6(x) the intermediate evaluated on the image extended by 3 pixels and `ring` its values
+        outside the image.  The first term is ONE 13x13 convolution of the 3-channel flow (w12 = w2 * w1, K = 13 * 64 after
+        an x-direction im2col, plus the constant w2 . b1); the second only touches output pixels within 3 of the border
+        and only the kernel rows / columns that reach outside: four GEMMs of 21 taps over the four ring strips, whose
+        values come from the init_noise GEMM on the strips' im2col rows.  47 instead of 157 MFLOP per pixel-row of 64."""
+        cfg, pk, B, H, W = self.cfg, self.pk, self.B, self.H, self.W
+        T, tc, tp = cfg.T, cfg.tc, cfg.tp
+        d = cfg.dim
+        hw = H * W
+        xc = torch.zeros(B, T, H, W, 64, device=self.dev, dtype=BF16)
+        ops.im2col13x_flow(rec, self.x, xc, tc)
+        rbase = tc * hw * d
+        ops.conv_cl(rec, xc, pk.w["init_comp"], d, 0, x0, t_range=(tc, T), taps=[(0, dy, 0) for dy in range(-6, 7)],
+                    bias=bias, res=res, res_fp32=res_fp32)
+        # ---- ring values of the intermediate: im2col rows of the four strips -> init_noise GEMM (bias b1 included)
+        n_tb, n_lr = ops.ring_rows(B, tp, H, W)
+        rows = 2 * n_tb + 2 * n_lr
+        a_ring = self.buf(rows, 192)
+        ring = self.buf(rows, 256)
+        ops.im2col7_ring(rec, self.x, a_ring)
+        ops.linear_rows(rec, a_ring, pk.w["init_noise"], 256, ring, bias=pk.f32["init_noise_conv.bias"])
+        ostr = (d, W * d, hw * d, T * hw * d)
+        strips = {
+            "top": (ring[:n_tb], (W + 6, 3), (32, 4), (W, 3), 0),
+            "bottom": (ring[n_tb:2 * n_tb], (W + 6, 3), (32, 4), (W, 3), (H - 3) * W * d),
+            "left": (ring[2 * n_tb:2 * n_tb + n_lr], (3, H), (4, 32), (3, H), 0),
+            "right": (ring[2 * n_tb + n_lr:], (3, H), (4, 32), (3, H), (W - 3) * d),
+        }
+        for name, (a, (d1, d2), (b1_, b2_), (c1, c2), off) in strips.items():
+            ops.gemm(rec, a0=a, c0=256, dims=(d1, d2, tp, B), strides0=(256, d1 * 256, d2 * d1 * 256, tp * d2 * d1 * 256),
+                     box=(b1_, b2_, 1, 1), start=(0, 0, 0, 0), count=(c1, c2, tp, B), taps=PackedUnet.RING_TAPS[name],
+                     w=pk.w["init_ring_" + name], n=d, out=x0, out_stride=ostr, out_base=rbase + off,
+                     res=x0, res_base=rbase + off, res_stride=ostr)
 
     def _im2col_gemm(self, rec, a, w, n, out, t0, nt, bias=None, res=None):
         """rows of `a` are (b, t, p) for t in [0, nt); write to frames [t0, t0+nt) of out (B, T, H, W, n')."""

@@ -96,7 +96,7 @@ def test_c_abi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(cdll, name), f"{name} declared in the header but not exported"
     assert declared == set(lib.PROTOTYPES), declared ^ set(lib.PROTOTYPES)
-    assert lib.load().extdm_abi_version() == 4
+    assert lib.load().extdm_abi_version() == 5
     assert ctypes.sizeof(lib.ExtdmGemm) == lib.load().extdm_sizeof_gemm()
 
 

@@ -95,6 +95,40 @@ def test_unet_layers_vs_oracle(name):
     assert worst <= 3e-2, worst
 
 
+@pytest.mark.parametrize("name", ["unet_ada_c2p5", "unet_u12_c2p3", "unet_ada_c10p20"])
+def test_composite_init_conv(name):
+    """UnetRunner.composite_init: init_conv(init_noise_conv(x)) on the predicted frames as one 13x13 convolution of the flow
+    plus the ring correction, against the two-stage 7x7 path of the same runner (and, through
+    test_unet_layers_vs_oracle's `init_conv` tap, against the oracle).  Border pixels are where the composition needs the
+    correction: they are gated separately."""
+    from extdm_b200.unet import UnetRunner
+    fx = torch.load(os.path.join(GOLD, name + ".pt"))
+    inp = unet_inputs(fx["variant"], fx["tc"], fx["tp"], fx["B"], fx["input_seed"])
+    got = {}
+    for flag in (False, True):
+        UnetRunner.composite_init = flag
+        try:
+            u, _ = build_unet(fx)
+            out = u(inp["x"].cuda(), inp["time"].cuda(), cond_frames=inp["cond_frames"].cuda(),
+                    cond_fea=inp["cond_fea"].cuda())
+            r = u.runner(fx["B"], 32, 32, inp["cond_fea"].shape[-1])
+            names = [n for _, _, n in r.step.steps]
+            assert ("extdm_im2col13x_flow" in names) == flag
+            got[flag] = (r.taps["init_conv"].float()[:, fx["tc"]:].clone(), out.float().clone())
+        finally:
+            UnetRunner.composite_init = True
+    a, b = got[False][0], got[True][0]                      # (B, tp, H, W, C)
+    scale = a.abs().max().item()
+    border = torch.ones(32, 32, dtype=torch.bool, device=a.device)
+    border[3:-3, 3:-3] = False
+    e_in = (a - b)[:, :, ~border].abs().max().item() / scale
+    e_bd = (a - b)[:, :, border].abs().max().item() / scale
+    print(name, "init_conv composite vs two-stage: interior", e_in, "border", e_bd, "rel-L2", rel_l2(b.cpu(), a.cpu()))
+    assert e_in <= 2e-2 and e_bd <= 2e-2, (e_in, e_bd)
+    assert rel_l2(b.cpu(), a.cpu()) <= 1e-2
+    assert rel_l2(got[True][1].cpu(), got[False][1].cpu()) <= 2e-2
+
+
 def test_unet_forward_with_groupnorm_fused_into_attention():
     """UnetRunner.fuse_gn_stw: the ResnetBlock's last GroupNorm + SiLU + residual applied on load by the following
     window-attention kernel (extdm_stw_fused_pre) -- same gate as the default path."""
