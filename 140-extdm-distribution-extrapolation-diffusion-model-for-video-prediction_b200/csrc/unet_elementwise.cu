@@ -452,9 +452,11 @@ __global__ void __launch_bounds__(256) im2col13x_kernel(const float* __restrict_
   }
 }
 
-// (2) 7x7 im2col rows (K = 147 -> 192, same layout as im2col7_flow) of the positions of the 3-pixel ring around the image,
-//     strip by strip: top (B, tp, 3, W+6) rows y = -3..-1, bottom (same shape) y = H..H+2, left (B, tp, H, 3) columns
-//     x = -3..-1, right (same shape) x = W..W+2 -- the init_noise GEMM turns them into the intermediate's ring values.
+// (2) 7x7 im2col rows (K = 147 -> 192, same layout as im2col7_flow, plus a constant 1 in column 147 that carries
+//     init_noise_conv's bias) of the positions of the 3-pixel ring around the image, strip by strip: top (B, tp, 3, W+6)
+//     rows y = -3..-1, bottom (same shape) y = H..H+2, left (B, tp, H, 3) columns x = -3..-1, right (same shape)
+//     x = W..W+2.  The intermediate's ring values are linear in these rows, so the correction GEMMs read them directly
+//     with init_noise_conv folded into their weights (K = 192 per tap instead of 256, no GEMM in between).
 __global__ void __launch_bounds__(256) im2col7_ring_kernel(const float* __restrict__ xin, __nv_bfloat16* __restrict__ a,
                                                            int B, int tp, int H, int W) {
   const long long n_tb = static_cast<long long>(B) * tp * 3 * (W + 6), n_lr = static_cast<long long>(B) * tp * H * 3;
@@ -495,6 +497,8 @@ __global__ void __launch_bounds__(256) im2col7_ring_kernel(const float* __restri
         const int tap = k / 3, c = k % 3;
         const int y2 = qy + tap / 7 - 3, x2 = qx + tap % 7 - 3;
         if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) val = __ldg(src + static_cast<long long>(c) * tp * H * W + y2 * W + x2);
+      } else if (k == 147) {
+        val = 1.0f;
       }
       o[j] = val;
     }

@@ -142,8 +142,13 @@ class PackedUnet:
         wc[:, :, :39] = w12.permute(0, 2, 3, 1).reshape(co, 13, 39)
         self.w["init_comp"] = wc.reshape(co, 13 * 64).to(BF16).contiguous()
         self.f32["init_comp.bias"] = torch.einsum("omab,m->o", w2, b1).float().contiguous()
-        for name, taps in self.RING_KERNEL.items():                           # K index = tap*256 + m, negated
-            blk = torch.stack([w2[:, :, ky + 3, kx + 3] for ky, kx in taps], dim=1)     # (Cout, taps, 256)
+        # ring correction: the intermediate on the ring is b1 + w1 . patch7(q), so its 7x7 sub-kernels act on the ring's
+        # im2col rows directly: per tap a (Cout, 192) block = -(w2[tap] . [w1 as (256, 147) | b1 | 0]), K index = tap*192 + j
+        w1b = torch.zeros(256, 192, dtype=torch.float64, device=w2.device)
+        w1b[:, :147] = w1.permute(0, 2, 3, 1).reshape(256, 147)               # j = (ky'*7 + kx')*3 + c  (= pack7)
+        w1b[:, 147] = b1
+        for name, taps in self.RING_KERNEL.items():
+            blk = torch.stack([w2[:, :, ky + 3, kx + 3] @ w1b for ky, kx in taps], dim=1)     # (Cout, taps, 192)
             self.w["init_ring_" + name] = (-blk).reshape(co, -1).to(BF16).contiguous()
 
 
@@ -563,8 +568,8 @@ class UnetRunner:
         with xn_ext = b1 + w1 * pad6(x) the intermediate evaluated on the image extended by 3 pixels and `ring` its values
         outside the image.  The first term is ONE 13x13 convolution of the 3-channel flow (w12 = w2 * w1, K = 13 * 64 after
         an x-direction im2col, plus the constant w2 . b1); the second only touches output pixels within 3 of the border
-        and only the kernel rows / columns that reach outside: four GEMMs of 21 taps over the four ring strips, whose
-        values come from the init_noise GEMM on the strips' im2col rows.  47 instead of 157 MFLOP per pixel-row of 64."""
+        and only the kernel rows / columns that reach outside: four GEMMs of 21 taps over the four ring strips' im2col
+        rows (the ring values are linear in them: init_noise_conv is folded into the correction weights)."""
         cfg, pk, B, H, W = self.cfg, self.pk, self.B, self.H, self.W
         T, tc, tp = cfg.T, cfg.tc, cfg.tp
         d = cfg.dim
@@ -574,13 +579,12 @@ class UnetRunner:
         rbase = tc * hw * d
         ops.conv_cl(rec, xc, pk.w["init_comp"], d, 0, x0, t_range=(tc, T), taps=[(0, dy, 0) for dy in range(-6, 7)],
                     bias=bias, res=res, res_fp32=res_fp32)
-        # ---- ring values of the intermediate: im2col rows of the four strips -> init_noise GEMM (bias b1 included)
+        # ---- ring correction: im2col rows (147 patch values + a constant 1) of the four strips; init_noise_conv is folded
+        # into the correction weights, so the intermediate's ring values are never materialised
         n_tb, n_lr = ops.ring_rows(B, tp, H, W)
         rows = 2 * n_tb + 2 * n_lr
-        a_ring = self.buf(rows, 192)
-        ring = self.buf(rows, 256)
-        ops.im2col7_ring(rec, self.x, a_ring)
-        ops.linear_rows(rec, a_ring, pk.w["init_noise"], 256, ring, bias=pk.f32["init_noise_conv.bias"])
+        ring = self.buf(rows, 192)
+        ops.im2col7_ring(rec, self.x, ring)
         ostr = (d, W * d, hw * d, T * hw * d)
         strips = {
             "top": (ring[:n_tb], (W + 6, 3), (32, 4), (W, 3), 0),
@@ -589,7 +593,7 @@ class UnetRunner:
             "right": (ring[2 * n_tb + n_lr:], (3, H), (4, 32), (3, H), (W - 3) * d),
         }
         for name, (a, (d1, d2), (b1_, b2_), (c1, c2), off) in strips.items():
-            ops.gemm(rec, a0=a, c0=256, dims=(d1, d2, tp, B), strides0=(256, d1 * 256, d2 * d1 * 256, tp * d2 * d1 * 256),
+            ops.gemm(rec, a0=a, c0=192, dims=(d1, d2, tp, B), strides0=(192, d1 * 192, d2 * d1 * 192, tp * d2 * d1 * 192),
                      box=(b1_, b2_, 1, 1), start=(0, 0, 0, 0), count=(c1, c2, tp, B), taps=PackedUnet.RING_TAPS[name],
                      w=pk.w["init_ring_" + name], n=d, out=x0, out_stride=ostr, out_base=rbase + off,
                      res=x0, res_base=rbase + off, res_stride=ostr)

@@ -156,7 +156,8 @@ int extdm_im2col7_flow(const float* cond, const float* x, void* a, int B, int tc
  * image (the intermediate is zero padded, so the composition holds only away from the border).
  * im2col13x_flow: out[b, t_off + t, y, x, (dx + 6)*3 + c] = x[b, c, t, y, x + dx], dx in [-6, 6] (zeros outside the image and
  * in channels 39..63); x (B, 3, tp, H, W) fp32, out (B, T, H, W, 64) bf16 -- the 13 kernel rows are taps of the GEMM.
- * im2col7_ring: 7x7 im2col rows (K = 147 -> 192, layout of im2col7_flow) of the ring positions, strip by strip: top
+ * im2col7_ring: 7x7 im2col rows (K = 147 -> 192, layout of im2col7_flow; column 147 = 1, the carrier of
+ * init_noise_conv's bias) of the ring positions, strip by strip: top
  * (B, tp, 3, W+6) y = -3..-1, bottom y = H..H+2, left (B, tp, H, 3) x = -3..-1, right x = W..W+2;
  * a: (2*B*tp*3*(W+6) + 2*B*tp*H*3, 192) bf16. */
 int extdm_im2col13x_flow(const float* x, void* out, int B, int tp, int T, int t_off, int H, int W, void* stream);
