@@ -426,29 +426,33 @@ __global__ void __launch_bounds__(256) im2col7_image_kernel(const float* __restr
 // which is exact everywhere (unet.py: _composite_init).  Two gather kernels feed the GEMMs:
 // (1) x-direction im2col: out[b, t_off + t, y, x, (dx + 6) * 3 + c] = xin[b, c, t, y, x + dx], dx in [-6, 6], zeros outside
 //     the image and in channels 39..63; the 13 rows of the kernel are taps of the GEMM that follows.
+// One block per frame: the frame's three H x W planes are staged in shared memory with a zero halo of 6 columns.
 __global__ void __launch_bounds__(256) im2col13x_kernel(const float* __restrict__ xin, __nv_bfloat16* __restrict__ out,
                                                         int B, int tp, int T, int t_off, int H, int W) {
-  const long long total = static_cast<long long>(B) * tp * H * W * 8;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int v = i & 7;
-    long long r = i >> 3;
-    const int xx = r % W; r /= W;
-    const int yy = r % H; r /= H;
-    const int t = r % tp;
-    const int b = r / tp;
+  extern __shared__ float s_x[];                             // [3][H][W + 12]
+  const int t = blockIdx.x % tp, b = blockIdx.x / tp;
+  const int Wp = W + 12;
+  for (int i = threadIdx.x; i < 3 * H * Wp; i += blockDim.x) {
+    const int xp = i % Wp, yy = (i / Wp) % H, c = i / (Wp * H);
+    const int x2 = xp - 6;
+    s_x[i] = (x2 >= 0 && x2 < W) ? __ldg(xin + ((static_cast<long long>(b) * 3 + c) * tp + t) * H * W + yy * W + x2) : 0.f;
+  }
+  __syncthreads();
+  __nv_bfloat16* dst = out + (static_cast<long long>(b) * T + t_off + t) * H * W * 64;
+  // a thread keeps its vector index (blockDim.x % 8 == 0): the element -> (channel plane, column offset) map is loop invariant
+  const int v = threadIdx.x & 7;
+  int off[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = v * 8 + j;
+    off[j] = k < 39 ? (k % 3) * H * Wp + k / 3 : -1;         // x + dx + 6 with dx = k / 3 - 6
+  }
+  for (int px = threadIdx.x >> 3; px < H * W; px += blockDim.x >> 3) {
+    const int base = (px / W) * Wp + px % W;
     float o[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = v * 8 + j;
-      float val = 0.f;
-      if (k < 39) {
-        const int x2 = xx + k / 3 - 6, c = k % 3;
-        if (x2 >= 0 && x2 < W) val = __ldg(xin + ((static_cast<long long>(b) * 3 + c) * tp + t) * H * W + yy * W + x2);
-      }
-      o[j] = val;
-    }
-    store8(out + (((static_cast<long long>(b) * T + t_off + t) * H + yy) * W + xx) * 64 + v * 8, o);
+    for (int j = 0; j < 8; ++j) o[j] = off[j] >= 0 ? s_x[base + off[j]] : 0.f;
+    store8(dst + (static_cast<long long>(px) * 8 + v) * 8, o);
   }
 }
 
@@ -457,52 +461,58 @@ __global__ void __launch_bounds__(256) im2col13x_kernel(const float* __restrict_
 //     rows y = -3..-1, bottom (same shape) y = H..H+2, left (B, tp, H, 3) columns x = -3..-1, right (same shape)
 //     x = W..W+2.  The intermediate's ring values are linear in these rows, so the correction GEMMs read them directly
 //     with init_noise_conv folded into their weights (K = 192 per tap instead of 256, no GEMM in between).
+// One block per frame (planes staged in shared memory with a zero halo of 6: ring position +- 3).
 __global__ void __launch_bounds__(256) im2col7_ring_kernel(const float* __restrict__ xin, __nv_bfloat16* __restrict__ a,
                                                            int B, int tp, int H, int W) {
+  extern __shared__ float s_x[];                             // [3][H + 12][W + 12]
+  const int bt = blockIdx.x, t = bt % tp, b = bt / tp;
+  const int Wp = W + 12, Hp = H + 12;
+  for (int i = threadIdx.x; i < 3 * Hp * Wp; i += blockDim.x) {
+    const int xp = i % Wp, yp = (i / Wp) % Hp, c = i / (Wp * Hp);
+    const int x2 = xp - 6, y2 = yp - 6;
+    s_x[i] = (x2 >= 0 && x2 < W && y2 >= 0 && y2 < H)
+                 ? __ldg(xin + ((static_cast<long long>(b) * 3 + c) * tp + t) * H * W + y2 * W + x2) : 0.f;
+  }
+  __syncthreads();
   const long long n_tb = static_cast<long long>(B) * tp * 3 * (W + 6), n_lr = static_cast<long long>(B) * tp * H * 3;
-  const long long total = (2 * n_tb + 2 * n_lr) * 24;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int v = i % 24;
-    long long r = i / 24;
+  const int f_tb = 3 * (W + 6), f_lr = 3 * H;                // rows of this frame in a top / bottom and a left / right strip
+  const int rows = 2 * f_tb + 2 * f_lr;
+  // one warp per ring position, lane = 16-byte vector of its row (24 of 32 lanes): the position decode is warp-uniform and
+  // a lane's element -> (plane, tap) offsets are loop invariant
+  const int v = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  int off[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = v * 8 + j;
+    off[j] = k < 147 ? ((k % 3) * Hp + (k / 3) / 7 + 3) * Wp + (k / 3) % 7 + 3 : (k == 147 ? -1 : -2);
+  }
+  for (int r0 = warp; r0 < rows; r0 += nwarp) {
+    int r = r0;
     int qx, qy;
-    long long bt;
-    if (r < 2 * n_tb) {
-      const bool bottom = r >= n_tb;
-      if (bottom) r -= n_tb;
-      const int xi = r % (W + 6); r /= (W + 6);
-      const int yi = r % 3;
-      bt = r / 3;
+    long long row;                                           // global row of the strip-major buffer
+    if (r < 2 * f_tb) {
+      const bool bottom = r >= f_tb;
+      if (bottom) r -= f_tb;
+      const int xi = r % (W + 6), yi = r / (W + 6);
       qx = xi - 3;
       qy = bottom ? H + yi : yi - 3;
+      row = (bottom ? n_tb : 0) + static_cast<long long>(bt) * f_tb + r;
     } else {
-      r -= 2 * n_tb;
-      const bool right = r >= n_lr;
-      if (right) r -= n_lr;
-      const int xi = r % 3; r /= 3;
-      const int yi = r % H;
-      bt = r / H;
+      r -= 2 * f_tb;
+      const bool right = r >= f_lr;
+      if (right) r -= f_lr;
+      const int xi = r % 3, yi = r / 3;
       qx = right ? W + xi : xi - 3;
       qy = yi;
+      row = 2 * n_tb + (right ? n_lr : 0) + static_cast<long long>(bt) * f_lr + r;
     }
-    const int t = bt % tp;
-    const int b = bt / tp;
-    const float* src = xin + (static_cast<long long>(b) * 3 * tp + t) * H * W;      // + c * tp * H * W
-    float o[8];
+    if (v < 24) {
+      const int base = qy * Wp + qx;                         // (q + tap - 3) + 6 = q + tap + 3: the + 3 is inside off[]
+      float o[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = v * 8 + j;
-      float val = 0.f;
-      if (k < 147) {
-        const int tap = k / 3, c = k % 3;
-        const int y2 = qy + tap / 7 - 3, x2 = qx + tap % 7 - 3;
-        if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) val = __ldg(src + static_cast<long long>(c) * tp * H * W + y2 * W + x2);
-      } else if (k == 147) {
-        val = 1.0f;
-      }
-      o[j] = val;
+      for (int j = 0; j < 8; ++j) o[j] = off[j] >= 0 ? s_x[base + off[j]] : (off[j] == -1 ? 1.0f : 0.f);
+      store8(a + (row * 24 + v) * 8, o);
     }
-    store8(a + i * 8, o);
   }
 }
 
@@ -1005,20 +1015,18 @@ extern "C" int extdm_im2col7_image(const float* img, void* a, long long F, int H
 
 extern "C" int extdm_im2col13x_flow(const float* x, void* out, int B, int tp, int T, int t_off, int H, int W, void* stream) {
   if (!x || !out || B < 1 || tp < 1 || t_off < 0 || t_off + tp > T) return bad_arg("im2col13x_flow: bad frame range");
-  const long long total = static_cast<long long>(B) * tp * H * W * 8;
-  im2col13x_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(x, BFW(out), B, tp, T, t_off, H, W);
+  const size_t smem = static_cast<size_t>(3) * H * (W + 12) * sizeof(float);
+  if (smem > 48 * 1024) return bad_arg("im2col13x_flow: frame too large for the shared-memory stage");
+  im2col13x_kernel<<<B * tp, 256, smem, STREAM>>>(x, BFW(out), B, tp, T, t_off, H, W);
   EXTDM_CHECK_LAUNCH();
   return EXTDM_OK;
 }
 
-static long long im2col7_ring_rows(int B, int tp, int H, int W) {
-  return 2ll * B * tp * 3 * (W + 6) + 2ll * B * tp * H * 3;
-}
-
 extern "C" int extdm_im2col7_ring(const float* x, void* a, int B, int tp, int H, int W, void* stream) {
   if (!x || !a || B < 1 || tp < 1 || H < 7 || W < 7) return bad_arg("im2col7_ring: H, W >= 7");
-  const long long total = im2col7_ring_rows(B, tp, H, W) * 24;
-  im2col7_ring_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(x, BFW(a), B, tp, H, W);
+  const size_t smem = static_cast<size_t>(3) * (H + 12) * (W + 12) * sizeof(float);
+  if (smem > 48 * 1024) return bad_arg("im2col7_ring: frame too large for the shared-memory stage");
+  im2col7_ring_kernel<<<B * tp, 256, smem, STREAM>>>(x, BFW(a), B, tp, H, W);
   EXTDM_CHECK_LAUNCH();
   return EXTDM_OK;
 }
