@@ -6,7 +6,8 @@ forward is a *launch list* of C-ABI kernels (ops.Recorder) over channels-last bf
   * a prologue that only depends on the conditioning (cond_frames, cond_fea) -- cond_adaptor,
     cond_temporal_attn, the bilinear resize, the cond_fea half of init_conv and the conditioning frames of
     init_noise_conv / init_conv (exact up to fp re-association), run once per round, and
-  * a step list run once per DDIM iteration.
+  * a step list run once per DDIM iteration; on the predicted frames init_conv(init_noise_conv(x)) is evaluated as one
+    13x13 convolution of the flow plus a ring correction (UnetRunner._composite_init: exact, 4x fewer FLOPs).
 No torch op touches activations; torch supplies memory, weights and the state_dict plumbing.
 """
 import math
