@@ -112,8 +112,8 @@ __device__ __forceinline__ void epilogue_loop(const GemmDev& p, uint64_t* acc_fu
                         g3 < p.start[2] + p.count[2] && g4 < p.start[3] + p.count[3];
     const long long orow = p.out_base + p.phase_out[tc.phase] + g1 * p.out_stride[0] + g2 * p.out_stride[1] +
                            g3 * p.out_stride[2] + g4 * p.out_stride[3];
-    const long long rrow = p.res_base + g1 * p.res_stride[0] + g2 * p.res_stride[1] + g3 * p.res_stride[2] +
-                           g4 * p.res_stride[3];
+    const long long rrow = p.res_base + p.phase_out[tc.phase] + g1 * p.res_stride[0] + g2 * p.res_stride[1] +
+                           g3 * p.res_stride[2] + g4 * p.res_stride[3];
     // The accumulator is drained in groups of 4 chunks (64 columns): the group body is unrolled (static register
     // indices for the double-buffered tcgen05.ld and the prefetched residual), the group loop is not (code size).
     // residual prefetch: bf16 residuals 64 columns (8 x 16 B) at a time, fp32 residuals 32 columns

@@ -445,13 +445,13 @@ __global__ void __launch_bounds__(256) im2col13x_kernel(const float* __restrict_
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int k = v * 8 + j;
-    off[j] = k < 39 ? (k % 3) * H * Wp + k / 3 : -1;         // x + dx + 6 with dx = k / 3 - 6
+    off[j] = k < 39 ? (k % 3) * H * Wp + k / 3 : (k == 39 ? -1 : -2);      // x + dx + 6 with dx = k / 3 - 6; 39: constant 1
   }
   for (int px = threadIdx.x >> 3; px < H * W; px += blockDim.x >> 3) {
     const int base = (px / W) * Wp + px % W;
     float o[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = off[j] >= 0 ? s_x[base + off[j]] : 0.f;
+    for (int j = 0; j < 8; ++j) o[j] = off[j] >= 0 ? s_x[base + off[j]] : (off[j] == -1 ? 1.0f : 0.f);
     store8(dst + (static_cast<long long>(px) * 8 + v) * 8, o);
   }
 }
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(256) im2col13x_kernel(const float* __restrict_
 //     with init_noise_conv folded into their weights (K = 192 per tap instead of 256, no GEMM in between).
 // One block per frame (planes staged in shared memory with a zero halo of 6: ring position +- 3).
 __global__ void __launch_bounds__(256) im2col7_ring_kernel(const float* __restrict__ xin, __nv_bfloat16* __restrict__ a,
-                                                           int B, int tp, int H, int W) {
+                                                           int B, int tp, int H, int W, int with_tb) {
   extern __shared__ float s_x[];                             // [3][H + 12][W + 12]
   const int bt = blockIdx.x, t = bt % tp, b = bt / tp;
   const int Wp = W + 12, Hp = H + 12;
@@ -474,8 +474,8 @@ __global__ void __launch_bounds__(256) im2col7_ring_kernel(const float* __restri
                  ? __ldg(xin + ((static_cast<long long>(b) * 3 + c) * tp + t) * H * W + y2 * W + x2) : 0.f;
   }
   __syncthreads();
-  const long long n_tb = static_cast<long long>(B) * tp * 3 * (W + 6), n_lr = static_cast<long long>(B) * tp * H * 3;
-  const int f_tb = 3 * (W + 6), f_lr = 3 * H;                // rows of this frame in a top / bottom and a left / right strip
+  const int f_tb = with_tb ? 3 * (W + 6) : 0, f_lr = 3 * H;  // rows of this frame in a top / bottom and a left / right strip
+  const long long n_tb = static_cast<long long>(B) * tp * f_tb, n_lr = static_cast<long long>(B) * tp * f_lr;
   const int rows = 2 * f_tb + 2 * f_lr;
   // one warp per ring position, lane = 16-byte vector of its row (24 of 32 lanes): the position decode is warp-uniform and
   // a lane's element -> (plane, tap) offsets are loop invariant
@@ -1022,11 +1022,11 @@ extern "C" int extdm_im2col13x_flow(const float* x, void* out, int B, int tp, in
   return EXTDM_OK;
 }
 
-extern "C" int extdm_im2col7_ring(const float* x, void* a, int B, int tp, int H, int W, void* stream) {
+extern "C" int extdm_im2col7_ring(const float* x, void* a, int B, int tp, int H, int W, int with_top_bottom, void* stream) {
   if (!x || !a || B < 1 || tp < 1 || H < 7 || W < 7) return bad_arg("im2col7_ring: H, W >= 7");
   const size_t smem = static_cast<size_t>(3) * (H + 12) * (W + 12) * sizeof(float);
   if (smem > 48 * 1024) return bad_arg("im2col7_ring: frame too large for the shared-memory stage");
-  im2col7_ring_kernel<<<B * tp, 256, smem, STREAM>>>(x, BFW(a), B, tp, H, W);
+  im2col7_ring_kernel<<<B * tp, 256, smem, STREAM>>>(x, BFW(a), B, tp, H, W, with_top_bottom);
   EXTDM_CHECK_LAUNCH();
   return EXTDM_OK;
 }

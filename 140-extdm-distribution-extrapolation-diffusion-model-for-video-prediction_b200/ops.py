@@ -390,10 +390,11 @@ def ring_rows(B, tp, H, W):
     return n_tb, n_lr
 
 
-def im2col7_ring(rec, x, a):
-    """x (B, 3, tp, H, W) fp32 -> 7x7 im2col rows (K 147 -> 192) of the 3-pixel ring around each frame."""
+def im2col7_ring(rec, x, a, with_top_bottom=True):
+    """x (B, 3, tp, H, W) fp32 -> 7x7 im2col rows (K 147 -> 192, column 147 = 1) of the 3-pixel ring around each frame
+    (with_top_bottom=False: the left and right strips only)."""
     B, _, tp, H, W = x.shape
-    rec.emit("extdm_im2col7_ring", (_p(x), _p(a), B, tp, H, W), keep=(x, a))
+    rec.emit("extdm_im2col7_ring", (_p(x), _p(a), B, tp, H, W, int(with_top_bottom)), keep=(x, a))
 
 
 def bilinear_resize_cl(rec, x, y):

@@ -143,14 +143,37 @@ class PackedUnet:
         wc[:, :, :39] = w12.permute(0, 2, 3, 1).reshape(co, 13, 39)
         self.w["init_comp"] = wc.reshape(co, 13 * 64).to(BF16).contiguous()
         self.f32["init_comp.bias"] = torch.einsum("omab,m->o", w2, b1).float().contiguous()
-        # ring correction: the intermediate on the ring is b1 + w1 . patch7(q), so its 7x7 sub-kernels act on the ring's
-        # im2col rows directly: per tap a (Cout, 192) block = -(w2[tap] . [w1 as (256, 147) | b1 | 0]), K index = tap*192 + j
+        # ring correction, left / right strips: the intermediate on the ring is b1 + w1 . patch7(q), so its 7x7 sub-kernels
+        # act on the ring's im2col rows directly: per tap a (Cout, 192) block = -(w2[tap] . [w1 as (256, 147) | b1 | 0]),
+        # K index = tap*192 + j
         w1b = torch.zeros(256, 192, dtype=torch.float64, device=w2.device)
         w1b[:, :147] = w1.permute(0, 2, 3, 1).reshape(256, 147)               # j = (ky'*7 + kx')*3 + c  (= pack7)
         w1b[:, 147] = b1
-        for name, taps in self.RING_KERNEL.items():
-            blk = torch.stack([w2[:, :, ky + 3, kx + 3] @ w1b for ky, kx in taps], dim=1)     # (Cout, taps, 192)
+        for name in ("left", "right"):
+            blk = torch.stack([w2[:, :, ky + 3, kx + 3] @ w1b for ky, kx in self.RING_KERNEL[name]], dim=1)
             self.w["init_ring_" + name] = (-blk).reshape(co, -1).to(BF16).contiguous()
+        # ring correction, rows above / below the image: ring rows only see the image's first / last three rows, and the
+        # x-direction im2col (channel (dx + 6)*3 + c, channel 39 = 1) makes the correction of output row p a position-
+        # independent product over those three rows: one GEMM phase per output row, K index = s*64 + (dx + 6)*3 + c with s
+        # the source row.  top: output row p, kernel rows ky <= -1 - p reach outside, source row s = p + ky + a;
+        # bottom (rows counted from H - 3): output row p, ky >= 3 - p, source row s = p + ky + a as well.
+        for name in ("top", "bottom"):
+            mats = []
+            for pr in range(3):
+                cp = torch.zeros(co, 3, 64, dtype=torch.float64, device=w2.device)
+                kys = range(-3, -pr) if name == "top" else range(3 - pr, 4)
+                for ky in kys:
+                    for kx in range(-3, 4):
+                        w2t = w2[:, :, ky + 3, kx + 3]                                     # (Cout, 256)
+                        cp[:, 0, 39] += w2t @ b1                                           # constant carrier (a pixel of row 0 / H-3)
+                        for sr in range(3):
+                            a = sr - pr - ky                                               # kernel row of init_noise_conv
+                            if -3 <= a <= 3:
+                                blk = torch.einsum("om,mcb->obc", w2t, w1[:, :, a + 3, :])  # (Cout, 7 (b), 3 (c))
+                                lo = (kx + 3) * 3                                          # dx + 6 = kx + b + 6, b = -3 .. 3
+                                cp[:, sr, lo:lo + 21] += blk.reshape(co, 21)
+                mats.append(-cp.reshape(co, 192))
+            self.w["init_ring_" + name] = torch.cat(mats, dim=0).to(BF16).contiguous()      # (3 phases * Cout, 192)
 
 
 class UnetRunner:
@@ -569,8 +592,10 @@ class UnetRunner:
         with xn_ext = b1 + w1 * pad6(x) the intermediate evaluated on the image extended by 3 pixels and `ring` its values
         outside the image.  The first term is ONE 13x13 convolution of the 3-channel flow (w12 = w2 * w1, K = 13 * 64 after
         an x-direction im2col, plus the constant w2 . b1); the second only touches output pixels within 3 of the border
-        and only the kernel rows / columns that reach outside: four GEMMs of 21 taps over the four ring strips' im2col
-        rows (the ring values are linear in them: init_noise_conv is folded into the correction weights)."""
+        and only the kernel rows / columns that reach outside.  The ring values are linear in x (init_noise_conv is
+        folded into the correction weights): rows above / below the image become one 3-phase GEMM each over the first /
+        last three rows of the x-im2col tensor (K = 192), columns left / right a 21-tap GEMM each over strips of the ring
+        positions' im2col rows (a tap that leaves the strip reads zeros, which is the partition of the ring)."""
         cfg, pk, B, H, W = self.cfg, self.pk, self.B, self.H, self.W
         T, tc, tp = cfg.T, cfg.tc, cfg.tp
         d = cfg.dim
@@ -582,16 +607,20 @@ class UnetRunner:
                     bias=bias, res=res, res_fp32=res_fp32)
         # ---- ring correction: im2col rows (147 patch values + a constant 1) of the four strips; init_noise_conv is folded
         # into the correction weights, so the intermediate's ring values are never materialised
-        n_tb, n_lr = ops.ring_rows(B, tp, H, W)
-        rows = 2 * n_tb + 2 * n_lr
-        ring = self.buf(rows, 192)
-        ops.im2col7_ring(rec, self.x, ring)
         ostr = (d, W * d, hw * d, T * hw * d)
+        # rows above / below: three phases (output rows) over the image's first / last three rows of the x-im2col tensor
+        for name, y0 in (("top", 0), ("bottom", H - 3)):
+            ops.gemm(rec, a0=xc, c0=64, dims=(W, H, T, B), strides0=(64, W * 64, hw * 64, T * hw * 64),
+                     box=(32, 1, 4, 1), start=(0, y0, tc, 0), count=(W, 1, tp, B), taps=[(0, 0, 0), (0, 1, 0), (0, 2, 0)],
+                     w=pk.w["init_ring_" + name], n=d, out=x0, out_stride=ostr, res=x0, res_stride=ostr,
+                     phases=[([(0, 0, 0), (0, 1, 0), (0, 2, 0)], pr * W * d) for pr in range(3)])
+        # columns left / right of the image (rows inside it): strips of im2col rows, 21 taps each
+        _, n_lr = ops.ring_rows(B, tp, H, W)
+        ring = self.buf(2 * n_lr, 192)
+        ops.im2col7_ring(rec, self.x, ring, with_top_bottom=False)
         strips = {
-            "top": (ring[:n_tb], (W + 6, 3), (32, 4), (W, 3), 0),
-            "bottom": (ring[n_tb:2 * n_tb], (W + 6, 3), (32, 4), (W, 3), (H - 3) * W * d),
-            "left": (ring[2 * n_tb:2 * n_tb + n_lr], (3, H), (4, 32), (3, H), 0),
-            "right": (ring[2 * n_tb + n_lr:], (3, H), (4, 32), (3, H), (W - 3) * d),
+            "left": (ring[:n_lr], (3, H), (4, 32), (3, H), 0),
+            "right": (ring[n_lr:], (3, H), (4, 32), (3, H), (W - 3) * d),
         }
         for name, (a, (d1, d2), (b1_, b2_), (c1, c2), off) in strips.items():
             ops.gemm(rec, a0=a, c0=192, dims=(d1, d2, tp, B), strides0=(192, d1 * 192, d2 * d1 * 192, tp * d2 * d1 * 192),

@@ -88,7 +88,7 @@ typedef struct ExtdmGemm {
   /* Phases: n_phase (0 or 1 = none, up to 4) independent products over the SAME A tiles in one launch -- the four
    * sub-pixel phases of ConvTranspose3d (1,4,4)/s2/p1 (...cross_multi.py:125-127, Upsample).  Phase p uses the taps
    * tap[p*ntaps .. (p+1)*ntaps), the weight rows [p*n, (p+1)*n) of W (w_rows = n_phase*n, block_n | n) and writes at
-   * out_base + phase_out_offset[p].  n_phase*ntaps <= 64.  Plain (non-halo) kernel only; no gn_partials. */
+   * out_base + phase_out_offset[p] (a residual is read at res_base + phase_out_offset[p]).  n_phase*ntaps <= 64.  Plain (non-halo) kernel only; no gn_partials. */
   int n_phase;
   long long phase_out_offset[4];
 } ExtdmGemm;
@@ -155,13 +155,14 @@ int extdm_im2col7_flow(const float* cond, const float* x, void* a, int B, int tc
  * convolution of the 3-channel flow minus a 7x7 convolution of the intermediate's values on the 3-pixel ring outside the
  * image (the intermediate is zero padded, so the composition holds only away from the border).
  * im2col13x_flow: out[b, t_off + t, y, x, (dx + 6)*3 + c] = x[b, c, t, y, x + dx], dx in [-6, 6] (zeros outside the image and
- * in channels 39..63); x (B, 3, tp, H, W) fp32, out (B, T, H, W, 64) bf16 -- the 13 kernel rows are taps of the GEMM.
+ * in channels 40..63, channel 39 = 1: the carrier of constants); x (B, 3, tp, H, W) fp32, out (B, T, H, W, 64) bf16 -- the 13
+ * kernel rows are taps of the GEMM.
  * im2col7_ring: 7x7 im2col rows (K = 147 -> 192, layout of im2col7_flow; column 147 = 1, the carrier of
  * init_noise_conv's bias) of the ring positions, strip by strip: top
  * (B, tp, 3, W+6) y = -3..-1, bottom y = H..H+2, left (B, tp, H, 3) x = -3..-1, right x = W..W+2;
- * a: (2*B*tp*3*(W+6) + 2*B*tp*H*3, 192) bf16. */
+ * a: (2*B*tp*3*(W+6) + 2*B*tp*H*3, 192) bf16; with_top_bottom = 0: the left and right strips only. */
 int extdm_im2col13x_flow(const float* x, void* out, int B, int tp, int T, int t_off, int H, int W, void* stream);
-int extdm_im2col7_ring(const float* x, void* a, int B, int tp, int H, int W, void* stream);
+int extdm_im2col7_ring(const float* x, void* a, int B, int tp, int H, int W, int with_top_bottom, void* stream);
 
 /* Bilinear resize (align_corners=False) of channels-last frames: F.interpolate in ..._traj_ada.py:1039-1041. */
 int extdm_bilinear_resize_cl(const void* x, void* y, long long F, int h, int w, int H, int W, int C, void* stream);
