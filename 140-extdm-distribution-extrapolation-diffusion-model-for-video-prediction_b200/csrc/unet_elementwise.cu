@@ -456,62 +456,50 @@ __global__ void __launch_bounds__(256) im2col13x_kernel(const float* __restrict_
   }
 }
 
-// (2) 7x7 im2col rows (K = 147 -> 192, same layout as im2col7_flow, plus a constant 1 in column 147 that carries
-//     init_noise_conv's bias) of the positions of the 3-pixel ring around the image, strip by strip: top (B, tp, 3, W+6)
-//     rows y = -3..-1, bottom (same shape) y = H..H+2, left (B, tp, H, 3) columns x = -3..-1, right (same shape)
-//     x = W..W+2.  The intermediate's ring values are linear in these rows, so the correction GEMMs read them directly
-//     with init_noise_conv folded into their weights (K = 192 per tap instead of 256, no GEMM in between).
-// One block per frame (planes staged in shared memory with a zero halo of 6: ring position +- 3).
-__global__ void __launch_bounds__(256) im2col7_ring_kernel(const float* __restrict__ xin, __nv_bfloat16* __restrict__ a,
-                                                           int B, int tp, int H, int W, int with_tb) {
-  extern __shared__ float s_x[];                             // [3][H + 12][W + 12]
-  const int bt = blockIdx.x, t = bt % tp, b = bt / tp;
-  const int Wp = W + 12, Hp = H + 12;
-  for (int i = threadIdx.x; i < 3 * Hp * Wp; i += blockDim.x) {
-    const int xp = i % Wp, yp = (i / Wp) % Hp, c = i / (Wp * Hp);
-    const int x2 = xp - 6, y2 = yp - 6;
-    s_x[i] = (x2 >= 0 && x2 < W && y2 >= 0 && y2 < H)
-                 ? __ldg(xin + ((static_cast<long long>(b) * 3 + c) * tp + t) * H * W + y2 * W + x2) : 0.f;
+// (2) Corner add-back.  The ring correction is evaluated as (rows above) + (rows below) + (columns left) + (columns
+//     right), each over ALL positions of its side so that it is position independent; the four 3x3 corner blocks of
+//     the ring are then counted twice.  Their contribution only reaches the 3x3 output pixels next to each corner and
+//     is linear in the 3x3x3 image values there (+ a constant): table[corner][pixel][k][co], k = (r*3 + s)*3 + c for
+//     the image value (row y0 + r, column x0 + s, channel c) of the corner block, k = 27 the constant.  One block
+//     handles kCornerFrames frames (a thread's 28 weights per output are loaded once and reused for every frame).
+constexpr int kCornerFrames = 8;
+__global__ void __launch_bounds__(256) init_corner_fix_kernel(const float* __restrict__ xin, const float* __restrict__ table,
+                                                              __nv_bfloat16* __restrict__ x0, int B, int tp, int T,
+                                                              int t_off, int H, int W, int C) {
+  __shared__ float s_p[kCornerFrames][4][28];
+  const int f0 = blockIdx.x * kCornerFrames, nf = B * tp;
+  for (int i = threadIdx.x; i < kCornerFrames * 4 * 28; i += blockDim.x) {
+    const int k = i % 28, cn = (i / 28) & 3, fi = i / 112;
+    const int f = f0 + fi;
+    float v = 0.f;
+    if (f < nf) {
+      if (k == 27) {
+        v = 1.0f;
+      } else {
+        const int c = k % 3, sx = (k / 3) % 3, r = k / 9;
+        const int yy = ((cn >> 1) ? H - 3 : 0) + r, xx = ((cn & 1) ? W - 3 : 0) + sx;
+        const int t = f % tp, b = f / tp;
+        v = __ldg(xin + ((static_cast<long long>(b) * 3 + c) * tp + t) * H * W + yy * W + xx);
+      }
+    }
+    s_p[fi][cn][k] = v;
   }
   __syncthreads();
-  const int f_tb = with_tb ? 3 * (W + 6) : 0, f_lr = 3 * H;  // rows of this frame in a top / bottom and a left / right strip
-  const long long n_tb = static_cast<long long>(B) * tp * f_tb, n_lr = static_cast<long long>(B) * tp * f_lr;
-  const int rows = 2 * f_tb + 2 * f_lr;
-  // one warp per ring position, lane = 16-byte vector of its row (24 of 32 lanes): the position decode is warp-uniform and
-  // a lane's element -> (plane, tap) offsets are loop invariant
-  const int v = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  int off[8];
+  for (int o = threadIdx.x; o < 4 * 9 * C; o += blockDim.x) {        // output = (corner, pixel, channel), channel fastest
+    const int co = o % C, px = (o / C) % 9, cn = o / (9 * C);
+    float w[28];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int k = v * 8 + j;
-    off[j] = k < 147 ? ((k % 3) * Hp + (k / 3) / 7 + 3) * Wp + (k / 3) % 7 + 3 : (k == 147 ? -1 : -2);
-  }
-  for (int r0 = warp; r0 < rows; r0 += nwarp) {
-    int r = r0;
-    int qx, qy;
-    long long row;                                           // global row of the strip-major buffer
-    if (r < 2 * f_tb) {
-      const bool bottom = r >= f_tb;
-      if (bottom) r -= f_tb;
-      const int xi = r % (W + 6), yi = r / (W + 6);
-      qx = xi - 3;
-      qy = bottom ? H + yi : yi - 3;
-      row = (bottom ? n_tb : 0) + static_cast<long long>(bt) * f_tb + r;
-    } else {
-      r -= 2 * f_tb;
-      const bool right = r >= f_lr;
-      if (right) r -= f_lr;
-      const int xi = r % 3, yi = r / 3;
-      qx = right ? W + xi : xi - 3;
-      qy = yi;
-      row = 2 * n_tb + (right ? n_lr : 0) + static_cast<long long>(bt) * f_lr + r;
-    }
-    if (v < 24) {
-      const int base = qy * Wp + qx;                         // (q + tap - 3) + 6 = q + tap + 3: the + 3 is inside off[]
-      float o[8];
+    for (int k = 0; k < 28; ++k) w[k] = __ldg(table + ((static_cast<long long>(cn) * 9 + px) * 28 + k) * C + co);
+    const int yy = ((cn >> 1) ? H - 3 : 0) + px / 3, xx = ((cn & 1) ? W - 3 : 0) + px % 3;
+    for (int fi = 0; fi < kCornerFrames; ++fi) {
+      const int f = f0 + fi;
+      if (f >= nf) break;
+      float acc = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = off[j] >= 0 ? s_x[base + off[j]] : (off[j] == -1 ? 1.0f : 0.f);
-      store8(a + (row * 24 + v) * 8, o);
+      for (int k = 0; k < 28; ++k) acc += w[k] * s_p[fi][cn][k];
+      const int t = f % tp, b = f / tp;
+      __nv_bfloat16* dst = x0 + (((static_cast<long long>(b) * T + t_off + t) * H + yy) * W + xx) * C + co;
+      *dst = __float2bfloat16(__bfloat162float(*dst) + acc);
     }
   }
 }
@@ -1022,11 +1010,13 @@ extern "C" int extdm_im2col13x_flow(const float* x, void* out, int B, int tp, in
   return EXTDM_OK;
 }
 
-extern "C" int extdm_im2col7_ring(const float* x, void* a, int B, int tp, int H, int W, int with_top_bottom, void* stream) {
-  if (!x || !a || B < 1 || tp < 1 || H < 7 || W < 7) return bad_arg("im2col7_ring: H, W >= 7");
-  const size_t smem = static_cast<size_t>(3) * (H + 12) * (W + 12) * sizeof(float);
-  if (smem > 48 * 1024) return bad_arg("im2col7_ring: frame too large for the shared-memory stage");
-  im2col7_ring_kernel<<<B * tp, 256, smem, STREAM>>>(x, BFW(a), B, tp, H, W, with_top_bottom);
+extern "C" int extdm_init_corner_fix(const float* x, const float* table, void* x0, int B, int tp, int T, int t_off, int H,
+                                     int W, int C, void* stream) {
+  if (!x || !table || !x0 || B < 1 || tp < 1 || t_off < 0 || t_off + tp > T || H < 6 || W < 6 || C < 1)
+    return bad_arg("init_corner_fix: bad arguments");
+  const int frames = B * tp;
+  init_corner_fix_kernel<<<(frames + kCornerFrames - 1) / kCornerFrames, 256, 0, STREAM>>>(x, table, BFW(x0), B, tp, T,
+                                                                                          t_off, H, W, C);
   EXTDM_CHECK_LAUNCH();
   return EXTDM_OK;
 }

@@ -384,17 +384,12 @@ def im2col13x_flow(rec, x, out, t_off):
     rec.emit("extdm_im2col13x_flow", (_p(x), _p(out), B, tp, out.shape[1], t_off, H, W), keep=(x, out))
 
 
-def ring_rows(B, tp, H, W):
-    """Rows of the four ring strips (top, bottom, left, right) in im2col7_ring's order."""
-    n_tb, n_lr = B * tp * 3 * (W + 6), B * tp * H * 3
-    return n_tb, n_lr
-
-
-def im2col7_ring(rec, x, a, with_top_bottom=True):
-    """x (B, 3, tp, H, W) fp32 -> 7x7 im2col rows (K 147 -> 192, column 147 = 1) of the 3-pixel ring around each frame
-    (with_top_bottom=False: the left and right strips only)."""
+def init_corner_fix(rec, x, table, x0, t_off):
+    """Corner add-back of the composite init_conv's ring correction: x (B, 3, tp, H, W) fp32, table (4, 9, 28, C) fp32,
+    x0 (B, T, H, W, C) bf16 updated in place on frames [t_off, t_off + tp)."""
     B, _, tp, H, W = x.shape
-    rec.emit("extdm_im2col7_ring", (_p(x), _p(a), B, tp, H, W, int(with_top_bottom)), keep=(x, a))
+    rec.emit("extdm_init_corner_fix", (_p(x), _p(table), _p(x0), B, tp, x0.shape[1], t_off, H, W, x0.shape[-1]),
+             keep=(x, table, x0))
 
 
 def bilinear_resize_cl(rec, x, y):

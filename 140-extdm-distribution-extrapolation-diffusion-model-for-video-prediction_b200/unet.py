@@ -113,20 +113,6 @@ class PackedUnet:
         self.rope_w = _rope_tables(wd * wh * ww, cfg.dim_head, device)
 
 
-    # taps of the four ring-correction GEMMs (UnetRunner._composite_init): offsets into the strip tensors
-    RING_TAPS = {
-        "top": [(kx + 3, ky + 3, 0) for ky in (-3, -2, -1) for kx in range(-3, 4)],
-        "bottom": [(kx + 3, ky - 3, 0) for ky in (1, 2, 3) for kx in range(-3, 4)],
-        "left": [(kx + 3, ky, 0) for ky in range(-3, 4) for kx in (-3, -2, -1)],
-        "right": [(kx - 3, ky, 0) for ky in range(-3, 4) for kx in (1, 2, 3)],
-    }
-    RING_KERNEL = {          # the (ky, kx) each tap stands for, same order
-        "top": [(ky, kx) for ky in (-3, -2, -1) for kx in range(-3, 4)],
-        "bottom": [(ky, kx) for ky in (1, 2, 3) for kx in range(-3, 4)],
-        "left": [(ky, kx) for ky in range(-3, 4) for kx in (-3, -2, -1)],
-        "right": [(ky, kx) for ky in range(-3, 4) for kx in (1, 2, 3)],
-    }
-
     def _pack_composite_init(self, w2):
         """init_conv's weights over the init_noise_conv channels, w2 (Cout, 256, 7, 7), composed with init_noise_conv
         (256, 3, 7, 7) into one 13x13 kernel over the 3 flow channels (..._traj_ada.py:916,1032-1042: two linear
@@ -143,26 +129,22 @@ class PackedUnet:
         wc[:, :, :39] = w12.permute(0, 2, 3, 1).reshape(co, 13, 39)
         self.w["init_comp"] = wc.reshape(co, 13 * 64).to(BF16).contiguous()
         self.f32["init_comp.bias"] = torch.einsum("omab,m->o", w2, b1).float().contiguous()
-        # ring correction, left / right strips: the intermediate on the ring is b1 + w1 . patch7(q), so its 7x7 sub-kernels
-        # act on the ring's im2col rows directly: per tap a (Cout, 192) block = -(w2[tap] . [w1 as (256, 147) | b1 | 0]),
-        # K index = tap*192 + j
-        w1b = torch.zeros(256, 192, dtype=torch.float64, device=w2.device)
-        w1b[:, :147] = w1.permute(0, 2, 3, 1).reshape(256, 147)               # j = (ky'*7 + kx')*3 + c  (= pack7)
-        w1b[:, 147] = b1
-        for name in ("left", "right"):
-            blk = torch.stack([w2[:, :, ky + 3, kx + 3] @ w1b for ky, kx in self.RING_KERNEL[name]], dim=1)
-            self.w["init_ring_" + name] = (-blk).reshape(co, -1).to(BF16).contiguous()
-        # ring correction, rows above / below the image: ring rows only see the image's first / last three rows, and the
-        # x-direction im2col (channel (dx + 6)*3 + c, channel 39 = 1) makes the correction of output row p a position-
-        # independent product over those three rows: one GEMM phase per output row, K index = s*64 + (dx + 6)*3 + c with s
-        # the source row.  top: output row p, kernel rows ky <= -1 - p reach outside, source row s = p + ky + a;
-        # bottom (rows counted from H - 3): output row p, ky >= 3 - p, source row s = p + ky + a as well.
-        for name in ("top", "bottom"):
+        # ---- ring correction.  The intermediate on the ring is b1 + w1 . (7x7 patch of x), so every piece is linear in x;
+        # the x-direction im2col (channel (dx + 6)*3 + c = x at column offset dx, channel 39 = 1) is the A tensor of all four
+        # sides.  A side sums over ALL ring positions of that side, which makes it position independent:
+        #   rows above / below: output row p (counted from row 0 / H - 3), kernel rows ky that reach outside, source row
+        #     s = p + ky + a in {0, 1, 2} (three taps), K index = s*64 + (dx + 6)*3 + c;
+        #   columns left / right: output column p (counted from column 0 / W - 3), kernel columns kx that reach outside,
+        #     all 13 row offsets dy = ky + a as taps, read at the output column itself: K index = (dy + 6)*64 + (dx + 6)*3 + c.
+        # One GEMM phase per output row / column; weights negated (the correction is subtracted).
+        def outside(side, pr):                 # kernel rows / columns of init_conv that reach outside for output row / col pr
+            return range(-3, -pr) if side in ("top", "left") else range(3 - pr, 4)
+
+        for side in ("top", "bottom"):
             mats = []
             for pr in range(3):
                 cp = torch.zeros(co, 3, 64, dtype=torch.float64, device=w2.device)
-                kys = range(-3, -pr) if name == "top" else range(3 - pr, 4)
-                for ky in kys:
+                for ky in outside(side, pr):
                     for kx in range(-3, 4):
                         w2t = w2[:, :, ky + 3, kx + 3]                                     # (Cout, 256)
                         cp[:, 0, 39] += w2t @ b1                                           # constant carrier (a pixel of row 0 / H-3)
@@ -173,7 +155,37 @@ class PackedUnet:
                                 lo = (kx + 3) * 3                                          # dx + 6 = kx + b + 6, b = -3 .. 3
                                 cp[:, sr, lo:lo + 21] += blk.reshape(co, 21)
                 mats.append(-cp.reshape(co, 192))
-            self.w["init_ring_" + name] = torch.cat(mats, dim=0).to(BF16).contiguous()      # (3 phases * Cout, 192)
+            self.w["init_ring_" + side] = torch.cat(mats, dim=0).to(BF16).contiguous()      # (3 phases * Cout, 3*64)
+        for side in ("left", "right"):
+            mats = []
+            for pr in range(3):
+                cp = torch.zeros(co, 13, 64, dtype=torch.float64, device=w2.device)
+                for kx in outside(side, pr):
+                    for ky in range(-3, 4):
+                        w2t = w2[:, :, ky + 3, kx + 3]
+                        cp[:, 6, 39] += w2t @ b1                                           # constant: tap dy = 0
+                        blk = torch.einsum("om,mcab->oabc", w2t, w1)                       # (Cout, 7 (a), 7 (b), 3)
+                        lo = (kx + 3) * 3
+                        cp[:, ky + 3:ky + 10, lo:lo + 21] += blk.reshape(co, 7, 21)        # dy + 6 = ky + a + 6
+                mats.append(-cp.reshape(co, 13 * 64))
+            self.w["init_ring_" + side] = torch.cat(mats, dim=0).to(BF16).contiguous()      # (3 phases * Cout, 13*64)
+        # ---- the four 3x3 corner blocks of the ring are inside a row side AND a column side: added back once.  Output pixel
+        # (py, px) of the corner's 3x3 block, image values (r, s, c) of the same block: r = py + ky + a, s = px + kx + b.
+        tab = torch.zeros(4, 9, 28, co, dtype=torch.float64, device=w2.device)
+        for cn, (vs, hs) in enumerate((("top", "left"), ("top", "right"), ("bottom", "left"), ("bottom", "right"))):
+            for py in range(3):
+                for px in range(3):
+                    for ky in outside(vs, py):
+                        for kx in outside(hs, px):
+                            w2t = w2[:, :, ky + 3, kx + 3]
+                            tab[cn, py * 3 + px, 27] += w2t @ b1
+                            for r in range(3):
+                                for sc in range(3):
+                                    a, b = r - py - ky, sc - px - kx
+                                    if -3 <= a <= 3 and -3 <= b <= 3:
+                                        k0 = (r * 3 + sc) * 3
+                                        tab[cn, py * 3 + px, k0:k0 + 3] += (w2t @ w1[:, :, a + 3, b + 3]).t()
+        self.f32["init_ring_corners"] = tab.float().contiguous()
 
 
 class UnetRunner:
@@ -593,9 +605,10 @@ class UnetRunner:
         outside the image.  The first term is ONE 13x13 convolution of the 3-channel flow (w12 = w2 * w1, K = 13 * 64 after
         an x-direction im2col, plus the constant w2 . b1); the second only touches output pixels within 3 of the border
         and only the kernel rows / columns that reach outside.  The ring values are linear in x (init_noise_conv is
-        folded into the correction weights): rows above / below the image become one 3-phase GEMM each over the first /
-        last three rows of the x-im2col tensor (K = 192), columns left / right a 21-tap GEMM each over strips of the ring
-        positions' im2col rows (a tap that leaves the strip reads zeros, which is the partition of the ring)."""
+        folded into the correction weights), and summed over ALL ring positions of a side the correction of an output row
+        / column is position independent: one 3-phase GEMM per side over the same x-im2col tensor (rows above / below:
+        K = 192; columns left / right: K = 832), then the four 3x3 corner blocks, which two sides both contain, are
+        added back by a small kernel (36 pixels per frame)."""
         cfg, pk, B, H, W = self.cfg, self.pk, self.B, self.H, self.W
         T, tc, tp = cfg.T, cfg.tc, cfg.tp
         d = cfg.dim
@@ -608,25 +621,21 @@ class UnetRunner:
         # ---- ring correction: im2col rows (147 patch values + a constant 1) of the four strips; init_noise_conv is folded
         # into the correction weights, so the intermediate's ring values are never materialised
         ostr = (d, W * d, hw * d, T * hw * d)
-        # rows above / below: three phases (output rows) over the image's first / last three rows of the x-im2col tensor
-        for name, y0 in (("top", 0), ("bottom", H - 3)):
-            ops.gemm(rec, a0=xc, c0=64, dims=(W, H, T, B), strides0=(64, W * 64, hw * 64, T * hw * 64),
-                     box=(32, 1, 4, 1), start=(0, y0, tc, 0), count=(W, 1, tp, B), taps=[(0, 0, 0), (0, 1, 0), (0, 2, 0)],
-                     w=pk.w["init_ring_" + name], n=d, out=x0, out_stride=ostr, res=x0, res_stride=ostr,
-                     phases=[([(0, 0, 0), (0, 1, 0), (0, 2, 0)], pr * W * d) for pr in range(3)])
-        # columns left / right of the image (rows inside it): strips of im2col rows, 21 taps each
-        _, n_lr = ops.ring_rows(B, tp, H, W)
-        ring = self.buf(2 * n_lr, 192)
-        ops.im2col7_ring(rec, self.x, ring, with_top_bottom=False)
-        strips = {
-            "left": (ring[:n_lr], (3, H), (4, 32), (3, H), 0),
-            "right": (ring[n_lr:], (3, H), (4, 32), (3, H), (W - 3) * d),
-        }
-        for name, (a, (d1, d2), (b1_, b2_), (c1, c2), off) in strips.items():
-            ops.gemm(rec, a0=a, c0=192, dims=(d1, d2, tp, B), strides0=(192, d1 * 192, d2 * d1 * 192, tp * d2 * d1 * 192),
-                     box=(b1_, b2_, 1, 1), start=(0, 0, 0, 0), count=(c1, c2, tp, B), taps=PackedUnet.RING_TAPS[name],
-                     w=pk.w["init_ring_" + name], n=d, out=x0, out_stride=ostr, out_base=rbase + off,
-                     res=x0, res_base=rbase + off, res_stride=ostr)
+        xstr = (64, W * 64, hw * 64, T * hw * 64)
+        # rows above / below: three phases (output rows) over the image's first / last three rows
+        for side, y0 in (("top", 0), ("bottom", H - 3)):
+            taps = [(0, 0, 0), (0, 1, 0), (0, 2, 0)]
+            ops.gemm(rec, a0=xc, c0=64, dims=(W, H, T, B), strides0=xstr, box=(32, 1, 4, 1), start=(0, y0, tc, 0),
+                     count=(W, 1, tp, B), taps=taps, w=pk.w["init_ring_" + side], n=d, out=x0, out_stride=ostr, res=x0,
+                     res_stride=ostr, phases=[(taps, pr * W * d) for pr in range(3)])
+        # columns left / right: three phases (output columns), the 13 row offsets as taps, read at the output column
+        for side, x_0 in (("left", 0), ("right", W - 3)):
+            ops.gemm(rec, a0=xc, c0=64, dims=(W, H, T, B), strides0=xstr, box=(1, 32, 4, 1), start=(x_0, 0, tc, 0),
+                     count=(1, H, tp, B), taps=[(0, dy, 0) for dy in range(-6, 7)], w=pk.w["init_ring_" + side], n=d,
+                     out=x0, out_stride=ostr, res=x0, res_stride=ostr,
+                     phases=[([(pr, dy, 0) for dy in range(-6, 7)], pr * d) for pr in range(3)])
+        # the corner blocks of the ring were subtracted twice
+        ops.init_corner_fix(rec, self.x, pk.f32["init_ring_corners"], x0, tc)
 
     def _im2col_gemm(self, rec, a, w, n, out, t0, nt, bias=None, res=None):
         """rows of `a` are (b, t, p) for t in [0, nt); write to frames [t0, t0+nt) of out (B, T, H, W, n')."""

@@ -153,16 +153,19 @@ int extdm_im2col7_flow(const float* cond, const float* x, void* a, int B, int tc
 
 /* Gather kernels of the composite init_conv: init_conv(init_noise_conv(x)) (..._traj_ada.py:916,1032-1042) is one 13x13
  * convolution of the 3-channel flow minus a 7x7 convolution of the intermediate's values on the 3-pixel ring outside the
- * image (the intermediate is zero padded, so the composition holds only away from the border).
+ * image (the intermediate is zero padded, so the composition holds only away from the border); the ring correction is a
+ * set of phase GEMMs over the same x-im2col tensor (extdm_b200/unet.py: _composite_init).
  * im2col13x_flow: out[b, t_off + t, y, x, (dx + 6)*3 + c] = x[b, c, t, y, x + dx], dx in [-6, 6] (zeros outside the image and
  * in channels 40..63, channel 39 = 1: the carrier of constants); x (B, 3, tp, H, W) fp32, out (B, T, H, W, 64) bf16 -- the 13
  * kernel rows are taps of the GEMM.
- * im2col7_ring: 7x7 im2col rows (K = 147 -> 192, layout of im2col7_flow; column 147 = 1, the carrier of
- * init_noise_conv's bias) of the ring positions, strip by strip: top
- * (B, tp, 3, W+6) y = -3..-1, bottom y = H..H+2, left (B, tp, H, 3) x = -3..-1, right x = W..W+2;
- * a: (2*B*tp*3*(W+6) + 2*B*tp*H*3, 192) bf16; with_top_bottom = 0: the left and right strips only. */
+ * init_corner_fix: the ring correction is summed side by side over all positions of each side, which counts the four
+ * 3x3 corner blocks of the ring twice; their contribution (linear in the image's 3x3x3 corner values + a constant) is added
+ * back to the 3x3 output pixels next to each corner.  table: (4 corners [top-left, top-right, bottom-left, bottom-right],
+ * 9 pixels, 28, C) fp32, k = (r*3 + s)*3 + c of the corner block's image values, k = 27 the constant; x0 (B, T, H, W, C)
+ * bf16, updated in place on frames [t_off, t_off + tp). */
 int extdm_im2col13x_flow(const float* x, void* out, int B, int tp, int T, int t_off, int H, int W, void* stream);
-int extdm_im2col7_ring(const float* x, void* a, int B, int tp, int H, int W, int with_top_bottom, void* stream);
+int extdm_init_corner_fix(const float* x, const float* table, void* x0, int B, int tp, int T, int t_off, int H, int W,
+                          int C, void* stream);
 
 /* Bilinear resize (align_corners=False) of channels-last frames: F.interpolate in ..._traj_ada.py:1039-1041. */
 int extdm_bilinear_resize_cl(const void* x, void* y, long long F, int h, int w, int H, int W, int C, void* stream);
