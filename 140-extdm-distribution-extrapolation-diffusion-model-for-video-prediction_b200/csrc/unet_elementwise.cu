@@ -461,8 +461,8 @@ __global__ void __launch_bounds__(256) im2col13x_kernel(const float* __restrict_
 //     the ring are then counted twice.  Their contribution only reaches the 3x3 output pixels next to each corner and
 //     is linear in the 3x3x3 image values there (+ a constant): table[corner][pixel][k][co], k = (r*3 + s)*3 + c for
 //     the image value (row y0 + r, column x0 + s, channel c) of the corner block, k = 27 the constant.  One block
-//     handles kCornerFrames frames (a thread's 28 weights per output are loaded once and reused for every frame).
-constexpr int kCornerFrames = 8;
+//     handles kCornerFrames frames (a thread's weights are loaded once and reused for every frame).
+constexpr int kCornerFrames = 2;
 __global__ void __launch_bounds__(256) init_corner_fix_kernel(const float* __restrict__ xin, const float* __restrict__ table,
                                                               __nv_bfloat16* __restrict__ x0, int B, int tp, int T,
                                                               int t_off, int H, int W, int C) {
@@ -485,21 +485,39 @@ __global__ void __launch_bounds__(256) init_corner_fix_kernel(const float* __res
     s_p[fi][cn][k] = v;
   }
   __syncthreads();
-  for (int o = threadIdx.x; o < 4 * 9 * C; o += blockDim.x) {        // output = (corner, pixel, channel), channel fastest
-    const int co = o % C, px = (o / C) % 9, cn = o / (9 * C);
-    float w[28];
-#pragma unroll
-    for (int k = 0; k < 28; ++k) w[k] = __ldg(table + ((static_cast<long long>(cn) * 9 + px) * 28 + k) * C + co);
+  // thread = two adjacent channels of one (corner, pixel): 4-byte read-modify-writes, all loads of a pass in flight at once
+  const int pairs = 4 * 9 * (C / 2);
+  for (int o = blockIdx.y * blockDim.x + threadIdx.x; o < pairs; o += gridDim.y * blockDim.x) {
+    const int co = (o % (C / 2)) * 2, px = (o / (C / 2)) % 9, cn = o / (9 * (C / 2));
     const int yy = ((cn >> 1) ? H - 3 : 0) + px / 3, xx = ((cn & 1) ? W - 3 : 0) + px % 3;
-    for (int fi = 0; fi < kCornerFrames; ++fi) {
-      const int f = f0 + fi;
-      if (f >= nf) break;
-      float acc = 0.f;
+    uint32_t* dst[kCornerFrames];
+    uint32_t old[kCornerFrames];
 #pragma unroll
-      for (int k = 0; k < 28; ++k) acc += w[k] * s_p[fi][cn][k];
+    for (int fi = 0; fi < kCornerFrames; ++fi) {
+      const int f = min(f0 + fi, nf - 1);
       const int t = f % tp, b = f / tp;
-      __nv_bfloat16* dst = x0 + (((static_cast<long long>(b) * T + t_off + t) * H + yy) * W + xx) * C + co;
-      *dst = __float2bfloat16(__bfloat162float(*dst) + acc);
+      dst[fi] = reinterpret_cast<uint32_t*>(x0 + (((static_cast<long long>(b) * T + t_off + t) * H + yy) * W + xx) * C + co);
+      old[fi] = *dst[fi];
+    }
+    float a0[kCornerFrames], a1[kCornerFrames];
+#pragma unroll
+    for (int fi = 0; fi < kCornerFrames; ++fi) { a0[fi] = 0.f; a1[fi] = 0.f; }
+    const float2* wp = reinterpret_cast<const float2*>(table + (static_cast<long long>(cn) * 9 + px) * 28 * C + co);
+#pragma unroll 4
+    for (int k = 0; k < 28; ++k) {
+      const float2 w = __ldg(wp + k * (C / 2));
+#pragma unroll
+      for (int fi = 0; fi < kCornerFrames; ++fi) {
+        a0[fi] += w.x * s_p[fi][cn][k];
+        a1[fi] += w.y * s_p[fi][cn][k];
+      }
+    }
+#pragma unroll
+    for (int fi = 0; fi < kCornerFrames; ++fi) {
+      if (f0 + fi < nf) {
+        const float2 v = unpack_bf16(old[fi]);
+        *dst[fi] = pack_bf16(v.x + a0[fi], v.y + a1[fi]);
+      }
     }
   }
 }
@@ -1012,11 +1030,11 @@ extern "C" int extdm_im2col13x_flow(const float* x, void* out, int B, int tp, in
 
 extern "C" int extdm_init_corner_fix(const float* x, const float* table, void* x0, int B, int tp, int T, int t_off, int H,
                                      int W, int C, void* stream) {
-  if (!x || !table || !x0 || B < 1 || tp < 1 || t_off < 0 || t_off + tp > T || H < 6 || W < 6 || C < 1)
+  if (!x || !table || !x0 || B < 1 || tp < 1 || t_off < 0 || t_off + tp > T || H < 6 || W < 6 || C < 2 || C % 2)
     return bad_arg("init_corner_fix: bad arguments");
   const int frames = B * tp;
-  init_corner_fix_kernel<<<(frames + kCornerFrames - 1) / kCornerFrames, 256, 0, STREAM>>>(x, table, BFW(x0), B, tp, T,
-                                                                                          t_off, H, W, C);
+  dim3 grid((frames + kCornerFrames - 1) / kCornerFrames, (4 * 9 * (C / 2) + 255) / 256);
+  init_corner_fix_kernel<<<grid, 256, 0, STREAM>>>(x, table, BFW(x0), B, tp, T, t_off, H, W, C);
   EXTDM_CHECK_LAUNCH();
   return EXTDM_OK;
 }
