@@ -15,7 +15,7 @@ import math
 import torch
 from torch import nn
 
-from . import ops
+from . import composite, ops
 from .manifest import UNET_ARCHITECTURES, UnetConfig, is_int_key, unet_manifest
 from .paramtree import ParamTree
 from .weights import synth_state_dict
@@ -114,78 +114,15 @@ class PackedUnet:
 
 
     def _pack_composite_init(self, w2):
-        """init_conv's weights over the init_noise_conv channels, w2 (Cout, 256, 7, 7), composed with init_noise_conv
-        (256, 3, 7, 7) into one 13x13 kernel over the 3 flow channels (..._traj_ada.py:916,1032-1042: two linear
-        convolutions in a row), plus the negated 7x7 sub-kernels of the ring correction -- see UnetRunner._composite_init."""
-        w1 = self.f32["init_noise_conv.weight"][:, :, 0].double()            # (256, 3, 7, 7)  [m, c, ky, kx]
-        b1 = self.f32["init_noise_conv.bias"].double()
-        w2 = w2.double()                                                       # (Cout, 256, 7, 7)
+        """Weight blocks of the composite init_conv (composite.compose: the 13x13 kernel w2 * w1 over the flow, the four
+        ring sides as GEMM phases, the corner table), cast to the kernels' dtypes / layouts -- UnetRunner._composite_init."""
+        c = composite.compose(self.f32["init_noise_conv.weight"][:, :, 0], self.f32["init_noise_conv.bias"], w2)
         co = w2.shape[0]
-        w12 = torch.zeros(co, 3, 13, 13, dtype=torch.float64, device=w2.device)
-        for a in range(7):                                                     # out(p) = sum_a w2[a] xn(p + a), xn(q) = sum_a' w1[a'] x(q + a')
-            for b in range(7):
-                w12[:, :, a:a + 7, b:b + 7] += torch.einsum("om,mcij->ocij", w2[:, :, a, b], w1)
-        wc = torch.zeros(co, 13, 64, dtype=torch.float64, device=w2.device)    # K index = (dy + 6)*64 + (dx + 6)*3 + c
-        wc[:, :, :39] = w12.permute(0, 2, 3, 1).reshape(co, 13, 39)
-        self.w["init_comp"] = wc.reshape(co, 13 * 64).to(BF16).contiguous()
-        self.f32["init_comp.bias"] = torch.einsum("omab,m->o", w2, b1).float().contiguous()
-        # ---- ring correction.  The intermediate on the ring is b1 + w1 . (7x7 patch of x), so every piece is linear in x;
-        # the x-direction im2col (channel (dx + 6)*3 + c = x at column offset dx, channel 39 = 1) is the A tensor of all four
-        # sides.  A side sums over ALL ring positions of that side, which makes it position independent:
-        #   rows above / below: output row p (counted from row 0 / H - 3), kernel rows ky that reach outside, source row
-        #     s = p + ky + a in {0, 1, 2} (three taps), K index = s*64 + (dx + 6)*3 + c;
-        #   columns left / right: output column p (counted from column 0 / W - 3), kernel columns kx that reach outside,
-        #     all 13 row offsets dy = ky + a as taps, read at the output column itself: K index = (dy + 6)*64 + (dx + 6)*3 + c.
-        # One GEMM phase per output row / column; weights negated (the correction is subtracted).
-        def outside(side, pr):                 # kernel rows / columns of init_conv that reach outside for output row / col pr
-            return range(-3, -pr) if side in ("top", "left") else range(3 - pr, 4)
-
-        for side in ("top", "bottom"):
-            mats = []
-            for pr in range(3):
-                cp = torch.zeros(co, 3, 64, dtype=torch.float64, device=w2.device)
-                for ky in outside(side, pr):
-                    for kx in range(-3, 4):
-                        w2t = w2[:, :, ky + 3, kx + 3]                                     # (Cout, 256)
-                        cp[:, 0, 39] += w2t @ b1                                           # constant carrier (a pixel of row 0 / H-3)
-                        for sr in range(3):
-                            a = sr - pr - ky                                               # kernel row of init_noise_conv
-                            if -3 <= a <= 3:
-                                blk = torch.einsum("om,mcb->obc", w2t, w1[:, :, a + 3, :])  # (Cout, 7 (b), 3 (c))
-                                lo = (kx + 3) * 3                                          # dx + 6 = kx + b + 6, b = -3 .. 3
-                                cp[:, sr, lo:lo + 21] += blk.reshape(co, 21)
-                mats.append(-cp.reshape(co, 192))
-            self.w["init_ring_" + side] = torch.cat(mats, dim=0).to(BF16).contiguous()      # (3 phases * Cout, 3*64)
-        for side in ("left", "right"):
-            mats = []
-            for pr in range(3):
-                cp = torch.zeros(co, 13, 64, dtype=torch.float64, device=w2.device)
-                for kx in outside(side, pr):
-                    for ky in range(-3, 4):
-                        w2t = w2[:, :, ky + 3, kx + 3]
-                        cp[:, 6, 39] += w2t @ b1                                           # constant: tap dy = 0
-                        blk = torch.einsum("om,mcab->oabc", w2t, w1)                       # (Cout, 7 (a), 7 (b), 3)
-                        lo = (kx + 3) * 3
-                        cp[:, ky + 3:ky + 10, lo:lo + 21] += blk.reshape(co, 7, 21)        # dy + 6 = ky + a + 6
-                mats.append(-cp.reshape(co, 13 * 64))
-            self.w["init_ring_" + side] = torch.cat(mats, dim=0).to(BF16).contiguous()      # (3 phases * Cout, 13*64)
-        # ---- the four 3x3 corner blocks of the ring are inside a row side AND a column side: added back once.  Output pixel
-        # (py, px) of the corner's 3x3 block, image values (r, s, c) of the same block: r = py + ky + a, s = px + kx + b.
-        tab = torch.zeros(4, 9, 28, co, dtype=torch.float64, device=w2.device)
-        for cn, (vs, hs) in enumerate((("top", "left"), ("top", "right"), ("bottom", "left"), ("bottom", "right"))):
-            for py in range(3):
-                for px in range(3):
-                    for ky in outside(vs, py):
-                        for kx in outside(hs, px):
-                            w2t = w2[:, :, ky + 3, kx + 3]
-                            tab[cn, py * 3 + px, 27] += w2t @ b1
-                            for r in range(3):
-                                for sc in range(3):
-                                    a, b = r - py - ky, sc - px - kx
-                                    if -3 <= a <= 3 and -3 <= b <= 3:
-                                        k0 = (r * 3 + sc) * 3
-                                        tab[cn, py * 3 + px, k0:k0 + 3] += (w2t @ w1[:, :, a + 3, b + 3]).t()
-        self.f32["init_ring_corners"] = tab.float().contiguous()
+        self.w["init_comp"] = c["comp"].reshape(co, 13 * 64).to(BF16).contiguous()
+        self.f32["init_comp.bias"] = c["comp_bias"].float().contiguous()
+        for side in ("top", "bottom", "left", "right"):            # phases stacked along the rows: (3 * Cout, taps * 64)
+            self.w["init_ring_" + side] = c[side].reshape(3 * co, -1).to(BF16).contiguous()
+        self.f32["init_ring_corners"] = c["corners"].float().contiguous()
 
 
 class UnetRunner:

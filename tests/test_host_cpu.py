@@ -215,3 +215,45 @@ def test_wrapper_registry():
     assert UNET_ARCHITECTURES["DenoiseNet_STWAtt_w_w_ref_adaptor_cross_multi_traj_ada_u22"] == "u22"
     c = UnetConfig("u22", 2, 5)
     assert (c.window, c.dim_head, c.channels, c.resample_slot, c.extrap_kt) == ((4, 4, 4), 32, 259, 6, 3)
+
+
+def test_composite_init_conv_algebra():
+    """extdm_b200/composite.py: init_conv(init_noise_conv(x)) = 13x13 convolution of x - ring correction (four position-
+    independent sides + corner add-back), emulated with torch in float64 exactly as the runner's GEMMs and corner kernel
+    read the blocks, against the two-stage zero-padded convolution (..._traj_ada.py:916,1032-1042).  Exact algebra: 1e-10."""
+    import torch.nn.functional as F
+    from extdm_b200 import composite
+    g = torch.Generator().manual_seed(5)
+    M, co, H, W = 12, 5, 11, 9
+    w1 = torch.randn(M, 3, 7, 7, generator=g, dtype=torch.float64)
+    b1 = torch.randn(M, generator=g, dtype=torch.float64)
+    w2 = torch.randn(co, M, 7, 7, generator=g, dtype=torch.float64)
+    x = torch.randn(1, 3, H, W, generator=g, dtype=torch.float64)
+    want = F.conv2d(F.conv2d(x, w1, b1, padding=3), w2, None, padding=3)[0].permute(1, 2, 0)       # (H, W, co)
+    c = composite.compose(w1, b1, w2)
+    # x-direction im2col with the constant channel, zero rows / columns outside the image
+    xc = torch.zeros(H, W, 64, dtype=torch.float64)
+    for dx in range(-6, 7):
+        for ch in range(3):
+            lo, hi = max(0, -dx), min(W, W - dx)
+            xc[:, lo:hi, (dx + 6) * 3 + ch] = x[0, ch, :, lo + dx:hi + dx]
+    xc[:, :, 39] = 1.0
+    row = lambda y, xx: xc[y, xx] if 0 <= y < H and 0 <= xx < W else torch.zeros(64, dtype=torch.float64)
+    got = torch.zeros(H, W, co, dtype=torch.float64)
+    for y in range(H):
+        for xx in range(W):
+            got[y, xx] = c["comp_bias"] + sum(c["comp"][:, dy + 6] @ row(y + dy, xx) for dy in range(-6, 7))
+    for pr in range(3):
+        for xx in range(W):
+            got[pr, xx] += sum(c["top"][pr][:, sr] @ row(sr, xx) for sr in range(3))
+            got[H - 3 + pr, xx] += sum(c["bottom"][pr][:, sr] @ row(H - 3 + sr, xx) for sr in range(3))
+        for y in range(H):
+            got[y, pr] += sum(c["left"][pr][:, dy + 6] @ row(y + dy, pr) for dy in range(-6, 7))
+            got[y, W - 3 + pr] += sum(c["right"][pr][:, dy + 6] @ row(y + dy, W - 3 + pr) for dy in range(-6, 7))
+    for cn, (y0, x0) in enumerate(((0, 0), (0, W - 3), (H - 3, 0), (H - 3, W - 3))):
+        patch = torch.cat([x[0, :, y0:y0 + 3, x0:x0 + 3].permute(1, 2, 0).reshape(27), torch.ones(1, dtype=torch.float64)])
+        for py in range(3):
+            for px in range(3):
+                got[y0 + py, x0 + px] += patch @ c["corners"][cn, py * 3 + px]
+    err = (got - want).abs().max().item()
+    assert err <= 1e-10 * want.abs().max().item(), err
