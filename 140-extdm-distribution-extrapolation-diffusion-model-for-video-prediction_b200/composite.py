@@ -87,3 +87,51 @@ def compose(w1, b1, w2):
                                     tab[cn, py * 3 + px, k0:k0 + 3] += (w2t @ w1[:, :, a + 3, b + 3]).t()
     out["corners"] = tab
     return out
+
+
+def _bilinear2_taps(phase):
+    """B[k, u]: weight of low-resolution index i + (u - 2) in the x2 bilinear (align_corners=False) up-sampling at the
+    high-resolution position 2 i + phase + (k - 3), k = 0 .. 6 (ATen area_pixel_compute_source_index: s = (P + 0.5) / 2 - 0.5;
+    the border clamping equals replicate padding of the low-resolution row)."""
+    b = torch.zeros(7, 5, dtype=torch.float64)
+    for k in range(7):
+        e = phase + k - 3
+        j = e // 2
+        if e % 2 == 0:                       # s = i + j - 0.25
+            b[k, j - 1 + 2] += 0.25
+            b[k, j + 2] += 0.75
+        else:                                # s = i + j + 0.25
+            b[k, j + 2] += 0.75
+            b[k, j + 1 + 2] += 0.25
+    return b
+
+
+def compose_upsampled(w2):
+    """7x7 zero-padded convolution (weights w2 (Cout, M, 7, 7)) of a x2 bilinearly up-sampled tensor, evaluated on the
+    LOW-resolution tensor f (TrajWarp branch of the u12 UNet, ..._traj_u12.py:1017-1042: F.interpolate then init_conv):
+
+        w2 * pad0(up(f))  =  w2 * rep3(up(f))  -  w2 * (rep3(up(f)) outside the image)
+
+    The first term is a 5x5 convolution of the replicate-padded f per output phase (py, px) = output pixel parity
+    (49 -> 25 taps); outside the image rep3(up(f)) repeats the border rows / columns of up(f), so the correction of an output
+    row / column next to the border is a 7-tap 1-D convolution of that border row / column.
+
+        poly   (4, Cout, 5, 5, M)  out[2i + py, 2j + px] = sum_uv poly[py*2 + px][:, u, v] . fpad[i + u, j + v]   (fpad = rep2(f))
+        top    (3, Cout, 7, M)     out[p, x] += sum_kx top[p][:, kx + 3] . T[x + kx + 3],  T[x'] = up(f)[0, clamp(x' - 3)]  (negated)
+        bottom (3, Cout, 7, M)     out[H - 3 + p, x] += sum_kx bottom[p][:, kx + 3] . Bo[x + kx + 3],  Bo = last row likewise
+        left   (3, Cout, 7, M)     out[y, p] += sum_ky left[p][:, ky + 3] . L[y + ky]  (L[y] = up(f)[y, 0], zero outside 0 .. H-1)
+        right  (3, Cout, 7, M)     out[y, W - 3 + p] += sum_ky right[p][:, ky + 3] . R[y + ky]  (R[y] = up(f)[y, W - 1])
+    (the corner positions of the ring are in the top / bottom rows only: the columns stop at the image's rows)"""
+    w2 = w2.double()
+    co, m = w2.shape[:2]
+    poly = []
+    for py in range(2):
+        for px in range(2):
+            by, bx = _bilinear2_taps(py).to(w2.device), _bilinear2_taps(px).to(w2.device)
+            poly.append(torch.einsum("omyx,yu,xv->ouvm", w2, by, bx))
+    out = {"poly": torch.stack(poly)}
+    out["top"] = torch.stack([-w2[:, :, 0:3 - p, :].sum(2).permute(0, 2, 1) for p in range(3)])          # ky <= -1 - p
+    out["bottom"] = torch.stack([-w2[:, :, 6 - p:7, :].sum(2).permute(0, 2, 1) for p in range(3)])       # ky >= 3 - p
+    out["left"] = torch.stack([-w2[:, :, :, 0:3 - p].sum(3).permute(0, 2, 1) for p in range(3)])         # kx <= -1 - p
+    out["right"] = torch.stack([-w2[:, :, :, 6 - p:7].sum(3).permute(0, 2, 1) for p in range(3)])        # kx >= 3 - p
+    return out

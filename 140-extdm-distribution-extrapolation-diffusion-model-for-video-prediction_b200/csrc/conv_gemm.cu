@@ -972,7 +972,7 @@ extern "C" int extdm_conv_gemm(const ExtdmGemm* g, void* stream_) {
   }
 
   // ---- halo variant: a full k x k tap grid over tiles made of whole-width rows of a single frame
-  int kk = g->ntaps == 9 ? 3 : (g->ntaps == 49 ? 7 : 0);
+  int kk = g->ntaps == 9 ? 3 : (g->ntaps == 25 ? 5 : (g->ntaps == 49 ? 7 : 0));
   if (kk) {
     for (int t = 0; t < g->ntaps && kk; ++t)
       if (g->tap[t][0] != t % kk - kk / 2 || g->tap[t][1] != t / kk - kk / 2 || g->tap[t][2] != 0) kk = 0;

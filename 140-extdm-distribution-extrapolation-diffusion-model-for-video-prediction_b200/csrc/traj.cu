@@ -241,6 +241,61 @@ __global__ void __launch_bounds__(256) bilinear_resize_frames_kernel(const __nv_
   }
 }
 
+// Companion of the polyphase init_conv (extdm_b200/composite.py: compose_upsampled): the 7x7 convolution of the x2
+// bilinearly up-sampled TrajWarp features is evaluated on the low-resolution tensor, which needs (a) that tensor
+// replicate-padded by 2 (the up-sampling's border clamping) and (b) the border rows / columns of the up-sampled tensor
+// (what the zero padding of the convolution replaces outside the image is a repetition of them).
+// fp: (F, h + 4, w + 4, C) with the interior written; top / bottom: (F, W + 6, C) = up[0 | H-1, clamp(x' - 3)];
+// left / right: (F, H, C) = up[y, 0 | W-1].  One block per frame.
+__global__ void __launch_bounds__(256) upsample2_border_kernel(__nv_bfloat16* __restrict__ fp, __nv_bfloat16* __restrict__ top,
+                                                               __nv_bfloat16* __restrict__ bottom,
+                                                               __nv_bfloat16* __restrict__ left,
+                                                               __nv_bfloat16* __restrict__ right, int h, int w, int C) {
+  const int vecs = C / 8, hp = h + 4, wp = w + 4, H = 2 * h, W = 2 * w;
+  __nv_bfloat16* f = fp + static_cast<long long>(blockIdx.x) * hp * wp * C;
+  // (a) replicate padding: every cell outside the interior copies its clamped interior cell
+  for (int i = threadIdx.x; i < hp * wp * vecs; i += blockDim.x) {
+    const int vv = i % vecs, x = (i / vecs) % wp, y = i / (vecs * wp);
+    const int ys = min(max(y, 2), h + 1), xs = min(max(x, 2), w + 1);
+    if (ys != y || xs != x)
+      *reinterpret_cast<uint4*>(f + (static_cast<long long>(y) * wp + x) * C + vv * 8) =
+          *reinterpret_cast<const uint4*>(f + (static_cast<long long>(ys) * wp + xs) * C + vv * 8);
+  }
+  // (b) border rows / columns of the up-sampled tensor, with the arithmetic of bilinear_resize_frames_kernel
+  const int n_tb = W + 6;
+  for (int i = threadIdx.x; i < (2 * n_tb + 2 * H) * vecs; i += blockDim.x) {
+    const int vv = i % vecs;
+    int r = i / vecs;
+    __nv_bfloat16* dst;
+    int ya, yb, xa, xb;
+    float ly, lx;
+    if (r < 2 * n_tb) {                                        // a row: Y = 0 or H - 1, X = clamp(x' - 3)
+      const bool bot = r >= n_tb;
+      if (bot) r -= n_tb;
+      tj_bilinear_src(bot ? H - 1 : 0, 0.5f, h, ya, yb, ly);
+      tj_bilinear_src(min(max(r - 3, 0), W - 1), 0.5f, w, xa, xb, lx);
+      dst = (bot ? bottom : top) + (static_cast<long long>(blockIdx.x) * n_tb + r) * C;
+    } else {                                                   // a column: X = 0 or W - 1
+      r -= 2 * n_tb;
+      const bool rgt = r >= H;
+      if (rgt) r -= H;
+      tj_bilinear_src(r, 0.5f, h, ya, yb, ly);
+      tj_bilinear_src(rgt ? W - 1 : 0, 0.5f, w, xa, xb, lx);
+      dst = (rgt ? right : left) + (static_cast<long long>(blockIdx.x) * H + r) * C;
+    }
+    const __nv_bfloat16* src = f + vv * 8;                     // interior cell (y, x) sits at (y + 2, x + 2)
+    float a[8], b[8], c[8], d[8], o[8];
+    tj_load8(src + (static_cast<long long>(ya + 2) * wp + xa + 2) * C, a);
+    tj_load8(src + (static_cast<long long>(ya + 2) * wp + xb + 2) * C, b);
+    tj_load8(src + (static_cast<long long>(yb + 2) * wp + xa + 2) * C, c);
+    tj_load8(src + (static_cast<long long>(yb + 2) * wp + xb + 2) * C, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      o[j] = (1.f - ly) * ((1.f - lx) * a[j] + lx * b[j]) + ly * ((1.f - lx) * c[j] + lx * d[j]);
+    tj_store8(dst + vv * 8, o);
+  }
+}
+
 static inline int tj_grid(long long total, int threads) {
   long long gsz = (total + threads - 1) / threads;
   if (gsz < 1) gsz = 1;
@@ -299,6 +354,19 @@ extern "C" int extdm_bilinear_resize_frames_cl(const void* x, void* y, int group
   bilinear_resize_frames_kernel<<<tj_grid(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), groups, frames_per_group,
       x_group_stride, y_group_stride, h, w, H, W, C);
+  EXTDM_CHECK_LAUNCH();
+  return EXTDM_OK;
+}
+
+extern "C" int extdm_upsample2_border(void* fpad, void* top, void* bottom, void* left, void* right, long long F, int h, int w,
+                                      int C, void* stream) {
+  if (!fpad || !top || !bottom || !left || !right || F < 1 || h < 2 || w < 2 || C % 8) {
+    extdm_set_error("upsample2_border: bad arguments", __FILE__, __LINE__);
+    return EXTDM_ERR_ARG;
+  }
+  upsample2_border_kernel<<<static_cast<int>(F), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<__nv_bfloat16*>(fpad), reinterpret_cast<__nv_bfloat16*>(top), reinterpret_cast<__nv_bfloat16*>(bottom),
+      reinterpret_cast<__nv_bfloat16*>(left), reinterpret_cast<__nv_bfloat16*>(right), h, w, C);
   EXTDM_CHECK_LAUNCH();
   return EXTDM_OK;
 }

@@ -58,6 +58,7 @@ PROTOTYPES = {
     "extdm_im2col7_flow": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "extdm_im2col13x_flow": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "extdm_init_corner_fix": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "extdm_upsample2_border": [_P, _P, _P, _P, _P, _L, _I, _I, _I, _P],
     "extdm_bilinear_resize_cl": [_P, _P, _L, _I, _I, _I, _I, _I, _P],
     "extdm_time_mlp": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "extdm_head_project": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],

@@ -221,10 +221,11 @@ def linear_rows(rec, x, w, n, out, *, bias=None, res=None, res_fp32=False, act=0
 
 def conv_cl(rec, x, w, n, k, out, *, x2=None, bias=None, res=None, res_fp32=False, act=0, out_fp32=False,
             t_range=None, col_scale=None, col_shift=None, out_t_offset=0, res_t_offset=0, taps=None,
-            out_scale=1, out_phase=(0, 0), block_n=0, gn_partials=None, x2_t_offset=0, tf32=False):
+            out_scale=1, out_phase=(0, 0), block_n=0, gn_partials=None, x2_t_offset=0, tf32=False, out_pixel_offset=(0, 0)):
     """k x k 'same' convolution over channels-last x (B, T, H, W, C) [channel-concatenated with x2].
     out: (B, To, Ho, Wo, n') with n' >= n.  t_range=(t0, t1) restricts the frames computed; the output
-    frame index is t + out_t_offset.  out_scale/out_phase write a strided output (ConvTranspose phases)."""
+    frame index is t + out_t_offset.  out_scale/out_phase write a strided output (ConvTranspose phases);
+    out_pixel_offset (dy, dx) shifts the output pixel (writing the interior of a padded tensor)."""
     B, T, H, W, c0 = x.shape
     c1 = 0 if x2 is None else x2.shape[-1]
     bw, bh, bt = std_box(H, W)
@@ -232,7 +233,7 @@ def conv_cl(rec, x, w, n, k, out, *, x2=None, bias=None, res=None, res_fp32=Fals
     oB, oT, oH, oW, oC = out.shape
     s = out_scale
     ostr = (s * oC, s * oW * oC, oH * oW * oC, oT * oH * oW * oC)
-    obase = out_t_offset * oH * oW * oC + (out_phase[0] * oW + out_phase[1]) * oC
+    obase = out_t_offset * oH * oW * oC + ((out_phase[0] + out_pixel_offset[0]) * oW + out_phase[1] + out_pixel_offset[1]) * oC
     rstr, rbase = None, 0
     if res is not None:
         rB, rT, rH, rW, rC = res.shape
@@ -390,6 +391,14 @@ def init_corner_fix(rec, x, table, x0, t_off):
     B, _, tp, H, W = x.shape
     rec.emit("extdm_init_corner_fix", (_p(x), _p(table), _p(x0), B, tp, x0.shape[1], t_off, H, W, x0.shape[-1]),
              keep=(x, table, x0))
+
+
+def upsample2_border(rec, fpad, top, bottom, left, right):
+    """fpad (F.., h + 4, w + 4, C) with the interior written -> replicate-padded in place; border rows / columns of its x2
+    bilinear up-sampling into top / bottom (F.., 2w + 6, C) and left / right (F.., 2h, C)."""
+    hp, wp, Cc = fpad.shape[-3:]
+    rec.emit("extdm_upsample2_border", (_p(fpad), _p(top), _p(bottom), _p(left), _p(right), fpad.numel() // (hp * wp * Cc),
+                                        hp - 4, wp - 4, Cc), keep=(fpad, top, bottom, left, right))
 
 
 def bilinear_resize_cl(rec, x, y):

@@ -89,6 +89,13 @@ class PackedUnet:
             self.w["init_full"] = ops.pack_conv_weight(ic)
             self.w["init_fea"] = ops.pack_conv_weight(ic[:, 256:])
             self._pack_composite_init(ic[:, :256, 0])
+            # the cond_fea half acts on a x2 bilinearly up-sampled tensor: 5x5 polyphase kernels on the low-resolution
+            # tensor + 1-D border corrections (composite.compose_upsampled, UnetRunner._polyphase_fea)
+            c2 = composite.compose_upsampled(ic[:, 256:, 0])
+            co = ic.shape[0]
+            self.w["init_poly"] = [c2["poly"][i].reshape(co, 25 * 256).to(BF16).contiguous() for i in range(4)]
+            for side in ("top", "bottom", "left", "right"):
+                self.w["init_fea_" + side] = c2[side].reshape(3 * co, 7 * 256).to(BF16).contiguous()
         else:
             self.w["init_noise"] = pack7(self.f32["init_noise_conv.weight"])
             self.w["init_x"] = ops.pack_conv_weight(ic[:, :256])
@@ -140,6 +147,9 @@ class UnetRunner:
     # init_conv(init_noise_conv(x)) on the predicted frames as one composite 13x13 convolution of the 3-channel flow plus a
     # ring correction (_composite_init) instead of a 7x7 convolution over 256 channels (K = 12544) per DDIM step
     composite_init = True
+    # u12: the cond_fea half of init_conv (7x7 over the x2 up-sampled TrajWarp features) as 5x5 polyphase convolutions of the
+    # low-resolution features + 1-D border corrections (_polyphase_fea); needs composite_init
+    polyphase_fea = True
 
     def __init__(self, packed, B, H=32, W=32, fea_hw=16):
         cfg = packed.cfg
@@ -463,6 +473,15 @@ class UnetRunner:
         ops.cross_attention(st, qq.view(B, -1, 256), kk.view(B, -1, 256), vv.view(B, -1, 256), ao, 8)
         yo = self.buf(B, tp, fh, fh, 256)
         ops.linear_rows(st, ao, pk.w[ca + "linear_o.weight"], 256, yo, bias=pk.f32[ca + "linear_o.bias"], act=1)
+        if self.composite_init and self.polyphase_fea and H == 32 and W == 32:
+            fpad = torch.zeros(B, tp, fh + 4, fh + 4, 256, device=self.dev, dtype=BF16)
+            ops.conv_cl(st, cf, pk.w["init_traj.fuser.weight"], 256, 1, fpad, x2=yo, x2_t_offset=tc, t_range=(tc, T),
+                        out_t_offset=-tc, bias=pk.f32["init_traj.fuser.bias"], out_pixel_offset=(2, 2))
+            self._polyphase_fea(st, fpad, x0)
+            self._composite_init(st, x0, res=x0, res_fp32=False, bias=pk.f32["init_comp.bias"])
+            self.taps["init_conv"] = x0
+            self._build_body(x0)
+            return
         fpn = self.buf(B, tp, fh, fh, 256)
         ops.conv_cl(st, cf, pk.w["init_traj.fuser.weight"], 256, 1, fpn, x2=yo, x2_t_offset=tc, t_range=(tc, T),
                     out_t_offset=-tc, bias=pk.f32["init_traj.fuser.bias"])
@@ -533,6 +552,40 @@ class UnetRunner:
         ho = self._resblock(st, x, "occlusion_map.0", d, x2=x0, time=False)
         ops.head_project(st, hf, ho, pk.f32["final_conv.1.weight"], pk.f32["final_conv.1.bias"],
                          pk.f32["occlusion_map.1.weight"], pk.f32["occlusion_map.1.bias"], self.out, tm)
+
+    def _polyphase_fea(self, rec, fpad, x0):
+        """frames [tc, T) of x0 = init_conv's cond_fea half over up2(f) + bias, computed on the low-resolution f (interior
+        of fpad (B, tp, h + 4, w + 4, 256), ..._traj_u12.py:1039-1042): per output parity a 5x5 convolution of the
+        replicate-padded f (25 instead of 49 taps per output pixel), then the zero padding of the 7x7 window at the image
+        border: outside the image the replicate-extended up-sampled tensor repeats its border rows / columns, so each side
+        is a 3-phase GEMM of 7 taps over one row / column (composite.compose_upsampled)."""
+        cfg, pk, B, H, W = self.cfg, self.pk, self.B, self.H, self.W
+        T, tc, tp = cfg.T, cfg.tc, cfg.tp
+        d, hw = cfg.dim, H * W
+        hp, h = fpad.shape[2], fpad.shape[2] - 4
+        top, bottom = self.buf(B, tp, W + 6, 256), self.buf(B, tp, W + 6, 256)
+        left, right = self.buf(B, tp, H, 256), self.buf(B, tp, H, 256)
+        ops.upsample2_border(rec, fpad, top, bottom, left, right)
+        base = tc * hw * d
+        for py in range(2):
+            for px in range(2):
+                ops.gemm(rec, a0=fpad, c0=256, dims=(hp, hp, tp, B), strides0=(256, hp * 256, hp * hp * 256, tp * hp * hp * 256),
+                         box=(16, 8, 1, 1), start=(2, 2, 0, 0), count=(h, h, tp, B), taps=ops.conv_taps(5),
+                         w=pk.w["init_poly"][py * 2 + px], n=d, out=x0, out_stride=(2 * d, 2 * W * d, hw * d, T * hw * d),
+                         out_base=base - 4 * d - 4 * W * d + (py * W + px) * d, bias=pk.f32["init_conv.bias"])
+        ostr = (d, W * d, hw * d, T * hw * d)
+        for side, a, y0 in (("top", top, 0), ("bottom", bottom, H - 3)):
+            taps = [(kx + 3, 0, 0) for kx in range(-3, 4)]
+            ops.gemm(rec, a0=a, c0=256, dims=(W + 6, 1, tp, B), strides0=(256, (W + 6) * 256, (W + 6) * 256, tp * (W + 6) * 256),
+                     box=(32, 1, 4, 1), start=(0, 0, 0, 0), count=(W, 1, tp, B), taps=taps, w=pk.w["init_fea_" + side], n=d,
+                     out=x0, out_stride=ostr, out_base=base + y0 * W * d, res=x0, res_base=base + y0 * W * d, res_stride=ostr,
+                     phases=[(taps, pr * W * d) for pr in range(3)])
+        for side, a, x_0 in (("left", left, 0), ("right", right, W - 3)):
+            taps = [(0, ky, 0) for ky in range(-3, 4)]
+            ops.gemm(rec, a0=a, c0=256, dims=(1, H, tp, B), strides0=(256, 256, H * 256, tp * H * 256), box=(1, 32, 4, 1),
+                     start=(0, 0, 0, 0), count=(1, H, tp, B), taps=taps, w=pk.w["init_fea_" + side], n=d, out=x0,
+                     out_stride=ostr, out_base=base + x_0 * d, res=x0, res_base=base + x_0 * d, res_stride=ostr,
+                     phases=[(taps, pr * d) for pr in range(3)])
 
     def _composite_init(self, rec, x0, res, res_fp32, bias):
         """frames [tc, T) of x0 (B, T, H, W, d) (+)= init_conv_x(init_noise_conv(x)), exactly, without the 256-channel

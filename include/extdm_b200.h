@@ -167,6 +167,13 @@ int extdm_im2col13x_flow(const float* x, void* out, int B, int tp, int T, int t_
 int extdm_init_corner_fix(const float* x, const float* table, void* x0, int B, int tp, int T, int t_off, int H, int W,
                           int C, void* stream);
 
+/* Polyphase init_conv of the u12 UNet (..._traj_u12.py:1039-1042: F.interpolate x2 then init_conv): the 7x7 convolution of
+ * the up-sampled TrajWarp features is evaluated on the low-resolution tensor (5x5 taps per output parity).  fpad:
+ * (F, h + 4, w + 4, C) bf16 with the interior written -> replicate-padded in place; top / bottom: (F, 2w + 6, C) = row 0 / 2h - 1
+ * of the up-sampled tensor with columns clamped; left / right: (F, 2h, C) = its column 0 / 2w - 1. */
+int extdm_upsample2_border(void* fpad, void* top, void* bottom, void* left, void* right, long long F, int h, int w, int C,
+                           void* stream);
+
 /* Bilinear resize (align_corners=False) of channels-last frames: F.interpolate in ..._traj_ada.py:1039-1041. */
 int extdm_bilinear_resize_cl(const void* x, void* y, long long F, int h, int w, int H, int W, int C, void* stream);
 

@@ -257,3 +257,40 @@ def test_composite_init_conv_algebra():
                 got[y0 + py, x0 + px] += patch @ c["corners"][cn, py * 3 + px]
     err = (got - want).abs().max().item()
     assert err <= 1e-10 * want.abs().max().item(), err
+
+
+def test_composite_upsampled_conv_algebra():
+    """extdm_b200/composite.py::compose_upsampled: 7x7 zero-padded convolution of a x2 bilinearly up-sampled tensor as 5x5
+    polyphase convolutions of the replicate-padded low-resolution tensor minus four 1-D border corrections, emulated in
+    float64 as the runner's GEMMs read the blocks, against F.interpolate + F.conv2d (..._traj_u12.py:1039-1042)."""
+    import torch.nn.functional as F
+    from extdm_b200 import composite
+    g = torch.Generator().manual_seed(9)
+    M, co, h, w = 6, 4, 5, 7
+    H, W = 2 * h, 2 * w
+    w2 = torch.randn(co, M, 7, 7, generator=g, dtype=torch.float64)
+    f = torch.randn(1, M, h, w, generator=g, dtype=torch.float64)
+    up = F.interpolate(f, scale_factor=2, mode="bilinear", align_corners=False)
+    want = F.conv2d(up, w2, None, padding=3)[0].permute(1, 2, 0)                       # (H, W, co)
+    c = composite.compose_upsampled(w2)
+    fpad = F.pad(f, (2, 2, 2, 2), mode="replicate")[0].permute(1, 2, 0)                # (h + 4, w + 4, M)
+    u = up[0].permute(1, 2, 0)                                                         # (H, W, M)
+    got = torch.zeros(H, W, co, dtype=torch.float64)
+    for i in range(h):
+        for j in range(w):
+            for py in range(2):
+                for px in range(2):
+                    blk = c["poly"][py * 2 + px]
+                    got[2 * i + py, 2 * j + px] = sum(blk[:, a, b] @ fpad[i + a, j + b] for a in range(5) for b in range(5))
+    clampx = lambda xx: min(max(xx, 0), W - 1)
+    zero = torch.zeros(M, dtype=torch.float64)
+    col = lambda t, y: t[y] if 0 <= y < H else zero
+    for p in range(3):
+        for xx in range(W):
+            got[p, xx] += sum(c["top"][p][:, kx + 3] @ u[0, clampx(xx + kx)] for kx in range(-3, 4))
+            got[H - 3 + p, xx] += sum(c["bottom"][p][:, kx + 3] @ u[H - 1, clampx(xx + kx)] for kx in range(-3, 4))
+        for y in range(H):
+            got[y, p] += sum(c["left"][p][:, ky + 3] @ col(u[:, 0], y + ky) for ky in range(-3, 4))
+            got[y, W - 3 + p] += sum(c["right"][p][:, ky + 3] @ col(u[:, W - 1], y + ky) for ky in range(-3, 4))
+    err = (got - want).abs().max().item()
+    assert err <= 1e-10 * want.abs().max().item(), err

@@ -114,6 +114,7 @@ def test_composite_init_conv(name):
             r = u.runner(fx["B"], 32, 32, inp["cond_fea"].shape[-1])
             names = [n for _, _, n in r.step.steps]
             assert ("extdm_im2col13x_flow" in names) == flag
+            assert ("extdm_upsample2_border" in names) == (flag and fx["variant"] == "u12")      # polyphase cond_fea half
             got[flag] = (r.taps["init_conv"].float()[:, fx["tc"]:].clone(), out.float().clone())
         finally:
             UnetRunner.composite_init = True
